@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: images/s for ViT-B/32 LoRA encode_image over the MTA crop batch
+(N=64 crops + 1 centre view per image) -> MTA x3 -> LP++ head -> top-5, image-sharded over N GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the whole hot path over `--images-per-gpu` images x 65 views on every rank
+(weak scaling: per-GPU work is fixed).  Rank 0 prints ONE JSON line:
+
+  value      images/s, whole job, inputs resident in HBM (device pointers into jcb_pipeline)
+  e2e        the same through HotPath.evaluate_base with PINNED HOST images: host->device copies of
+             the view chunks and the device->host read of the top-5 are inside the timed region
+  roofline   the tcgen05 GEMM family (99 % of the FLOPs): algorithmic FLOPs / CUDA-event time of its
+             launches, recorded on the launch stream inside the timed region, vs the measured bf16 peak
+  cpu_baseline  the fp32 CPU oracle (a port: the reference needs Jittor, which is not installable) on a
+             bounded sample of the same workload, on this box's host cores
+
+`--impl reference` times that CPU oracle alone (rank 0 only), one image x 65 views per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (ViT-B/32 LoRA + MTA N=64 + LP++)"
+UNIT = "images/s"
+GFLOP_PER_VIEW = 8.8176          # 8.7255 dense GEMM + 0.0922 attention
+GEMM_GFLOP_PER_VIEW = 8.7255
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images-per-gpu", type=int, default=128, help="images per step on every rank")
+    ap.add_argument("--crops", type=int, default=64, help="N random crops per image (views = N + 1)")
+    ap.add_argument("--chunk-views", type=int, default=0, help="views per pass through the tower (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"tflops": float(p["bf16_tflops_sustained"]), "hbm": float(p["hbm_gbs"]), "source": "measured"}
+    except Exception:
+        return {"tflops": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons every 200 ms during the timed region (NVML; nvidia-smi as fallback)."""
+
+    BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, threading.Event(), [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                     "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = get(h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+                self.stop_flag.wait(0.2)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+def build_problem(jb, torch, dev, args, seed=0):
+    """Random-init ViT-B/32 + LoRA (r=4 on q,k,v; merged in fp32), three text banks, LP++ head."""
+    sd = jb.synth.make_vit_state_dict(seed=0)
+    model = jb.jclip.build_model(sd)
+    largs = types.SimpleNamespace(encoder="vision", position="all", params=["q", "k", "v"], r=4, alpha=1,
+                                  dropout_rate=0.25, backbone="ViT-B/32")
+    layers = jb.apply_lora(largs, model)
+    lora = jb.synth.make_lora(seed=7)
+    for i, layer in enumerate(layers):
+        for name, (A, B) in lora[i].items():
+            getattr(layer, name).w_lora_A.data = A
+            getattr(layer, name).w_lora_B.data = B
+    texts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
+    lp_np = jb.synth.make_head(2, texts[2].numpy())
+    return sd, model, lora, texts, lp_np
+
+
+def cpu_oracle_image(torch, sd, lora, texts, lp_t, imgs_np):
+    """One image (V views) through the fp32 CPU oracle: tower -> MTA x3 -> head -> top-5."""
+    from oracle import pipeline_image, vit_encode_image
+    f = vit_encode_image(sd, imgs_np, lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    return pipeline_image(f, f, texts[0], texts[1], texts[2], lp_t, score="cs5")[0]
+
+
+def run_reference(args):
+    """The reference arm: its algorithm on the host cores.  Jittor 1.3.8.5 cannot be installed offline,
+    so this is the oracle port (PyTorch CPU fp32, all host threads), one image x (N+1) views per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    import jclip_b200                  # synthetic inputs only: no native code is loaded on this arm
+    jb_synth = jclip_b200.synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    V = args.crops + 1
+    sd = jb_synth.make_vit_state_dict(seed=0)
+    lora = jb_synth.make_lora(seed=7)
+    texts = [torch.from_numpy(jb_synth.make_text_features(seed=10 + i)) for i in range(3)]
+    lp_t = tuple(torch.from_numpy(a) for a in jb_synth.make_head(2, texts[2].numpy()))
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    imgs = jb_synth.make_views(100, 1, V)[0]
+    for _ in range(args.warmup):
+        cpu_oracle_image(torch, sd_t, lora, texts, lp_t, imgs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_image(torch, sd_t, lora, texts, lp_t, imgs)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    sample = f"{args.steps} steps x 1 image x {V} views (224x224 fp32), full pipeline, oracle port on host cores"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"ViT-B/32 LoRA(r=4,qkv) encode_image x {V} views/image + MTA x3 + LP++ head, top-5 of 403",
+                   "views_per_image": V, "images_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import jclip_b200 as jb
+
+    rank, world, local = jb.dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    peaks = measured_peaks()
+    V = args.crops + 1
+    I = args.images_per_gpu
+    K, W = args.steps, max(args.warmup, 0)
+
+    sd, model, lora, texts, lp_np = build_problem(jb, torch, dev, args)
+    # the path's only collectives: rank 0's text embeddings / head weights to everyone (once) ...
+    bank_t = [t.to(dev) for t in texts]
+    lp_dev = [torch.from_numpy(a).to(dev) for a in lp_np]
+    jb.dist.broadcast_tensors(bank_t + lp_dev, src=0)
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = [t.cpu() for t in lp_dev]
+    bank = jb.TextBank(bank_t[0], bank_t[1], bank_t[2], dev)
+    hp = jb.HotPath(model, bank, lp, rank_by="cs5", k=5)
+    ctx = jb.get_context(dev)
+    if args.chunk_views:
+        ctx.set_chunk_views(args.chunk_views)
+
+    # this rank's shard of the step's images: I images x V views, generated on the device
+    images = jb.synth.make_views_torch(1000 + rank, I, V, dev)
+    n_total = I * world
+
+    def step_device():
+        topk = hp.evaluate_base(images, topk_to_host=False)
+        return jb.dist.all_gather_topk(topk, n_total)      # ... and the per-image top-5 to everyone
+
+    for _ in range(max(W, 1)):
+        out = step_device()
+    torch.cuda.synchronize()
+    assert out.shape == (n_total, 5)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    jb.dist.barrier()
+    torch.cuda.synchronize()
+    n0 = ctx.launch_count
+    ctx.profile_start()
+    ev0.record()
+    for _ in range(K):
+        step_device()
+    ev1.record()
+    torch.cuda.synchronize()
+    jb.dist.barrier()
+    prof = ctx.profile_stop()
+    launches = ctx.launch_count - n0
+    ms_total = jb.dist.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    ms_step = ms_total / K
+    value = n_total * K / (ms_total / 1e3)
+
+    # ---- end to end: pinned host images in, host top-5 out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host_images = torch.empty(images.shape, dtype=images.dtype, pin_memory=True)
+        host_images.copy_(images)
+        torch.cuda.synchronize()
+        for _ in range(max(W, 1)):
+            tk = hp.evaluate_base(host_images)
+        assert not tk.is_cuda and torch.equal(tk, out[rank * I:(rank + 1) * I].cpu())
+        jb.dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            tk = hp.evaluate_base(host_images)
+            jb.dist.all_gather_topk(tk.to(dev), n_total)
+        torch.cuda.synchronize()
+        dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
+               "h2d_bytes_per_step": int(images.numel() * images.element_size()), "d2h_bytes_per_step": int(I * 5 * 4)}
+        del host_images
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    clocks = sampler.summary()
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel family: the tcgen05 GEMM (patch / qkv / out / fc1 / fc2)
+    gemm = {k: v for k, v in prof.items() if k.startswith("gemm_")}
+    g_ms = sum(v["ms"] for v in gemm.values())
+    g_fl = sum(v["flops"] * (v["timed_launches"] / max(v["launches"], 1)) for v in gemm.values())
+    achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else None
+    per_kernel = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        frac_timed = v["timed_launches"] / max(v["launches"], 1)
+        ent = {"ms_per_step": v["ms"] / K / max(frac_timed, 1e-9), "launches_per_step": v["launches"] / K}
+        if v["flops"] and v["ms"]:
+            ent["tflops"] = v["flops"] * frac_timed / (v["ms"] / 1e3) / 1e12
+        if v["bytes"] and v["ms"]:
+            ent["gbs"] = v["bytes"] * frac_timed / (v["ms"] / 1e3) / 1e9
+        per_kernel[k] = ent
+    kernel_ms_step = sum(e["ms_per_step"] for e in per_kernel.values())
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all epilogues: patch, qkv, out_proj, fc1, fc2)",
+        "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained", "gemm_ms_per_step": g_ms / K,
+        "gemm_share_of_kernel_time": (g_ms / K) / kernel_ms_step if kernel_ms_step else None,
+        "whole_step_tflops": I * V * GFLOP_PER_VIEW / 1e3 / (ms_step / 1e3),
+        "whole_step_frac": I * V * GFLOP_PER_VIEW / 1e3 / (ms_step / 1e3) / peaks["tflops"],
+        "per_kernel": per_kernel,
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+        lp_t = tuple(torch.from_numpy(a) for a in lp_np)
+        imgs_np = images[:4].cpu().numpy()
+        t0 = time.perf_counter()
+        cpu_oracle_image(torch, sd_t, lora, texts, lp_t, imgs_np[0])       # warm-up (thread pools, allocator)
+        t_first = time.perf_counter() - t0
+        n_img = max(1, min(3, int(15.0 / max(t_first, 1e-3))))
+        t0 = time.perf_counter()
+        cpu_top = [cpu_oracle_image(torch, sd_t, lora, texts, lp_t, imgs_np[1 + j]) for j in range(n_img)]
+        dt = time.perf_counter() - t0
+        agree = sum(len(set(cpu_top[j].tolist()) & set(out[1 + j].cpu().tolist())) for j in range(n_img)) / (5 * n_img)
+        cpu_baseline = {"value": n_img / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n_img} of the step's images x {V} views through the fp32 oracle (PyTorch CPU; the "
+                                  f"reference's Jittor cannot be installed offline), after 1 warm-up image",
+                        "top5_agreement_with_gpu": agree}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": f"ViT-B/32 LoRA(r=4 on q,k,v, merged) encode_image over {I} images x {V} views (N={args.crops} crops + "
+                        f"centre) per GPU per step, fp32 224x224 inputs + fused CLIP normalisation, MTA x3, LP++ head, "
+                        f"top-5 of 403 classes",
+            "images_per_gpu_per_step": I, "views_per_image": V, "parallelism": f"image-sharded dp{world}",
+            "l2_policy": f"inputs larger than L2 ({images.numel() * images.element_size() / 2**20:.0f} MiB of views per step)",
+            "chunk_views": args.chunk_views or 2048, "gflop_per_view": GFLOP_PER_VIEW,
+        },
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    rc = main()
+    try:
+        import torch.distributed as _d
+        if _d.is_initialized():
+            _d.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
+    sys.exit(rc)

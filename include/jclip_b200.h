@@ -1,0 +1,248 @@
+/* jclip_b200.h -- C ABI of libjclip_b200.so: the B200-native (sm_100a) hot path of
+ * Dokumushikun/jittor-clip-fewshot behind plain pointers and sizes.
+ *
+ * The reference has no FFI / plugin boundary: it is 100 % Python on top of Jittor, and the seam of the
+ * hot path is a handful of Python callables.  Each entry point below names the reference callable it
+ * stands in for (paths relative to the reference checkout); INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add at each of those seams.
+ *
+ * Conventions
+ *   - every function returns 0 (JCB_OK) or a negative JCB_E_* code; it never throws or aborts.  The
+ *     message of the last failure on a context is returned by jcb_last_error().
+ *   - "dev" pointers are CUDA device pointers on the context's device; "host" pointers are ordinary
+ *     (preferably page-locked) host memory.  The caller allocates every output.
+ *   - device work is enqueued on the context's stream (jcb_ctx_set_stream; default: a private
+ *     non-blocking stream) and the call returns without waiting, except the *_host entry points and
+ *     jcb_sync, which block until their results are in host memory.
+ *   - a context and the objects created from it may be used by one host thread at a time.
+ *   - there is no CPU fallback: without a CUDA device of compute capability 10.0 context creation fails.
+ */
+#ifndef JCLIP_B200_H_
+#define JCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JCB_OK 0
+#define JCB_E_INVALID (-1)     /* bad argument / unsupported shape */
+#define JCB_E_CUDA (-2)        /* CUDA runtime or driver error */
+#define JCB_E_STATE (-3)       /* call order (e.g. encode before finalize) */
+#define JCB_E_NO_DEVICE (-4)   /* no sm_100 device */
+#define JCB_E_KERNEL (-5)      /* a kernel reported a device-side status (pipeline timeout) */
+#define JCB_E_NOMEM (-6)
+
+#define JCB_ABI_VERSION 1
+
+typedef struct jcb_ctx jcb_ctx;
+typedef struct jcb_vit jcb_vit;
+
+/* image element types accepted by the encoder */
+#define JCB_IMG_F32 0   /* float32, the reference's dtype (T.ToTensor -> float32) */
+#define JCB_IMG_BF16 1
+#define JCB_IMG_U8 2    /* uint8 0..255, scaled by 1/255 on the device */
+
+/* LoRA target projections (reference test.py:625-640 `enable_lora` items q, k, v, o) */
+#define JCB_PROJ_Q 0
+#define JCB_PROJ_K 1
+#define JCB_PROJ_V 2
+#define JCB_PROJ_O 3
+
+/* which fused score the head ranks by (reference test.py:1729-1736 names) */
+#define JCB_SCORE_LOGITS 0  /* LP++ logits after logit_normalize            test.py:1721-1722 */
+#define JCB_SCORE_CS 1      /* cosine_similarity   (hand text)              test.py:1729 */
+#define JCB_SCORE_CS1 2     /* cosine_similarity1  (prompt-tuned text)      test.py:1730  <- what test.py:1738 ranks */
+#define JCB_SCORE_CS2 3     /* (cs + cs1) / 2                               test.py:1733 */
+#define JCB_SCORE_CS3 4     /* cosine_similarity3  (zero-shot tower)        test.py:1731 */
+#define JCB_SCORE_CS4 5     /* (cs2 + cs3) / 2                              test.py:1734 */
+#define JCB_SCORE_CS5 6     /* cs4 + 0.5 * logits  (LP++ fusion)            test.py:1735  <- BASELINE config 4 */
+#define JCB_SCORE_COUNT 7
+
+int jcb_abi_version(void);
+
+/* ---------------------------------------------------------------- context ------------------- */
+/* One per process / GPU.  Replaces `jt.flags.use_cuda = 1` (reference test.py:25). */
+int jcb_ctx_create(int device, jcb_ctx** out);
+int jcb_ctx_destroy(jcb_ctx* ctx);
+/* Use the caller's CUDA stream (a cudaStream_t / CUstream cast to void*), e.g. torch's current stream. */
+int jcb_ctx_set_stream(jcb_ctx* ctx, void* cuda_stream);
+/* Views processed per pass through the tower (workspace = ~1.2 MB per view).  Default 2048. */
+int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
+/* Wait for the context's stream and report any device-side kernel status. */
+int jcb_sync(jcb_ctx* ctx);
+const char* jcb_last_error(const jcb_ctx* ctx);
+/* Device properties the host side reports next to measurements. */
+int jcb_ctx_info(const jcb_ctx* ctx, int* num_sms, int* cc_major, int* cc_minor, size_t* workspace_bytes);
+/* Number of kernels this library has launched on the context so far (bench.py's gpu_launches). */
+int64_t jcb_ctx_launch_count(const jcb_ctx* ctx);
+
+/* Per-kernel-class timing with CUDA events recorded on the launch stream around every launch of the
+ * library (what bench.py's roofline uses).  jcb_ctx_profile(ctx, 1) resets and starts; (ctx, 0) waits for
+ * the stream and folds the event pairs into per-class totals, read with jcb_ctx_profile_read:
+ *   total_ms over the `timed_launches` launches that got an event pair (at most 32768 per session),
+ *   `launches` seen, and the ALGORITHMIC flops / bytes of all `launches`. */
+#define JCB_KC_IM2COL 0
+#define JCB_KC_GEMM_PATCH 1
+#define JCB_KC_EMBED_LN 2
+#define JCB_KC_GEMM_QKV 3
+#define JCB_KC_ATTENTION 4
+#define JCB_KC_GEMM_OUT 5
+#define JCB_KC_LAYERNORM 6
+#define JCB_KC_GEMM_FC1 7
+#define JCB_KC_GEMM_FC2 8
+#define JCB_KC_TAIL 9
+#define JCB_KC_MTA 10
+#define JCB_KC_HEAD 11
+#define JCB_KC_OTHER 12
+#define JCB_KC_COUNT 13
+int jcb_ctx_profile(jcb_ctx* ctx, int enable);
+int jcb_ctx_profile_read(const jcb_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches,
+                         int64_t* timed_launches, double* flops, double* bytes);
+const char* jcb_kernel_class_name(int kernel_class);
+
+/* ---------------------------------------------------------------- image tower ---------------- */
+typedef struct jcb_vit_config {
+  int32_t layers;      /* 12   number of visual.*.attn.in_proj_weight keys   jclip/model.py:240-243 */
+  int32_t width;       /* 768  visual.conv1.weight.shape[0]                  jclip/model.py:238 */
+  int32_t patch;       /* 32   visual.conv1.weight.shape[-1]                 jclip/model.py:244 */
+  int32_t resolution;  /* 224  patch * sqrt(pos_emb rows - 1)                jclip/model.py:245-247 */
+  int32_t embed_dim;   /* 512  visual.proj.shape[1] */
+} jcb_vit_config;
+
+/* Stands in for `build_model(state_dict)` restricted to the image tower (jclip/model.py:235-285). */
+int jcb_vit_create(jcb_ctx* ctx, const jcb_vit_config* cfg, jcb_vit** out);
+int jcb_vit_destroy(jcb_vit* vit);
+/* Load one fp32 tensor of the CLIP state dict by its reference key name ("visual.conv1.weight",
+ * "visual.transformer.resblocks.3.attn.in_proj_weight", ...; jclip/model.py:235-285 / load_parameters).
+ * `data` is host memory with `numel` floats; it is copied.  Unknown keys return JCB_E_INVALID. */
+int jcb_vit_set_param(jcb_vit* vit, const char* name, const float* data, int64_t numel);
+/* Attach one LoRA adapter (reference LinearLoRA, test.py:340-398): A [r, width], B [width, r] host fp32,
+ * scaling = alpha / sqrt(r) (test.py:288-289).  Replaces any adapter already on (layer, proj). */
+int jcb_vit_set_lora(jcb_vit* vit, int layer, int proj, const float* A, const float* B, int r, float scaling);
+int jcb_vit_clear_lora(jcb_vit* vit);
+/* Pack the weights for the device: W' = W + scaling * B A in fp32, then bf16 (GEMM operands); LayerNorm /
+ * bias / embedding / final projection parameters stay fp32.  Must be called after the last set_param /
+ * set_lora and before jcb_encode_image; may be called again after the adapters change. */
+int jcb_vit_finalize(jcb_vit* vit);
+
+/* `CLIP.encode_image(image)` (jclip/model.py:199-200 -> VisionTransformer.execute :104-126).
+ *   images_dev   [n_views, 3, R, R] on the device, element type `img_dtype`
+ *   apply_clip_norm != 0 fuses `tfm_clip` = ImageNormalize(mean, std) (test.py:1301, applied at :1705)
+ *   normalize   != 0 fuses `f / f.norm(dim=-1, keepdim=True)` (test.py:1706)
+ *   out_dev      [n_views, embed_dim] float32 */
+int jcb_encode_image(jcb_vit* vit, const void* images_dev, int img_dtype, int64_t n_views, int apply_clip_norm,
+                     int normalize, float* out_dev);
+/* Same with host buffers: host->device copies of the image chunks (overlapped with compute on a second
+ * stream) and the device->host copy of the embeddings happen inside the call; it returns when out_host
+ * is valid.  This is the call the end-to-end measurement times. */
+int jcb_encode_image_host(jcb_vit* vit, const void* images_host, int img_dtype, int64_t n_views,
+                          int apply_clip_norm, int normalize, float* out_host);
+
+/* Final token tensor of the tower [n_views * tokens, width] fp32 before ln_post (tests / debugging). */
+int jcb_vit_debug_tokens(jcb_vit* vit, const void* images_dev, int img_dtype, int64_t n_views, int apply_clip_norm,
+                         float* tokens_out_dev);
+
+/* ---------------------------------------------------------------- MTA ------------------------ */
+typedef struct jcb_mta_params {
+  float lambda_y;     /* 0.2   test.py:1395 */
+  float lambda_q;     /* 4     test.py:1396 */
+  float th;           /* 1e-6  test.py:1421 */
+  float temperature;  /* 1     test.py:1398 */
+  double k_frac;      /* 0.3   test.py:1405 */
+  int32_t max_iter;   /* 5     test.py:1397 */
+  int32_t reserved;
+} jcb_mta_params;
+void jcb_mta_default_params(jcb_mta_params* p);
+
+/* `solve_mta(image_features, text_features)` batched over images (test.py:1391-1461; ood.py:751-820).
+ *   feats_dev    [n_images, n_views, dim] float32 unit rows, view 0 = un-augmented image
+ *   text_dev     [dim, n_classes] float32  (the orientation the reference passes: `text_features.t()`)
+ *   out_mode_dev [n_images, dim]            the mode, unit norm            (test.py:1461)
+ *   out_logits_dev [n_images, n_classes] or NULL: 100 * mode @ text         (ood.py:819)
+ *   params NULL = reference constants */
+int jcb_mta(jcb_ctx* ctx, const float* feats_dev, const float* text_dev, int64_t n_images, int32_t n_views,
+            int32_t n_classes, int32_t dim, const jcb_mta_params* params, float* out_mode_dev,
+            float* out_logits_dev);
+
+/* ---------------------------------------------------------------- head ----------------------- */
+typedef struct jcb_head_weights {   /* Channel_LP parameters, test.py:1223-1228, all device fp32 */
+  const float* scale1;  /* [dim] */
+  const float* bias1;   /* [dim] */
+  const float* fc_w;    /* [n_classes, dim] */
+  const float* fc_b;    /* [n_classes] */
+} jcb_head_weights;
+
+/* Per-image body of evaluate_base after the three solve_mta calls (test.py:1710-1738):
+ * Channel_LP x2 -> logit_normalize x3 -> cosine logits x3 -> fusion -> top-k of `rank_by`.
+ *   m_*_dev [n_images, dim] modes; T_*_dev [n_classes, dim] text features (un-transposed, unit rows)
+ *   out_topk_dev [n_images, k] int32 (k <= 8); out_scores_dev [n_images, n_classes] or NULL (the ranked
+ *   score); out_all_dev [n_images, JCB_SCORE_COUNT, n_classes] or NULL. */
+int jcb_head(jcb_ctx* ctx, const float* m_pt_dev, const float* m_hand_dev, const float* m_zs_dev,
+             const float* T_pt_dev, const float* T_hand_dev, const float* T_zs_dev, const jcb_head_weights* lp,
+             int64_t n_images, int32_t n_classes, int32_t dim, int32_t rank_by, int32_t k, int32_t* out_topk_dev,
+             float* out_scores_dev, float* out_all_dev);
+
+/* `scale * f @ T.t()` then topk (evaluate_new test.py:1770-1774; OOD argmax ood.py:875-877 with k = 1). */
+int jcb_cosine_topk(jcb_ctx* ctx, const float* feats_dev, const float* text_dev /* [n_classes, dim] */,
+                    int64_t n, int32_t n_classes, int32_t dim, float scale, int32_t k, int32_t* out_topk_dev,
+                    float* out_scores_dev);
+/* `Channel_LP.execute(features)` (test.py:1229-1234): out [n, n_classes]. */
+int jcb_channel_lp(jcb_ctx* ctx, const float* feats_dev, int64_t n, int32_t n_classes, int32_t dim,
+                   const jcb_head_weights* lp, float* out_dev);
+/* `logit_normalize(logit)` (test.py:1304-1308): global unbiased std, per-row mean. */
+int jcb_logit_normalize(jcb_ctx* ctx, const float* in_dev, int64_t n, int32_t n_classes, float* out_dev);
+
+/* ---------------------------------------------------------------- whole hot path ------------- */
+typedef struct jcb_pipeline_args {
+  /* inputs */
+  const void* images;       /* [n_images, n_views, 3, R, R]; device or host pointer (see images_on_host) */
+  int32_t img_dtype;
+  int32_t images_on_host;   /* 1: page-locked host memory, copied chunk by chunk inside the call */
+  int64_t n_images;
+  int32_t n_views;          /* V = N + 1 (reference test.py:1700) */
+  int32_t apply_clip_norm;
+  const float* text_pt_dev;     /* [n_classes, dim] prompt-tuned text features   (test.py:1684-1686) */
+  const float* text_hand_dev;   /* [n_classes, dim] hand-template text features  (test.py:1678) */
+  const float* text_zs_dev;     /* [n_classes, dim] zero-shot tower text features (test.py:1679) */
+  const float* text_pt_t_dev;   /* the same three, transposed [dim, n_classes] (what solve_mta receives) */
+  const float* text_hand_t_dev;
+  const float* text_zs_t_dev;
+  jcb_head_weights lp;
+  int32_t n_classes;
+  int32_t rank_by;
+  int32_t k;
+  int32_t topk_on_host;     /* 1: out_topk is host memory and the call blocks until it is valid */
+  /* outputs */
+  int32_t* out_topk;        /* [n_images, k] */
+  float* out_feats_dev;     /* optional [n_images * n_views, dim] unit view embeddings, or NULL */
+  float* out_scores_dev;    /* optional [n_images, n_classes], or NULL */
+} jcb_pipeline_args;
+
+/* encode_image over every view -> L2 normalise -> solve_mta x3 -> head -> top-k: the loop body of
+ * evaluate_base (test.py:1692-1742) for a batch of images, one image tower (`vit`) feeding all three
+ * MTA solves.  `vit_zs` may be NULL (single tower) or a second tower for the zero-shot branch
+ * (test.py:1711-1713). */
+int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* args);
+
+/* ---------------------------------------------------------------- building blocks (tests) ---- */
+/* C[M,N] = A[M,K] (bf16) * B[N,K]^T (bf16) with the fused epilogues of the tower; see csrc/kernels.h. */
+int jcb_gemm_bf16(jcb_ctx* ctx, const void* A_dev, const void* B_dev, int32_t M, int32_t N, int32_t K,
+                  const float* bias_dev, int32_t epilogue, void* out_dev, int64_t ldo);
+int jcb_layernorm_bf16(jcb_ctx* ctx, const float* x_dev, int64_t rows, int32_t width, const float* gamma_dev,
+                       const float* beta_dev, void* out_bf16_dev);
+int jcb_attention_bf16(jcb_ctx* ctx, const void* qkv_bf16_dev, int64_t n_views, int32_t tokens, int32_t heads,
+                       void* out_bf16_dev);
+
+/* ---------------------------------------------------------------- DLPack hand-off ------------ */
+/* Zero-copy variant of jcb_encode_image taking DLManagedTensor* (dlpack.h ABI v0.x).  Tensors are
+ * borrowed: the deleters are never called.  images: [n,3,R,R] f32/bf16/u8 on kDLCUDA; out: [n,E] f32. */
+int jcb_encode_image_dlpack(jcb_vit* vit, void* images_dlmanaged, void* out_dlmanaged, int apply_clip_norm,
+                            int normalize);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JCLIP_B200_H_ */

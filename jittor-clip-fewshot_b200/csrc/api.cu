@@ -1,0 +1,899 @@
+// C-ABI of libjclip_b200.so (include/jclip_b200.h): contexts, weight packing, the image-tower schedule
+// and the MTA / head entry points.  Everything here is host orchestration; the arithmetic lives in
+// gemm.cu, attention.cu, rowwise.cu, mta.cu and head.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/jclip_b200.h"
+#include "kernels.h"
+
+using namespace jcb;
+
+// ------------------------------------------------------------------------------------------------
+struct jcb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};
+  cudaEvent_t compute_done[2] = {nullptr, nullptr};
+  int num_sms = 0, cc_major = 0, cc_minor = 0;
+  int* dev_status = nullptr;
+  int64_t chunk_views = 2048;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  void* stage[2] = {nullptr, nullptr};  // device staging for host images
+  size_t stage_bytes = 0;
+  int64_t launches = 0;
+  char err[512] = {0};
+  // per-kernel-class CUDA-event profile (jcb_ctx_profile): event pairs recorded on the launch stream
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;           // 2 * PROF_PAIRS events, created on first use
+  std::vector<int> prof_cls;                  // class of each recorded pair
+  double prof_ms[JCB_KC_COUNT] = {0};
+  int64_t prof_n[JCB_KC_COUNT] = {0};         // launches seen (recorded or not)
+  int64_t prof_timed[JCB_KC_COUNT] = {0};     // launches with an event pair
+  double prof_flops[JCB_KC_COUNT] = {0};
+  double prof_bytes[JCB_KC_COUNT] = {0};
+};
+
+namespace {
+
+int fail(jcb_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return fail((ctx), _e == cudaErrorInvalidValue ? JCB_E_INVALID : JCB_E_CUDA, "%s failed: %s (%s:%d)", \
+                  #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                                \
+  } while (0)
+
+#define LAUNCH(ctx, expr)    \
+  do {                       \
+    CUDA_TRY((ctx), (expr)); \
+    ++(ctx)->launches;       \
+  } while (0)
+
+constexpr size_t PROF_PAIRS = 32768;
+
+// Launch with an optional CUDA-event pair around it (same stream), attributed to kernel class `cls`
+// with its algorithmic FLOPs / bytes.  Costs two cudaEventRecord per launch while profiling is on.
+#define LAUNCH_P(ctx, cls, flops_, bytes_, expr)                                              \
+  do {                                                                                        \
+    jcb_ctx* _c = (ctx);                                                                      \
+    long _slot = -1;                                                                          \
+    if (_c->prof_on) {                                                                        \
+      _c->prof_n[(cls)] += 1;                                                                 \
+      _c->prof_flops[(cls)] += static_cast<double>(flops_);                                   \
+      _c->prof_bytes[(cls)] += static_cast<double>(bytes_);                                   \
+      if (_c->prof_cls.size() < PROF_PAIRS) {                                                 \
+        _slot = static_cast<long>(_c->prof_cls.size());                                       \
+        _c->prof_cls.push_back((cls));                                                        \
+        cudaEventRecord(_c->prof_ev[2 * _slot], _c->stream);                                  \
+      }                                                                                       \
+    }                                                                                         \
+    LAUNCH(_c, (expr));                                                                       \
+    if (_slot >= 0) cudaEventRecord(_c->prof_ev[2 * _slot + 1], _c->stream);                  \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Grow-only workspace.  Growth synchronises the stream (buffers may be in use); steady state never does.
+int ws_reserve(jcb_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return JCB_OK;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+  if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for the workspace failed: %s", bytes, cudaGetErrorString(e));
+  ctx->ws_bytes = bytes;
+  return JCB_OK;
+}
+int stage_reserve(jcb_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->stage_bytes) return JCB_OK;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    ctx->stage[i] = nullptr;
+  }
+  ctx->stage_bytes = 0;
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaMalloc(&ctx->stage[i], bytes);
+    if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for image staging failed: %s", bytes, cudaGetErrorString(e));
+  }
+  ctx->stage_bytes = bytes;
+  return JCB_OK;
+}
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return p;
+  }
+};
+
+size_t img_elem_bytes(int dt) { return dt == JCB_IMG_F32 ? 4 : dt == JCB_IMG_BF16 ? 2 : 1; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct LoraAdapter {
+  std::vector<float> A, B;
+  int r = 0;
+  float scaling = 0.f;
+};
+
+struct LayerDev {
+  __nv_bfloat16 *in_w = nullptr, *out_w = nullptr, *fc_w = nullptr, *proj_w = nullptr;
+  float *in_b = nullptr, *out_b = nullptr, *fc_b = nullptr, *proj_b = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct jcb_vit {
+  jcb_ctx* ctx = nullptr;
+  jcb_vit_config cfg{};
+  int grid = 0, tokens = 0, heads = 0, kpatch = 0;
+  std::map<std::string, std::vector<float>> host;   // fp32 staging by reference key name
+  std::map<std::string, int64_t> expected;          // key -> numel
+  std::map<int, LoraAdapter> lora;                  // layer * 4 + proj
+  bool finalized = false;
+  void* arena = nullptr;                            // device weights
+  size_t arena_bytes = 0;
+  __nv_bfloat16* conv_w = nullptr;
+  float *cls = nullptr, *pos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr,
+        *ln_post_b = nullptr, *proj = nullptr;
+  std::vector<LayerDev> layers;
+};
+
+namespace {
+
+std::string blk(int i, const char* tail) { return "visual.transformer.resblocks." + std::to_string(i) + "." + tail; }
+
+void build_expected(jcb_vit* v) {
+  const int64_t W = v->cfg.width, P = v->cfg.patch, E = v->cfg.embed_dim, T = v->tokens;
+  auto& e = v->expected;
+  e["visual.conv1.weight"] = W * 3 * P * P;
+  e["visual.class_embedding"] = W;
+  e["visual.positional_embedding"] = T * W;
+  e["visual.ln_pre.weight"] = W;
+  e["visual.ln_pre.bias"] = W;
+  e["visual.ln_post.weight"] = W;
+  e["visual.ln_post.bias"] = W;
+  e["visual.proj"] = W * E;
+  for (int i = 0; i < v->cfg.layers; ++i) {
+    e[blk(i, "attn.in_proj_weight")] = 3 * W * W;
+    e[blk(i, "attn.in_proj_bias")] = 3 * W;
+    e[blk(i, "attn.out_proj.weight")] = W * W;
+    e[blk(i, "attn.out_proj.bias")] = W;
+    e[blk(i, "ln_1.weight")] = W;
+    e[blk(i, "ln_1.bias")] = W;
+    e[blk(i, "ln_2.weight")] = W;
+    e[blk(i, "ln_2.bias")] = W;
+    e[blk(i, "mlp.c_fc.weight")] = 4 * W * W;
+    e[blk(i, "mlp.c_fc.bias")] = 4 * W;
+    e[blk(i, "mlp.c_proj.weight")] = 4 * W * W;
+    e[blk(i, "mlp.c_proj.bias")] = W;
+  }
+}
+
+// workspace layout for one chunk of n views
+struct TowerWs {
+  __nv_bfloat16* big;     // patches [n*G*G, 3PP]  /  MLP hidden [n*T, 4W]  (never live together)
+  float* tokens;          // residual stream [n*T, W] fp32
+  __nv_bfloat16* ln_out;  // [n*T, W]
+  __nv_bfloat16* qkv;     // [n*T, 3W]
+  __nv_bfloat16* attn;    // [n*T, W]
+};
+size_t tower_ws_bytes(const jcb_vit* v, int64_t n) {
+  const size_t W = v->cfg.width, T = v->tokens, GG = static_cast<size_t>(v->grid) * v->grid, KP = v->kpatch;
+  const size_t big = std::max(n * GG * KP, n * T * 4 * W) * 2;
+  return align_up(big) + align_up(n * T * W * 4) + align_up(n * T * W * 2) + align_up(n * T * 3 * W * 2) +
+         align_up(n * T * W * 2);
+}
+TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
+  const size_t W = v->cfg.width, T = v->tokens, GG = static_cast<size_t>(v->grid) * v->grid, KP = v->kpatch;
+  TowerWs w;
+  w.big = b.take<__nv_bfloat16>(std::max(n * GG * KP, n * T * 4 * W));
+  w.tokens = b.take<float>(n * T * W);
+  w.ln_out = b.take<__nv_bfloat16>(n * T * W);
+  w.qkv = b.take<__nv_bfloat16>(n * T * 3 * W);
+  w.attn = b.take<__nv_bfloat16>(n * T * W);
+  return w;
+}
+
+int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
+             const float* bias, int epi, void* out, int64_t ldo, const float* pos = nullptr, int tin = 49,
+             int tout = 50) {
+  GemmArgs g;
+  g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo; g.pos = pos; g.tokens_in = tin; g.tokens_out = tout;
+  // algorithmic bytes: A + B read once, C written once (read-modify-write for the residual epilogue)
+  const double out_b = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 ? 2.0 : (epi == EPI_BIAS_RESID_F32 ? 8.0 : 4.0);
+  const double bytes = 2.0 * M * K + 2.0 * N * K + out_b * M * N;
+  LAUNCH_P(ctx, cls, 2.0 * M * N * K, bytes, launch_gemm(g, ctx->dev_status, ctx->num_sms, ctx->stream));
+  return JCB_OK;
+}
+
+// The image tower on `n` views resident on the device.  Schedule = VisionTransformer.execute
+// (reference jclip/model.py:104-126) with every elementwise op fused into a neighbouring kernel.
+int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_norm, const TowerWs& w) {
+  jcb_ctx* ctx = v->ctx;
+  cudaStream_t s = ctx->stream;
+  const int W = v->cfg.width, T = v->tokens, GG = v->grid * v->grid, KP = v->kpatch;
+  const int M = static_cast<int>(n * T);
+  // conv1 as im2col + GEMM; epilogue scatters to token rows 1..T-1 and adds the positional embedding
+  const double MW = static_cast<double>(M) * W;  // elements of one [tokens, width] tensor
+  const double img_b = static_cast<double>(n) * 3 * v->cfg.resolution * v->cfg.resolution;
+  LAUNCH_P(ctx, JCB_KC_IM2COL, 0, img_b * img_elem_bytes(dt) + img_b * 2,
+           launch_im2col(images, dt, n, v->cfg.resolution, v->cfg.patch, apply_norm, w.big, s));
+  int rc = run_gemm(ctx, JCB_KC_GEMM_PATCH, w.big, v->conv_w, static_cast<int>(n * GG), W, KP, nullptr, EPI_PATCH_F32, w.tokens, W,
+                    v->pos, GG, T);
+  if (rc) return rc;
+  // class token + ln_pre (residual stream) + layer 0's ln_1
+  LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
+                              v->layers[0].ln1_b, w.ln_out, s));
+  for (int l = 0; l < v->cfg.layers; ++l) {
+    const LayerDev& L = v->layers[l];
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
+    LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * v->heads * T * T * 64, MW * (6 + 2),
+             launch_attention(w.qkv, n, T, v->heads, w.attn, s));
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+    LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+    if (l + 1 < v->cfg.layers) {
+      const LayerDev& Nx = v->layers[l + 1];
+      LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, Nx.ln1_g, Nx.ln1_b, w.ln_out, s));
+    }
+  }
+  return JCB_OK;
+}
+
+int check_vit(jcb_vit* v) {
+  if (!v) return JCB_E_INVALID;
+  if (!v->finalized) return fail(v->ctx, JCB_E_STATE, "jcb_vit_finalize has not been called");
+  return JCB_OK;
+}
+
+// encode `n` views (device-resident when !on_host) into out_dev [n, E]; ws_extra bytes at the start of
+// the workspace are reserved for the caller.
+int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n, int apply_norm, int normalize,
+                 float* out_dev, size_t ws_extra) {
+  jcb_ctx* ctx = v->ctx;
+  if (dt < 0 || dt > 2) return fail(ctx, JCB_E_INVALID, "unknown image dtype %d", dt);
+  if (n < 0) return fail(ctx, JCB_E_INVALID, "negative view count");
+  if (n == 0) return JCB_OK;
+  if (!images || !out_dev) return fail(ctx, JCB_E_INVALID, "null image / output pointer");
+  const int64_t chunk = std::min<int64_t>(ctx->chunk_views, n);
+  int rc = ws_reserve(ctx, ws_extra + tower_ws_bytes(v, chunk));
+  if (rc) return rc;
+  Bump b(static_cast<uint8_t*>(ctx->ws) + ws_extra);
+  TowerWs w = tower_ws_carve(v, chunk, b);
+  const size_t view_bytes = static_cast<size_t>(3) * v->cfg.resolution * v->cfg.resolution * img_elem_bytes(dt);
+  if (on_host && (rc = stage_reserve(ctx, chunk * view_bytes))) return rc;
+  int64_t ci = 0;
+  for (int64_t off = 0; off < n; off += chunk, ++ci) {
+    const int64_t m = std::min(chunk, n - off);
+    const void* src = static_cast<const uint8_t*>(images) + off * view_bytes;
+    if (on_host) {
+      const int buf = static_cast<int>(ci & 1);
+      if (ci >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[buf], 0));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[buf], src, m * view_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[buf], ctx->copy_stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[buf], 0));
+      src = ctx->stage[buf];
+    }
+    if ((rc = tower_forward(v, src, dt, m, apply_norm, w))) return rc;
+    LAUNCH_P(ctx, JCB_KC_TAIL, 2.0 * m * v->cfg.width * v->cfg.embed_dim,
+             static_cast<double>(m) * (v->cfg.width + v->cfg.embed_dim) * 4, launch_tail(w.tokens, m, v->tokens, v->cfg.width, v->ln_post_g, v->ln_post_b, v->proj,
+                            v->cfg.embed_dim, normalize, out_dev + off * v->cfg.embed_dim, ctx->stream));
+    if (on_host) CUDA_TRY(ctx, cudaEventRecord(ctx->compute_done[ci & 1], ctx->stream));
+  }
+  return JCB_OK;
+}
+
+int sync_and_check(jcb_ctx* ctx) {
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  int st = 0;
+  CUDA_TRY(ctx, cudaMemcpy(&st, ctx->dev_status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    int zero = 0;
+    cudaMemcpy(ctx->dev_status, &zero, sizeof(int), cudaMemcpyHostToDevice);
+    return fail(ctx, JCB_E_KERNEL, "device-side kernel status %d (101 producer / 102 mma / 103 epilogue pipeline timeout)", st);
+  }
+  return JCB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int jcb_abi_version(void) { return JCB_ABI_VERSION; }
+
+int jcb_ctx_create(int device, jcb_ctx** out) {
+  if (!out) return JCB_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return JCB_E_NO_DEVICE;
+  if (device < 0 || device >= count) return JCB_E_INVALID;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JCB_E_CUDA;
+  if (prop.major != 10) return JCB_E_NO_DEVICE;  // kernels are sm_100a only: tcgen05 / TMEM / TMA
+  jcb_ctx* ctx = new jcb_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  DeviceGuard g(device);
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->own_stream = ok;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    ok = cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaMalloc(&ctx->dev_status, sizeof(int)) == cudaSuccess &&
+       cudaMemset(ctx->dev_status, 0, sizeof(int)) == cudaSuccess;
+  const char* derr = ok ? gemm_init_driver_api() : "context setup failed";
+  if (!ok || derr) {
+    jcb_ctx_destroy(ctx);
+    return JCB_E_CUDA;
+  }
+  *out = ctx;
+  return JCB_OK;
+}
+
+int jcb_ctx_destroy(jcb_ctx* ctx) {
+  if (!ctx) return JCB_OK;
+  DeviceGuard g(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
+    if (ctx->compute_done[i]) cudaEventDestroy(ctx->compute_done[i]);
+  }
+  if (ctx->dev_status) cudaFree(ctx->dev_status);
+  for (auto e : ctx->prof_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return JCB_OK;
+}
+
+int jcb_ctx_set_stream(jcb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return JCB_E_INVALID;
+  DeviceGuard g(ctx->device);
+  cudaStream_t ns = static_cast<cudaStream_t>(cuda_stream);
+  if (ns == ctx->stream) return JCB_OK;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = ns;
+  ctx->own_stream = false;
+  return JCB_OK;
+}
+
+int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views) {
+  if (!ctx || chunk_views < 1 || chunk_views > 40000) return ctx ? fail(ctx, JCB_E_INVALID, "chunk_views out of range") : JCB_E_INVALID;
+  ctx->chunk_views = chunk_views;
+  return JCB_OK;
+}
+
+int jcb_sync(jcb_ctx* ctx) {
+  if (!ctx) return JCB_E_INVALID;
+  DeviceGuard g(ctx->device);
+  return sync_and_check(ctx);
+}
+
+const char* jcb_last_error(const jcb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int jcb_ctx_info(const jcb_ctx* ctx, int* num_sms, int* cc_major, int* cc_minor, size_t* workspace_bytes) {
+  if (!ctx) return JCB_E_INVALID;
+  if (num_sms) *num_sms = ctx->num_sms;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (workspace_bytes) *workspace_bytes = ctx->ws_bytes + 2 * ctx->stage_bytes;
+  return JCB_OK;
+}
+
+int64_t jcb_ctx_launch_count(const jcb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+
+int jcb_ctx_profile(jcb_ctx* ctx, int enable) {
+  if (!ctx) return JCB_E_INVALID;
+  DeviceGuard g(ctx->device);
+  if (enable) {
+    if (ctx->prof_ev.empty()) {
+      ctx->prof_ev.resize(2 * PROF_PAIRS, nullptr);
+      for (auto& e : ctx->prof_ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return fail(ctx, JCB_E_CUDA, "cudaEventCreate failed");
+      ctx->prof_cls.reserve(PROF_PAIRS);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof_cls.clear();
+    for (int i = 0; i < JCB_KC_COUNT; ++i) {
+      ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; ctx->prof_timed[i] = 0; ctx->prof_flops[i] = 0; ctx->prof_bytes[i] = 0;
+    }
+    ctx->prof_on = true;
+  } else if (ctx->prof_on) {
+    ctx->prof_on = false;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->prof_cls.size(); ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess) {
+        ctx->prof_ms[ctx->prof_cls[i]] += ms;
+        ctx->prof_timed[ctx->prof_cls[i]] += 1;
+      }
+    }
+    ctx->prof_cls.clear();
+  }
+  return JCB_OK;
+}
+
+int jcb_ctx_profile_read(const jcb_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches,
+                         int64_t* timed_launches, double* flops, double* bytes) {
+  if (!ctx || kernel_class < 0 || kernel_class >= JCB_KC_COUNT) return JCB_E_INVALID;
+  if (total_ms) *total_ms = ctx->prof_ms[kernel_class];
+  if (launches) *launches = ctx->prof_n[kernel_class];
+  if (timed_launches) *timed_launches = ctx->prof_timed[kernel_class];
+  if (flops) *flops = ctx->prof_flops[kernel_class];
+  if (bytes) *bytes = ctx->prof_bytes[kernel_class];
+  return JCB_OK;
+}
+
+const char* jcb_kernel_class_name(int kernel_class) {
+  static const char* names[JCB_KC_COUNT] = {"im2col", "gemm_patch", "embed_ln", "gemm_qkv", "attention", "gemm_out",
+                                            "layernorm", "gemm_fc1", "gemm_fc2", "tail", "mta", "head", "other"};
+  return kernel_class >= 0 && kernel_class < JCB_KC_COUNT ? names[kernel_class] : "?";
+}
+
+// ------------------------------------------------------------------------------------------------
+int jcb_vit_create(jcb_ctx* ctx, const jcb_vit_config* cfg, jcb_vit** out) {
+  if (!ctx || !cfg || !out) return JCB_E_INVALID;
+  *out = nullptr;
+  if (cfg->layers < 1 || cfg->layers > 64) return fail(ctx, JCB_E_INVALID, "layers=%d unsupported", cfg->layers);
+  if (cfg->width % 256 != 0 || cfg->width > 1024 || cfg->width < 256)
+    return fail(ctx, JCB_E_INVALID, "width=%d unsupported (need a multiple of 256 in [256, 1024])", cfg->width);
+  if (cfg->patch % 8 != 0 || cfg->resolution % cfg->patch != 0)
+    return fail(ctx, JCB_E_INVALID, "patch=%d / resolution=%d unsupported", cfg->patch, cfg->resolution);
+  if (cfg->embed_dim != 512) return fail(ctx, JCB_E_INVALID, "embed_dim=%d unsupported (512 only)", cfg->embed_dim);
+  jcb_vit* v = new jcb_vit();
+  v->ctx = ctx;
+  v->cfg = *cfg;
+  v->grid = cfg->resolution / cfg->patch;
+  v->tokens = v->grid * v->grid + 1;
+  v->heads = cfg->width / 64;  // jclip/model.py:152
+  v->kpatch = 3 * cfg->patch * cfg->patch;
+  if (v->tokens > 64 || v->heads % 4 != 0 || v->kpatch % 64 != 0) {
+    delete v;
+    return fail(ctx, JCB_E_INVALID, "tokens=%d (max 64) / heads=%d (multiple of 4) unsupported", v->tokens, v->heads);
+  }
+  build_expected(v);
+  *out = v;
+  return JCB_OK;
+}
+
+int jcb_vit_destroy(jcb_vit* v) {
+  if (!v) return JCB_OK;
+  DeviceGuard g(v->ctx->device);
+  cudaStreamSynchronize(v->ctx->stream);
+  if (v->arena) cudaFree(v->arena);
+  delete v;
+  return JCB_OK;
+}
+
+int jcb_vit_set_param(jcb_vit* v, const char* name, const float* data, int64_t numel) {
+  if (!v || !name || !data) return JCB_E_INVALID;
+  auto it = v->expected.find(name);
+  if (it == v->expected.end()) return fail(v->ctx, JCB_E_INVALID, "unknown parameter '%s'", name);
+  if (it->second != numel)
+    return fail(v->ctx, JCB_E_INVALID, "parameter '%s': expected %lld elements, got %lld", name,
+                static_cast<long long>(it->second), static_cast<long long>(numel));
+  v->host[name].assign(data, data + numel);
+  v->finalized = false;
+  return JCB_OK;
+}
+
+int jcb_vit_set_lora(jcb_vit* v, int layer, int proj, const float* A, const float* B, int r, float scaling) {
+  if (!v || !A || !B) return JCB_E_INVALID;
+  if (layer < 0 || layer >= v->cfg.layers || proj < 0 || proj > 3 || r < 1 || r > 256)
+    return fail(v->ctx, JCB_E_INVALID, "set_lora: layer=%d proj=%d r=%d out of range", layer, proj, r);
+  LoraAdapter& a = v->lora[layer * 4 + proj];
+  const int64_t W = v->cfg.width;
+  a.A.assign(A, A + r * W);
+  a.B.assign(B, B + W * r);
+  a.r = r;
+  a.scaling = scaling;
+  v->finalized = false;
+  return JCB_OK;
+}
+
+int jcb_vit_clear_lora(jcb_vit* v) {
+  if (!v) return JCB_E_INVALID;
+  v->lora.clear();
+  v->finalized = false;
+  return JCB_OK;
+}
+
+int jcb_vit_finalize(jcb_vit* v) {
+  if (!v) return JCB_E_INVALID;
+  jcb_ctx* ctx = v->ctx;
+  DeviceGuard g(ctx->device);
+  for (auto& kv : v->expected)
+    if (!v->host.count(kv.first)) return fail(ctx, JCB_E_STATE, "parameter '%s' was never set", kv.first.c_str());
+  const size_t W = v->cfg.width, E = v->cfg.embed_dim, T = v->tokens, KP = v->kpatch, L = v->cfg.layers;
+  // arena: bf16 GEMM operands, then fp32 vectors
+  size_t bytes = align_up(W * KP * 2) + L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2));
+  bytes += 8 * align_up(std::max(W * E, T * W) * 4) + L * 8 * align_up(4 * W * 4);
+  const size_t tmp_elems = 4 * W * W;  // largest single tensor (c_fc / c_proj / conv1 for P=32)
+  const size_t tmp_bytes = align_up(std::max(tmp_elems, W * KP) * 4) + 2 * align_up(256 * W * 4);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!v->arena || v->arena_bytes < bytes) {
+    if (v->arena) cudaFree(v->arena);
+    v->arena = nullptr;
+    cudaError_t e = cudaMalloc(&v->arena, bytes);
+    if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for weights failed: %s", bytes, cudaGetErrorString(e));
+    v->arena_bytes = bytes;
+  }
+  void* tmp = nullptr;
+  {
+    cudaError_t e = cudaMalloc(&tmp, tmp_bytes);
+    if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for packing failed: %s", tmp_bytes, cudaGetErrorString(e));
+  }
+  struct TmpFree { void* p; ~TmpFree() { cudaFree(p); } } tmp_free{tmp};
+  float* tmp_w = static_cast<float*>(tmp);
+  float* tmp_A = reinterpret_cast<float*>(static_cast<uint8_t*>(tmp) + align_up(std::max(tmp_elems, W * KP) * 4));
+  float* tmp_B = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmp_A) + align_up(256 * W * 4));
+  cudaStream_t s = ctx->stream;
+  Bump b(v->arena);
+
+  auto up_f32 = [&](const std::string& key, float** dst) -> int {
+    const std::vector<float>& h = v->host[key];
+    *dst = b.take<float>(h.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(*dst, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    return JCB_OK;
+  };
+  // bf16 weight [rows, cols]; `adapters` lists (row offset, adapter) pairs merged in fp32 before the cast
+  auto up_bf16 = [&](const std::string& key, size_t rows, size_t cols, __nv_bfloat16** dst,
+                     const std::vector<std::pair<size_t, const LoraAdapter*>>& adapters) -> int {
+    const std::vector<float>& h = v->host[key];
+    *dst = b.take<__nv_bfloat16>(h.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(tmp_w, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    LAUNCH(ctx, launch_cast_bf16(tmp_w, *dst, static_cast<int64_t>(rows * cols), s));
+    for (auto& ad : adapters) {
+      const LoraAdapter* a = ad.second;
+      CUDA_TRY(ctx, cudaMemcpyAsync(tmp_A, a->A.data(), a->A.size() * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(ctx, cudaMemcpyAsync(tmp_B, a->B.data(), a->B.size() * 4, cudaMemcpyHostToDevice, s));
+      // rows [off, off + W) of the packed weight: W' = W + s * B A   (test.py:310-313, :388-398)
+      LAUNCH(ctx, launch_merge_lora_cast(tmp_w + ad.first * cols, tmp_A, tmp_B, static_cast<int>(W),
+                                         static_cast<int>(cols), a->r, a->scaling, *dst + ad.first * cols, s));
+      // the staging buffers are reused by the next adapter
+      CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return JCB_OK;
+  };
+  int rc;
+  if ((rc = up_bf16("visual.conv1.weight", W, KP, &v->conv_w, {}))) return rc;
+  if ((rc = up_f32("visual.class_embedding", &v->cls))) return rc;
+  if ((rc = up_f32("visual.positional_embedding", &v->pos))) return rc;
+  if ((rc = up_f32("visual.ln_pre.weight", &v->ln_pre_g))) return rc;
+  if ((rc = up_f32("visual.ln_pre.bias", &v->ln_pre_b))) return rc;
+  if ((rc = up_f32("visual.ln_post.weight", &v->ln_post_g))) return rc;
+  if ((rc = up_f32("visual.ln_post.bias", &v->ln_post_b))) return rc;
+  if ((rc = up_f32("visual.proj", &v->proj))) return rc;
+  v->layers.assign(L, LayerDev());
+  for (size_t i = 0; i < L; ++i) {
+    LayerDev& Ld = v->layers[i];
+    std::vector<std::pair<size_t, const LoraAdapter*>> in_ad, out_ad;
+    for (int p = 0; p < 3; ++p) {  // packed in_proj rows: q 0:W, k W:2W, v 2W:3W  (test.py:491-501)
+      auto it = v->lora.find(static_cast<int>(i) * 4 + p);
+      if (it != v->lora.end()) in_ad.push_back({p * W, &it->second});
+    }
+    auto ito = v->lora.find(static_cast<int>(i) * 4 + JCB_PROJ_O);
+    if (ito != v->lora.end()) out_ad.push_back({0, &ito->second});
+    const int li = static_cast<int>(i);
+    if ((rc = up_bf16(blk(li, "attn.in_proj_weight"), 3 * W, W, &Ld.in_w, in_ad))) return rc;
+    if ((rc = up_bf16(blk(li, "attn.out_proj.weight"), W, W, &Ld.out_w, out_ad))) return rc;
+    if ((rc = up_bf16(blk(li, "mlp.c_fc.weight"), 4 * W, W, &Ld.fc_w, {}))) return rc;
+    if ((rc = up_bf16(blk(li, "mlp.c_proj.weight"), W, 4 * W, &Ld.proj_w, {}))) return rc;
+    if ((rc = up_f32(blk(li, "attn.in_proj_bias"), &Ld.in_b))) return rc;
+    if ((rc = up_f32(blk(li, "attn.out_proj.bias"), &Ld.out_b))) return rc;
+    if ((rc = up_f32(blk(li, "mlp.c_fc.bias"), &Ld.fc_b))) return rc;
+    if ((rc = up_f32(blk(li, "mlp.c_proj.bias"), &Ld.proj_b))) return rc;
+    if ((rc = up_f32(blk(li, "ln_1.weight"), &Ld.ln1_g))) return rc;
+    if ((rc = up_f32(blk(li, "ln_1.bias"), &Ld.ln1_b))) return rc;
+    if ((rc = up_f32(blk(li, "ln_2.weight"), &Ld.ln2_g))) return rc;
+    if ((rc = up_f32(blk(li, "ln_2.bias"), &Ld.ln2_b))) return rc;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  if (b.off > v->arena_bytes) return fail(ctx, JCB_E_STATE, "internal: weight arena overflow (%zu > %zu)", b.off, v->arena_bytes);
+  v->finalized = true;
+  return JCB_OK;
+}
+
+int jcb_encode_image(jcb_vit* v, const void* images_dev, int img_dtype, int64_t n_views, int apply_clip_norm,
+                     int normalize, float* out_dev) {
+  int rc = check_vit(v);
+  if (rc) return rc;
+  DeviceGuard g(v->ctx->device);
+  return encode_views(v, images_dev, img_dtype, false, n_views, apply_clip_norm, normalize, out_dev, 0);
+}
+
+int jcb_encode_image_host(jcb_vit* v, const void* images_host, int img_dtype, int64_t n_views, int apply_clip_norm,
+                          int normalize, float* out_host) {
+  int rc = check_vit(v);
+  if (rc) return rc;
+  jcb_ctx* ctx = v->ctx;
+  DeviceGuard g(ctx->device);
+  if (n_views == 0) return JCB_OK;
+  if (n_views < 0 || !out_host) return fail(ctx, JCB_E_INVALID, "bad arguments");
+  const size_t out_bytes = align_up(static_cast<size_t>(n_views) * v->cfg.embed_dim * 4);
+  if ((rc = ws_reserve(ctx, out_bytes + tower_ws_bytes(v, std::min<int64_t>(ctx->chunk_views, n_views))))) return rc;
+  float* out_dev = static_cast<float*>(ctx->ws);
+  if ((rc = encode_views(v, images_host, img_dtype, true, n_views, apply_clip_norm, normalize, out_dev, out_bytes)))
+    return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_host, out_dev, static_cast<size_t>(n_views) * v->cfg.embed_dim * 4,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_and_check(ctx);
+}
+
+int jcb_vit_debug_tokens(jcb_vit* v, const void* images_dev, int img_dtype, int64_t n_views, int apply_clip_norm,
+                         float* tokens_out_dev) {
+  int rc = check_vit(v);
+  if (rc) return rc;
+  jcb_ctx* ctx = v->ctx;
+  DeviceGuard g(ctx->device);
+  if (n_views < 1 || n_views > ctx->chunk_views) return fail(ctx, JCB_E_INVALID, "debug_tokens: 1 <= n_views <= chunk_views");
+  if ((rc = ws_reserve(ctx, tower_ws_bytes(v, n_views)))) return rc;
+  Bump b(ctx->ws);
+  TowerWs w = tower_ws_carve(v, n_views, b);
+  if ((rc = tower_forward(v, images_dev, img_dtype, n_views, apply_clip_norm, w))) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(tokens_out_dev, w.tokens, static_cast<size_t>(n_views) * v->tokens * v->cfg.width * 4,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+  return JCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+void jcb_mta_default_params(jcb_mta_params* p) {
+  if (!p) return;
+  p->lambda_y = 0.2f; p->lambda_q = 4.0f; p->th = 1e-6f; p->temperature = 1.0f; p->k_frac = 0.3; p->max_iter = 5;
+  p->reserved = 0;
+}
+
+namespace {
+MtaParams to_params(const jcb_mta_params* p) {
+  MtaParams m;
+  if (p) {
+    m.lambda_y = p->lambda_y; m.lambda_q = p->lambda_q; m.th = p->th; m.temperature = p->temperature;
+    m.k_frac = p->k_frac; m.max_iter = p->max_iter;
+  }
+  return m;
+}
+}  // namespace
+
+int jcb_mta(jcb_ctx* ctx, const float* feats_dev, const float* text_dev, int64_t n_images, int32_t n_views,
+            int32_t n_classes, int32_t dim, const jcb_mta_params* params, float* out_mode_dev, float* out_logits_dev) {
+  if (!ctx) return JCB_E_INVALID;
+  if (n_images < 0 || !feats_dev || !text_dev || !out_mode_dev) return fail(ctx, JCB_E_INVALID, "jcb_mta: bad arguments");
+  DeviceGuard g(ctx->device);
+  const size_t scratch = mta_scratch_bytes(n_images, n_views, n_classes, dim);
+  int rc = ws_reserve(ctx, scratch);
+  if (rc) return rc;
+  MtaSet set{feats_dev, text_dev, out_mode_dev, out_logits_dev};
+  LAUNCH_P(ctx, JCB_KC_MTA, 0, static_cast<double>(n_images) * (n_views + 1) * dim * 4,
+           launch_mta(&set, 1, n_images, n_views, n_classes, dim, to_params(params),
+                      scratch ? static_cast<float*>(ctx->ws) : nullptr, ctx->stream));
+  return JCB_OK;
+}
+
+int jcb_head(jcb_ctx* ctx, const float* m_pt, const float* m_hand, const float* m_zs, const float* T_pt,
+             const float* T_hand, const float* T_zs, const jcb_head_weights* lp, int64_t n_images, int32_t n_classes,
+             int32_t dim, int32_t rank_by, int32_t k, int32_t* out_topk, float* out_scores, float* out_all) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!m_pt || !m_hand || !m_zs || !T_pt || !T_hand || !T_zs || !lp || !out_topk || n_images < 0)
+    return fail(ctx, JCB_E_INVALID, "jcb_head: null argument");
+  DeviceGuard g(ctx->device);
+  HeadArgs a;
+  a.m_pt = m_pt; a.m_hand = m_hand; a.m_zs = m_zs; a.T_pt = T_pt; a.T_hand = T_hand; a.T_zs = T_zs;
+  a.scale1 = lp->scale1; a.bias1 = lp->bias1; a.fc_w = lp->fc_w; a.fc_b = lp->fc_b;
+  a.I = n_images; a.C = n_classes; a.D = dim; a.rank_by = rank_by; a.k = k;
+  a.out_topk = out_topk; a.out_scores = out_scores; a.out_all = out_all;
+  LAUNCH_P(ctx, JCB_KC_HEAD, 0, static_cast<double>(n_images) * (3 * dim + k) * 4, launch_head(a, ctx->stream));
+  return JCB_OK;
+}
+
+int jcb_cosine_topk(jcb_ctx* ctx, const float* feats, const float* text, int64_t n, int32_t n_classes, int32_t dim,
+                    float scale, int32_t k, int32_t* out_topk, float* out_scores) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!feats || !text || n < 0 || (!out_topk && !out_scores)) return fail(ctx, JCB_E_INVALID, "jcb_cosine_topk: bad arguments");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_cosine_topk(feats, text, n, n_classes, dim, scale, k, out_topk, out_scores, ctx->stream));
+  return JCB_OK;
+}
+
+int jcb_channel_lp(jcb_ctx* ctx, const float* feats, int64_t n, int32_t n_classes, int32_t dim,
+                   const jcb_head_weights* lp, float* out) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!feats || !lp || !out || n < 0) return fail(ctx, JCB_E_INVALID, "jcb_channel_lp: bad arguments");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_channel_lp(feats, n, n_classes, dim, lp->scale1, lp->bias1, lp->fc_w, lp->fc_b, out, ctx->stream));
+  return JCB_OK;
+}
+
+int jcb_logit_normalize(jcb_ctx* ctx, const float* in, int64_t n, int32_t n_classes, float* out) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!in || !out || n < 0) return fail(ctx, JCB_E_INVALID, "jcb_logit_normalize: bad arguments");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_logit_normalize(in, n, n_classes, out, ctx->stream));
+  return JCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
+  int rc = check_vit(vit);
+  if (rc) return rc;
+  jcb_ctx* ctx = vit->ctx;
+  if (vit_zs && ((rc = check_vit(vit_zs)) || vit_zs->ctx != ctx)) return rc ? rc : fail(ctx, JCB_E_INVALID, "vit_zs belongs to another context");
+  if (!a || !a->images || !a->out_topk || !a->text_pt_dev || !a->text_hand_dev || !a->text_zs_dev ||
+      !a->text_pt_t_dev || !a->text_hand_t_dev || !a->text_zs_t_dev)
+    return fail(ctx, JCB_E_INVALID, "jcb_pipeline: null argument");
+  if (a->n_images < 0 || a->n_views < 1 || a->k < 1 || a->k > 8) return fail(ctx, JCB_E_INVALID, "jcb_pipeline: bad sizes");
+  if (a->n_images == 0) return JCB_OK;
+  DeviceGuard g(ctx->device);
+  const int E = vit->cfg.embed_dim, C = a->n_classes, V = a->n_views;
+  const int64_t I = a->n_images, NV = I * V;
+  // persistent part of the workspace: [feats] [feats_zs] [modes x3] [topk] [mta scratch]
+  const size_t feats_b = align_up(static_cast<size_t>(NV) * E * 4);
+  const size_t modes_b = align_up(static_cast<size_t>(I) * E * 4);
+  const size_t topk_b = align_up(static_cast<size_t>(I) * a->k * 4);
+  const size_t scratch_b = align_up(mta_scratch_bytes(3 * I, V, C, E));
+  const bool own_feats = a->out_feats_dev == nullptr;
+  const size_t head_bytes = (own_feats ? feats_b : 0) + (vit_zs ? feats_b : 0) + 3 * modes_b + topk_b + scratch_b;
+  if ((rc = ws_reserve(ctx, head_bytes + tower_ws_bytes(vit, std::min<int64_t>(ctx->chunk_views, NV))))) return rc;
+  Bump b(ctx->ws);
+  float* feats = own_feats ? b.take<float>(static_cast<size_t>(NV) * E) : a->out_feats_dev;
+  float* feats_zs = vit_zs ? b.take<float>(static_cast<size_t>(NV) * E) : feats;
+  float* m_pt = b.take<float>(static_cast<size_t>(I) * E);
+  float* m_hand = b.take<float>(static_cast<size_t>(I) * E);
+  float* m_zs = b.take<float>(static_cast<size_t>(I) * E);
+  int32_t* topk_dev = a->topk_on_host ? b.take<int32_t>(static_cast<size_t>(I) * a->k) : a->out_topk;
+  if (!a->topk_on_host) b.take<int32_t>(static_cast<size_t>(I) * a->k);
+  float* scratch = scratch_b ? b.take<float>(scratch_b / 4) : nullptr;
+  if (b.off > head_bytes) return fail(ctx, JCB_E_STATE, "internal: pipeline workspace overflow");
+
+  // encode_image + L2 normalise over every view                      test.py:1705-1706 (:1711-1712)
+  if ((rc = encode_views(vit, a->images, a->img_dtype, a->images_on_host != 0, NV, a->apply_clip_norm, 1, feats, head_bytes))) return rc;
+  if (vit_zs && (rc = encode_views(vit_zs, a->images, a->img_dtype, a->images_on_host != 0, NV, a->apply_clip_norm, 1, feats_zs, head_bytes))) return rc;
+  // solve_mta x3 in one launch                                        test.py:1708-1709, :1713
+  MtaSet sets[3] = {{feats, a->text_pt_t_dev, m_pt, nullptr},
+                    {feats, a->text_hand_t_dev, m_hand, nullptr},
+                    {feats_zs, a->text_zs_t_dev, m_zs, nullptr}};
+  LAUNCH_P(ctx, JCB_KC_MTA, 0, 3.0 * I * (V + 1) * E * 4, launch_mta(sets, 3, I, V, C, E, MtaParams(), scratch, ctx->stream));
+  // Channel_LP, logit_normalize, fusion, top-k                        test.py:1710-1738
+  HeadArgs h;
+  h.m_pt = m_pt; h.m_hand = m_hand; h.m_zs = m_zs;
+  h.T_pt = a->text_pt_dev; h.T_hand = a->text_hand_dev; h.T_zs = a->text_zs_dev;
+  h.scale1 = a->lp.scale1; h.bias1 = a->lp.bias1; h.fc_w = a->lp.fc_w; h.fc_b = a->lp.fc_b;
+  h.I = I; h.C = C; h.D = E; h.rank_by = a->rank_by; h.k = a->k;
+  h.out_topk = topk_dev; h.out_scores = a->out_scores_dev; h.out_all = nullptr;
+  LAUNCH_P(ctx, JCB_KC_HEAD, 0, static_cast<double>(I) * (3 * E + a->k) * 4, launch_head(h, ctx->stream));
+  if (a->topk_on_host) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(a->out_topk, topk_dev, static_cast<size_t>(I) * a->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_and_check(ctx);
+  }
+  return JCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int jcb_gemm_bf16(jcb_ctx* ctx, const void* A, const void* B, int32_t M, int32_t N, int32_t K, const float* bias,
+                  int32_t epilogue, void* out, int64_t ldo) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!A || !B || !out) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: null pointer");
+  if (epilogue == EPI_PATCH_F32) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: the patch epilogue is internal");
+  DeviceGuard g(ctx->device);
+  return run_gemm(ctx, JCB_KC_OTHER, static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(B), M, N, K, bias,
+                  epilogue, out, ldo);
+}
+
+int jcb_layernorm_bf16(jcb_ctx* ctx, const float* x, int64_t rows, int32_t width, const float* gamma, const float* beta,
+                       void* out) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!x || !gamma || !beta || !out) return fail(ctx, JCB_E_INVALID, "jcb_layernorm_bf16: null pointer");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_layernorm(x, rows, width, gamma, beta, static_cast<__nv_bfloat16*>(out), ctx->stream));
+  return JCB_OK;
+}
+
+int jcb_attention_bf16(jcb_ctx* ctx, const void* qkv, int64_t n_views, int32_t tokens, int32_t heads, void* out) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!qkv || !out) return fail(ctx, JCB_E_INVALID, "jcb_attention_bf16: null pointer");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_attention(static_cast<const __nv_bfloat16*>(qkv), n_views, tokens, heads,
+                               static_cast<__nv_bfloat16*>(out), ctx->stream));
+  return JCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Minimal DLPack (dlpack.h v0.8) structures: enough to borrow a tensor.
+namespace {
+struct DLDevice { int32_t device_type; int32_t device_id; };
+struct DLDataType { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor {
+  void* data; DLDevice device; int32_t ndim; DLDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset;
+};
+struct DLManagedTensor { DLTensor dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor*); };
+constexpr int kDLCUDA = 2, kDLUInt = 1, kDLFloat = 2, kDLBfloat = 4;
+bool dl_contiguous(const DLTensor& t) {
+  if (!t.strides) return true;
+  int64_t expect = 1;
+  for (int i = t.ndim - 1; i >= 0; --i) {
+    if (t.shape[i] != 1 && t.strides[i] != expect) return false;
+    expect *= t.shape[i];
+  }
+  return true;
+}
+}  // namespace
+
+int jcb_encode_image_dlpack(jcb_vit* v, void* images_dlmanaged, void* out_dlmanaged, int apply_clip_norm, int normalize) {
+  int rc = check_vit(v);
+  if (rc) return rc;
+  jcb_ctx* ctx = v->ctx;
+  if (!images_dlmanaged || !out_dlmanaged) return fail(ctx, JCB_E_INVALID, "null DLManagedTensor");
+  const DLTensor& in = static_cast<DLManagedTensor*>(images_dlmanaged)->dl_tensor;
+  const DLTensor& out = static_cast<DLManagedTensor*>(out_dlmanaged)->dl_tensor;
+  if (in.device.device_type != kDLCUDA || out.device.device_type != kDLCUDA || in.device.device_id != ctx->device ||
+      out.device.device_id != ctx->device)
+    return fail(ctx, JCB_E_INVALID, "DLPack tensors must live on CUDA device %d", ctx->device);
+  int dt;
+  if (in.dtype.code == kDLFloat && in.dtype.bits == 32) dt = JCB_IMG_F32;
+  else if (in.dtype.code == kDLBfloat && in.dtype.bits == 16) dt = JCB_IMG_BF16;
+  else if (in.dtype.code == kDLUInt && in.dtype.bits == 8) dt = JCB_IMG_U8;
+  else return fail(ctx, JCB_E_INVALID, "unsupported image dtype (code %d, bits %d)", in.dtype.code, in.dtype.bits);
+  const int R = v->cfg.resolution;
+  if (in.ndim != 4 || in.shape[1] != 3 || in.shape[2] != R || in.shape[3] != R || !dl_contiguous(in))
+    return fail(ctx, JCB_E_INVALID, "images must be contiguous [n, 3, %d, %d]", R, R);
+  if (out.ndim != 2 || out.shape[0] != in.shape[0] || out.shape[1] != v->cfg.embed_dim || out.dtype.code != kDLFloat ||
+      out.dtype.bits != 32 || !dl_contiguous(out))
+    return fail(ctx, JCB_E_INVALID, "out must be contiguous float32 [n, %d]", v->cfg.embed_dim);
+  DeviceGuard g(ctx->device);
+  return encode_views(v, static_cast<const uint8_t*>(in.data) + in.byte_offset, dt, false, in.shape[0], apply_clip_norm,
+                      normalize, reinterpret_cast<float*>(static_cast<uint8_t*>(out.data) + out.byte_offset), 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// Fused single-tile multi-head attention for short sequences (T <= 64 tokens: 50 for ViT-B/32, 54 for
+// the VPT variant): softmax(Q K^T / sqrt(64)) V per (view, head) with Q, K and V held in shared memory,
+// scores and probabilities never leaving registers.
+//
+// One CTA = one view x 4 heads; 8 warps, two per head (32 query rows each).  Q K^T and P V run on
+// mma.sync m16n8k16 bf16 tiles with fp32 accumulation (a 64x64x64 problem per head is far below the
+// size where a tcgen05/TMEM round trip pays; this kernel is 1 % of the tower's FLOPs and is bounded by
+// the 307 KB/view/layer it streams).  Softmax is fp32 with exp2 and the 1/8 scale folded in.
+//
+// Reference: jclip/mha.py:55-83 scaled_dot_product_attention (attn_mask None for the vision tower,
+// jclip/model.py:99; dropout 0 in eval), head split jclip/mha.py:351-362 / test.py:584-590.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace jcb {
+
+namespace {
+
+constexpr int HD = 64;              // head dim
+constexpr int TP = 64;              // padded token count
+constexpr int LDS = HD + 8;         // smem row stride (bf16): 144 B, conflict-free for ldmatrix
+constexpr int HEADS_PER_CTA = 4;
+constexpr int ATT_THREADS = HEADS_PER_CTA * 2 * 32;
+constexpr int TILE_ELEMS = TP * LDS;
+constexpr int ATT_SMEM = HEADS_PER_CTA * 3 * TILE_ELEMS * 2;  // 110592 B
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_smem);
+  const int W = heads * HD;
+  const int groups = heads / HEADS_PER_CTA;
+  const long long view = blockIdx.x / groups;
+  const int hg = blockIdx.x % groups;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* base = qkv + view * T * (3LL * W) + hg * HEADS_PER_CTA * HD;
+
+  // ---- stage Q, K, V of 4 heads: tile (h, m) at sm + (h*3 + m) * TILE_ELEMS, rows >= T zeroed
+  constexpr int CH_PER_ROW = HEADS_PER_CTA * HD / 8;  // 32 x 16-byte chunks per (row, matrix)
+  for (int i = tid; i < 3 * TP * CH_PER_ROW; i += ATT_THREADS) {
+    const int m = i / (TP * CH_PER_ROW);
+    const int rem = i % (TP * CH_PER_ROW);
+    const int row = rem / CH_PER_ROW, ch = rem % CH_PER_ROW;
+    const int h = ch / (HD / 8), c8 = (ch % (HD / 8)) * 8;
+    __nv_bfloat16* dst = sm + (h * 3 + m) * TILE_ELEMS + row * LDS + c8;
+    if (row < T) {
+      cp_async_16(smem_u32(dst), base + static_cast<long long>(row) * (3 * W) + m * W + ch * 8);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+
+  const int h = warp >> 1;          // head within the group
+  const int r0 = (warp & 1) * 32;   // first query row of this warp
+  const uint32_t sQ = smem_u32(sm + (h * 3 + 0) * TILE_ELEMS);
+  const uint32_t sK = smem_u32(sm + (h * 3 + 1) * TILE_ELEMS);
+  const uint32_t sV = smem_u32(sm + (h * 3 + 2) * TILE_ELEMS);
+
+  // ---- S = Q K^T : 2 m-tiles x 8 n-tiles (keys) x 4 k-steps (head dim)
+  float s[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int row = r0 + mt * 16 + (lane & 15);
+      const int col = kk * 16 + ((lane >> 4) << 3);
+      ldmatrix_x4(a[mt], sQ + (row * LDS + col) * 2);
+    }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {  // pairs of key tiles
+      uint32_t b[4];
+      const int krow = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const int col = kk * 16 + (((lane >> 3) & 1) << 3);
+      ldmatrix_x4(b, sK + (krow * LDS + col) * 2);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16_16816(s[mt][2 * np], a[mt], b[0], b[1]);
+        mma_bf16_16816(s[mt][2 * np + 1], a[mt], b[2], b[3]);
+      }
+    }
+  }
+
+  // ---- softmax over keys (fp32); thread holds rows g and g+8 of each m-tile, cols nt*8 + 2*(lane&3) + {0,1}
+  const float scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  float inv_sum[2][2];
+  uint32_t pfrag[2][8][2];  // P as bf16 pairs: [mt][nt][row half]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c0 = nt * 8 + 2 * (lane & 3);
+      if (c0 >= T) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
+      if (c0 + 1 >= T) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+      mx[0] = fmaxf(mx[0], fmaxf(s[mt][nt][0], s[mt][nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[mt][nt][2], s[mt][nt][3]));
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((s[mt][nt][0] - mx[0]) * scale_log2);
+      const float p1 = exp2f((s[mt][nt][1] - mx[0]) * scale_log2);
+      const float p2 = exp2f((s[mt][nt][2] - mx[1]) * scale_log2);
+      const float p3 = exp2f((s[mt][nt][3] - mx[1]) * scale_log2);
+      sum[0] += p0 + p1;
+      sum[1] += p2 + p3;
+      pfrag[mt][nt][0] = pack_bf16x2(p0, p1);
+      pfrag[mt][nt][1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+      sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+      inv_sum[mt][hh] = 1.0f / sum[hh];
+    }
+  }
+
+  // ---- O = P V : 2 m-tiles x 8 d-tiles x 4 k-steps (keys)
+  float o[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][dt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      a[mt][0] = pfrag[mt][2 * ks][0];
+      a[mt][1] = pfrag[mt][2 * ks][1];
+      a[mt][2] = pfrag[mt][2 * ks + 1][0];
+      a[mt][3] = pfrag[mt][2 * ks + 1][1];
+    }
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {  // pairs of d tiles
+      uint32_t b[4];
+      const int krow = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int col = dp * 16 + ((lane >> 4) << 3);
+      ldmatrix_x4_trans(b, sV + (krow * LDS + col) * 2);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16_16816(o[mt][2 * dp], a[mt], b[0], b[1]);
+        mma_bf16_16816(o[mt][2 * dp + 1], a[mt], b[2], b[3]);
+      }
+    }
+  }
+
+  // ---- normalise, stage through this warp's own Q rows (dead by now), coalesced store
+  __nv_bfloat16* stage = sm + (h * 3 + 0) * TILE_ELEMS;
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int row = r0 + mt * 16 + (lane >> 2);
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = dt * 8 + 2 * (lane & 3);
+      *reinterpret_cast<uint32_t*>(stage + row * LDS + col) =
+          pack_bf16x2(o[mt][dt][0] * inv_sum[mt][0], o[mt][dt][1] * inv_sum[mt][0]);
+      *reinterpret_cast<uint32_t*>(stage + (row + 8) * LDS + col) =
+          pack_bf16x2(o[mt][dt][2] * inv_sum[mt][1], o[mt][dt][3] * inv_sum[mt][1]);
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* obase = out + view * T * static_cast<long long>(W) + hg * HEADS_PER_CTA * HD;
+  for (int i = tid; i < T * CH_PER_ROW; i += ATT_THREADS) {
+    const int row = i / CH_PER_ROW, ch = i % CH_PER_ROW;
+    const int hh = ch / (HD / 8), c8 = (ch % (HD / 8)) * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(sm + (hh * 3 + 0) * TILE_ELEMS + row * LDS + c8);
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(row) * W + ch * 8) = v;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                             cudaStream_t stream) {
+  if (T < 1 || T > TP || heads % HEADS_PER_CTA != 0) return cudaErrorInvalidValue;
+  if (n_views == 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const long long grid = n_views * (heads / HEADS_PER_CTA);
+  attention_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM, stream>>>(qkv, T, heads, out);
+  return cudaGetLastError();
+}
+
+}  // namespace jcb

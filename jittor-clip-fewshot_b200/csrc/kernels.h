@@ -1,0 +1,104 @@
+// Host-side launchers of the sm_100a kernels behind the C-ABI (include/jclip_b200.h).
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace jcb {
+
+// ---- GEMM epilogues (fused into the tcgen05 kernel) -------------------------------------------
+enum GemmEpilogue : int {
+  EPI_BIAS_BF16 = 0,       // out_bf16[m,n]  = acc + bias[n]                       (QKV projection)
+  EPI_BIAS_GELU_BF16 = 1,  // out_bf16[m,n]  = quickgelu(acc + bias[n])            (MLP c_fc)
+  EPI_BIAS_RESID_F32 = 2,  // out_f32[m,n]  += acc + bias[n]                       (out_proj / c_proj + residual)
+  EPI_PATCH_F32 = 3,       // out_f32[row(m),n] = acc + pos[1 + m % T_in, n], row(m) = (m / T_in) * T_out + 1 + m % T_in
+  EPI_F32 = 4,             // out_f32[m,n]   = acc (+ bias[n] if given)            (tests / generic)
+};
+
+struct GemmArgs {
+  const __nv_bfloat16* A = nullptr;  // [M, K] row-major, leading dimension lda (elements)
+  const __nv_bfloat16* B = nullptr;  // [N, K] row-major (nn.Linear weight layout), leading dimension ldb
+  int64_t lda = 0, ldb = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;       // [N] or nullptr
+  int epilogue = EPI_BIAS_BF16;
+  void* out = nullptr;               // bf16 or fp32 according to the epilogue
+  int64_t ldo = 0;
+  const float* pos = nullptr;        // EPI_PATCH_F32: positional embedding [T_out, N]
+  int tokens_in = 49, tokens_out = 50;
+};
+
+// Persistent TMA + tcgen05 GEMM.  Requires N % 128 == 0 and K % 64 == 0 (every GEMM of the ViT-B/32
+// tower satisfies it); any M.  Returns cudaErrorInvalidValue otherwise.
+cudaError_t launch_gemm(const GemmArgs& a, int* dev_status, int num_sms, cudaStream_t stream);
+// Resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency).
+const char* gemm_init_driver_api();
+
+// ---- row-wise / elementwise kernels ----------------------------------------------------------
+// images [B,3,R,R] (fp32 | bf16 | u8) -> patches [B*G*G, 3*P*P] bf16 (K-major rows for the patch GEMM).
+// apply_norm: fuse tfm_clip (x - mean_c) / std_c ; u8 input is scaled by 1/255 first.
+enum ImageDtype : int { IMG_F32 = 0, IMG_BF16 = 1, IMG_U8 = 2 };
+cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
+                          int apply_norm, __nv_bfloat16* patches, cudaStream_t stream);
+// tokens [B*T, W] fp32: row t==0 of each view := cls + pos[0] (rows t>0 already hold patch+pos);
+// then x := ln_pre(x) written back in place (the residual stream), and y := ln_1(x) as bf16.
+cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
+                            const float* g_pre, const float* b_pre, const float* g1, const float* b1,
+                            __nv_bfloat16* y, cudaStream_t stream);
+// y_bf16[r,:] = LayerNorm(x_f32[r,:]) * g + b   (eps 1e-5, biased variance), W == 768 or any W % 128 == 0 <= 1024
+cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
+                             __nv_bfloat16* y, cudaStream_t stream);
+// out[v,:] = (ln_post(tokens[v*T + 0, :]) @ proj[W,E]) ; optionally / ||.||_2
+cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, const float* g, const float* b,
+                        const float* proj, int E, int normalize, float* out, cudaStream_t stream);
+// qkv [B*T, 3W] bf16 (q | k | v, heads = 64-wide column blocks) -> out [B*T, W] bf16
+cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                             cudaStream_t stream);
+// fp32 -> bf16 cast (weight packing)
+cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
+// W'[rows, cols] (bf16) = W (fp32) + scaling * B[rows, r] @ A[r, cols]   for a row range of a packed weight
+cudaError_t launch_merge_lora_cast(const float* W, const float* A, const float* B, int rows, int cols, int r,
+                                   float scaling, __nv_bfloat16* dst, cudaStream_t stream);
+
+// ---- MTA + head --------------------------------------------------------------------------------
+struct MtaParams {
+  float lambda_y = 0.2f, lambda_q = 4.0f, th = 1e-6f, temperature = 1.0f;
+  double k_frac = 0.3;
+  int max_iter = 5;
+};
+constexpr int MTA_MAX_SETS = 4;
+struct MtaSet {
+  const float* feats;   // [I, V, D] unit rows, row 0 of each image = un-augmented view
+  const float* text;    // [D, C]  (the orientation the reference passes: text_features.t())
+  float* out_mode;      // [I, D]
+  float* out_logits;    // [I, C] = 100 * mode @ text, or nullptr
+};
+// bytes of global scratch launch_mta needs (0 when a problem fits in shared memory)
+size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D);
+// n_sets independent (feats, text) problems per image in one launch: grid = (I, n_sets)
+cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, int D, const MtaParams& p,
+                       float* scratch, cudaStream_t stream);
+
+enum HeadScore : int { SCORE_LOGITS = 0, SCORE_CS = 1, SCORE_CS1 = 2, SCORE_CS2 = 3, SCORE_CS3 = 4, SCORE_CS4 = 5, SCORE_CS5 = 6, SCORE_COUNT = 7 };
+struct HeadArgs {
+  const float *m_pt, *m_hand, *m_zs;  // [I, D] modes
+  const float *T_pt, *T_hand, *T_zs;  // [C, D] text features (unit rows)
+  const float *scale1, *bias1;        // [D]
+  const float *fc_w, *fc_b;           // [C, D], [C]
+  int64_t I;
+  int C, D;
+  int rank_by;                        // HeadScore used for the top-k
+  int k;                              // <= 8
+  int32_t* out_topk;                  // [I, k]
+  float* out_scores;                  // [I, C] (the ranked score) or nullptr
+  float* out_all;                     // [I, SCORE_COUNT, C] or nullptr (tests)
+};
+cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream);
+// Stand-alone pieces of the head (drop-in functions of the reference's Python API)
+cudaError_t launch_channel_lp(const float* feats, int64_t n, int C, int D, const float* scale1, const float* bias1,
+                              const float* fc_w, const float* fc_b, float* out, cudaStream_t stream);
+cudaError_t launch_logit_normalize(const float* in, int64_t n, int C, float* out, cudaStream_t stream);
+cudaError_t launch_cosine_topk(const float* feats, const float* text, int64_t n, int C, int D, float scale, int k,
+                               int32_t* out_topk, float* out_scores, cudaStream_t stream);
+
+}  // namespace jcb

@@ -1,0 +1,346 @@
+// MTA (MeanShift for Test-time Augmentation) mode seeking: the whole solver for one image in ONE CTA.
+//
+// The reference (test.py:1391-1461, twin ood.py:751-820) runs ~100 tiny Jittor kernels and up to 50
+// device->host syncs (`if jt.norm(...) < th`) per image.  Here each image is one thread block: view
+// embeddings, the affinity matrix and all iteration state live in shared memory, the data-dependent
+// early exits are block-uniform branches, and a batch of images is a single launch.
+//
+//   logits = 100 * X T                                     test.py:1393
+//   D = cdist(X, X); bandwidth_i from the k nearest         test.py:1403-1408   (D^2 clamped >= 0, k >= 1)
+//   A = softmax(logits) softmax(logits)^T                   test.py:1411
+//   5 x { y <- softmax((rho + 4 A y) / 0.2)  (<= 5 its)     test.py:1426-1438
+//         m <- normalise(sum rho_i y_i x_i)  (<= 5 its) }   test.py:1443-1453
+//
+// X [V, D] unit rows (row 0 = un-augmented view), T given as [D, C] (the orientation the reference
+// passes: `text_features.t()`), so class-parallel threads read it coalesced.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace jcb {
+
+namespace {
+
+constexpr int MTA_THREADS = 256;
+constexpr int MTA_WARPS = MTA_THREADS / 32;
+constexpr int VB = 8;  // views per register block in the logits GEMM
+
+struct MtaDev {
+  MtaSet sets[MTA_MAX_SETS];  // blockIdx.y selects (feats [I,V,D], text [D,C], out_mode [I,D], out_logits)
+  long long I;
+  int V, C, D, ldA, k;
+  MtaParams p;
+  float* scratch;       // per image: region R (max(V*C, V*D)) + A (V*ldA), only used when !in_smem
+  long long scratch_stride;
+  int in_smem;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();  // protect s_red from the previous use
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < MTA_WARPS; ++w) t += s_red[w];
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* s_red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < MTA_WARPS; ++w) t = fmaxf(t, s_red[w]);
+  return t;
+}
+
+// gaussian_kernel(mode, bandwidth, X)  (test.py:1310-1313): one warp per view
+__device__ __forceinline__ void density_step(const float* __restrict__ X, const float* s_mode, const float* s_bw,
+                                             float* s_dens, int V, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < V; i += MTA_WARPS) {
+    float q = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float t = X[i * D + d] - s_mode[d];
+      q = fmaf(t, t, q);
+    }
+    q = warp_sum(q);
+    if (lane == 0) {
+      const float dist = sqrtf(q);  // jt.norm(...), then dist**2 as the reference does
+      const float bw = s_bw[i];
+      s_dens[i] = expf(-(dist * dist) / (2.0f * bw * bw));
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
+  extern __shared__ __align__(16) float mta_smem[];
+  const int V = a.V, C = a.C, D = a.D, ldA = a.ldA;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long img = blockIdx.x;
+  const MtaSet& set = a.sets[blockIdx.y];
+  const long long problem = static_cast<long long>(blockIdx.y) * a.I + img;
+  const float* __restrict__ Xg = set.feats + img * V * D;
+  const float* __restrict__ Tt = set.text;
+
+  // small state (always in smem)
+  float* s_mode = mta_smem;           // [D]
+  float* s_new = s_mode + D;          // [D]
+  float* s_bw = s_new + D;            // [V]
+  float* s_y = s_bw + V;              // [V]
+  float* s_dens = s_y + V;            // [V]
+  float* s_z = s_dens + V;            // [V]
+  float* s_sq = s_z + V;              // [V]
+  float* s_red = s_sq + V;            // [32]
+  float* s_rows = s_red + 32;         // [MTA_WARPS][V] one distance row per warp
+  float* big = s_rows + MTA_WARPS * V;
+  big = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(big) + 15) & ~static_cast<uintptr_t>(15));
+  // region R (probabilities, later the view embeddings) and the V x V matrix
+  const long long r_elems = static_cast<long long>(V) * (C > D ? C : D);
+  float* R = a.in_smem ? big : a.scratch + problem * a.scratch_stride;
+  float* A = a.in_smem ? big + ((r_elems + 3) & ~3LL) : a.scratch + problem * a.scratch_stride + ((r_elems + 3) & ~3LL);
+
+  // ---- 1. logits = 100 * X T / temperature -> R[v*C + c]      (test.py:1393)
+  {
+    const float scale = 100.0f / a.p.temperature;
+    for (int c0 = 0; c0 < C; c0 += MTA_THREADS) {
+      const int c = c0 + tid;
+      const int cc = c < C ? c : C - 1;
+      for (int v0 = 0; v0 < V; v0 += VB) {
+        float acc[VB];
+#pragma unroll
+        for (int j = 0; j < VB; ++j) acc[j] = 0.f;
+        for (int d = 0; d < D; d += 4) {
+          float t[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) t[e] = __ldg(Tt + static_cast<long long>(d + e) * C + cc);
+#pragma unroll
+          for (int j = 0; j < VB; ++j) {
+            const int v = v0 + j < V ? v0 + j : V - 1;
+            const float4 x = __ldg(reinterpret_cast<const float4*>(Xg + v * D + d));  // warp-uniform address
+            acc[j] = fmaf(x.x, t[0], acc[j]);
+            acc[j] = fmaf(x.y, t[1], acc[j]);
+            acc[j] = fmaf(x.z, t[2], acc[j]);
+            acc[j] = fmaf(x.w, t[3], acc[j]);
+          }
+        }
+        if (c < C) {
+#pragma unroll
+          for (int j = 0; j < VB; ++j)
+            if (v0 + j < V) R[(v0 + j) * C + c] = acc[j] * scale;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 2. row softmax in place
+  for (int v = warp; v < V; v += MTA_WARPS) {
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, R[v * C + c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float e = expf(R[v * C + c] - mx);
+      R[v * C + c] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int c = lane; c < C; c += 32) R[v * C + c] *= inv;
+  }
+  __syncthreads();
+  // ---- 3. affinity A = P P^T                                    (test.py:1411)
+  for (int idx = tid; idx < V * V; idx += MTA_THREADS) {
+    const int i = idx / V, j = idx % V;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(R[i * C + c], R[j * C + c], s);
+    A[i * ldA + j] = s;
+  }
+  __syncthreads();
+  // ---- 4. bring the view embeddings on chip (region R is free now)
+  const float* X;
+  if (a.in_smem) {
+    for (int i = tid; i < V * D / 4; i += MTA_THREADS)
+      reinterpret_cast<float4*>(R)[i] = __ldg(reinterpret_cast<const float4*>(Xg) + i);
+    X = R;
+  } else {
+    X = Xg;
+  }
+  __syncthreads();
+  // ---- 5. pairwise distances and per-view bandwidth             (test.py:1314-1318, :1403-1408)
+  for (int i = warp; i < V; i += MTA_WARPS) {
+    float q = 0.f;
+    for (int d = lane; d < D; d += 32) q = fmaf(X[i * D + d], X[i * D + d], q);
+    q = warp_sum(q);
+    if (lane == 0) s_sq[i] = q;
+  }
+  __syncthreads();
+  {
+    float* my_row = s_rows + warp * V;
+    for (int i = warp; i < V; i += MTA_WARPS) {
+      for (int j = 0; j < V; ++j) {
+        float dot = 0.f;
+        for (int d = lane; d < D; d += 32) dot = fmaf(X[i * D + d], X[j * D + d], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) {
+          const float d2 = s_sq[i] - 2.0f * dot + s_sq[j];
+          my_row[j] = sqrtf(fmaxf(d2, 0.0f));
+        }
+      }
+      __syncwarp();
+      // mean of the squared k smallest distances, skipping rank 0 (the point itself)
+      float acc = 0.f;
+      for (int j = lane; j < V; j += 32) {
+        const float dj = my_row[j];
+        int rank = 0;
+        for (int l = 0; l < V; ++l) {
+          const float dl = my_row[l];
+          rank += (dl < dj || (dl == dj && l < j)) ? 1 : 0;
+        }
+        if (rank >= 1 && rank <= a.k) acc += dj * dj;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) s_bw[i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
+  for (int i = tid; i < V; i += MTA_THREADS) s_y[i] = 1.0f / static_cast<float>(V);
+  for (int d = tid; d < D; d += MTA_THREADS) s_mode[d] = X[d];
+  __syncthreads();
+
+  const float inv_lambda_y = 1.0f / a.p.lambda_y;
+  for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
+    density_step(X, s_mode, s_bw, s_dens, V, D);                   // :1426
+    for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
+      float zmax = -INFINITY;
+      for (int i = tid; i < V; i += MTA_THREADS) {
+        float s = 0.f;
+        for (int j = 0; j < V; ++j) s = fmaf(A[i * ldA + j], s_y[j], s);
+        const float z = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
+        s_z[i] = z;
+        zmax = fmaxf(zmax, z);
+      }
+      zmax = block_max(zmax, s_red);
+      float zs = 0.f;
+      for (int i = tid; i < V; i += MTA_THREADS) {
+        const float e = expf(s_z[i] - zmax);
+        s_z[i] = e;
+        zs += e;
+      }
+      zs = block_sum(zs, s_red);
+      const float inv = 1.0f / zs;
+      float diff = 0.f;
+      for (int i = tid; i < V; i += MTA_THREADS) {
+        const float yn = s_z[i] * inv;
+        const float t = s_y[i] - yn;
+        diff = fmaf(t, t, diff);
+        s_z[i] = yn;
+      }
+      diff = block_sum(diff, s_red);
+      // all threads finished reading s_y inside the A*y products before block_max's barrier
+      for (int i = tid; i < V; i += MTA_THREADS) s_y[i] = s_z[i];
+      __syncthreads();
+      if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1436
+    }
+    for (int it = 1;; ++it) {                                      // mode loop :1443-1453
+      density_step(X, s_mode, s_bw, s_dens, V, D);                 // :1446
+      float wsum = 0.f;
+      for (int i = tid; i < V; i += MTA_THREADS) {
+        const float w = s_dens[i] * s_y[i];                        // :1447
+        s_z[i] = w;
+        wsum += w;
+      }
+      wsum = block_sum(wsum, s_red);
+      float nrm = 0.f;
+      for (int d = tid; d < D; d += MTA_THREADS) {
+        float s = 0.f;
+        for (int i = 0; i < V; ++i) s = fmaf(s_z[i], X[i * D + d], s);
+        s = s / wsum;                                              // :1448
+        s_new[d] = s;
+        nrm = fmaf(s, s, nrm);
+      }
+      nrm = block_sum(nrm, s_red);
+      const float inv = 1.0f / sqrtf(nrm);                         // :1449
+      float diff = 0.f;
+      for (int d = tid; d < D; d += MTA_THREADS) {
+        const float m = s_new[d] * inv;
+        const float t = s_mode[d] - m;
+        diff = fmaf(t, t, diff);
+        s_new[d] = m;
+      }
+      diff = block_sum(diff, s_red);
+      for (int d = tid; d < D; d += MTA_THREADS) s_mode[d] = s_new[d];
+      __syncthreads();
+      if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
+    }
+  }
+
+  // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
+  for (int d = tid; d < D; d += MTA_THREADS) set.out_mode[img * D + d] = s_mode[d];
+  if (set.out_logits) {
+    for (int c = tid; c < C; c += MTA_THREADS) {
+      float s = 0.f;
+      for (int d = 0; d < D; ++d) s = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s);
+      set.out_logits[img * C + c] = s * 100.0f;
+    }
+  }
+}
+
+constexpr size_t MTA_SMEM_LIMIT = 220 * 1024;
+
+size_t small_state_bytes(int V, int D) { return sizeof(float) * (2 * D + (5 + MTA_WARPS) * V + 32) + 16; }
+long long big_elems(int V, int C, int D, int ldA) {
+  const long long r = static_cast<long long>(V) * (C > D ? C : D);
+  return ((r + 3) & ~3LL) + static_cast<long long>(V) * ldA;
+}
+
+}  // namespace
+
+static bool mta_fits_smem(int V, int C, int D) {
+  return small_state_bytes(V, D) + static_cast<size_t>(big_elems(V, C, D, V | 1)) * sizeof(float) <= MTA_SMEM_LIMIT;
+}
+
+size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D) {
+  if (mta_fits_smem(V, C, D)) return 0;
+  return static_cast<size_t>(n_problems) * static_cast<size_t>(big_elems(V, C, D, V | 1)) * sizeof(float);
+}
+
+cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, int D, const MtaParams& p,
+                       float* scratch, cudaStream_t stream) {
+  if (V < 1 || C < 1 || D < 32 || D % 32 != 0 || D > 1024) return cudaErrorInvalidValue;
+  if (V > 2048) return cudaErrorInvalidValue;  // small state must stay well inside shared memory
+  if (n_sets < 1 || n_sets > MTA_MAX_SETS) return cudaErrorInvalidValue;
+  if (I == 0) return cudaSuccess;
+  MtaDev a;
+  for (int s = 0; s < n_sets; ++s) a.sets[s] = sets[s];
+  for (int s = n_sets; s < MTA_MAX_SETS; ++s) a.sets[s] = sets[0];
+  a.I = I; a.V = V; a.C = C; a.D = D;
+  a.ldA = V | 1;  // odd row stride: conflict-free column walks
+  // int(0.3 * (V - 1)) in double precision, exactly as the Python expression (test.py:1405)
+  int k = static_cast<int>(p.k_frac * static_cast<double>(V - 1));
+  a.k = k < 1 ? 1 : k;
+  a.p = p;
+  const size_t small = small_state_bytes(V, D);
+  const long long be = big_elems(V, C, D, a.ldA);
+  a.in_smem = mta_fits_smem(V, C, D) ? 1 : 0;
+  if (!a.in_smem && scratch == nullptr) return cudaErrorInvalidValue;
+  a.scratch = scratch;
+  a.scratch_stride = be;
+  const size_t smem = a.in_smem ? small + static_cast<size_t>(be) * sizeof(float) : small;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(MTA_SMEM_LIMIT));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
+  mta_kernel<<<grid, MTA_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace jcb

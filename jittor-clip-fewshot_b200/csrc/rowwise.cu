@@ -1,0 +1,328 @@
+// Bandwidth-bound kernels of the image tower: im2col (+ CLIP normalisation), cls/pos + ln_pre + ln_1,
+// LayerNorm, the ln_post + projection + L2-norm tail, and the weight-packing helpers.
+// All are warp-per-row with 128-bit loads and shuffle reductions; fp32 statistics throughout.
+//
+// Reference: jclip/model.py:17-21 (LayerNorm), :105-115 (conv1 as patches, cls, pos, ln_pre),
+// :121-124 (ln_post, proj), test.py:1301 (tfm_clip), test.py:1706 (L2 normalisation),
+// test.py:310-313 (merge_BA).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace jcb {
+
+namespace {
+
+constexpr float LN_EPS = 1e-5f;  // Jittor nn.LayerNorm default
+
+__constant__ float c_clip_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+// ------------------------------------------------------------------------------------------ im2col
+template <int DT>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const void* __restrict__ images, long long n_views, int R, int P, int apply_norm,
+              __nv_bfloat16* __restrict__ patches) {
+  const int G = R / P;
+  const int K = 3 * P * P;
+  const int chunks_per_row = K / 8;
+  const long long total = n_views * G * G * chunks_per_row;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long row = idx / chunks_per_row;         // (view, py, px)
+  const int col = static_cast<int>(idx % chunks_per_row) * 8;  // (c, i, j) with j % 8 == 0
+  const int c = col / (P * P);
+  const int i = (col % (P * P)) / P;
+  const int j = col % P;
+  const long long b = row / (G * G);
+  const int pidx = static_cast<int>(row % (G * G));
+  const int py = pidx / G, px = pidx % G;
+  const long long src = ((b * 3 + c) * R + (py * P + i)) * R + px * P + j;
+  float f[8];
+  if (DT == IMG_F32) {
+    const float4* s = reinterpret_cast<const float4*>(static_cast<const float*>(images) + src);
+    const float4 a = __ldg(s), d = __ldg(s + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = d.x; f[5] = d.y; f[6] = d.z; f[7] = d.w;
+  } else if (DT == IMG_BF16) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(images) + src));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+  } else {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(images) + src));
+    const uint8_t* u = reinterpret_cast<const uint8_t*>(&a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = static_cast<float>(u[e]) * (1.0f / 255.0f);
+  }
+  if (apply_norm) {
+    const float m = c_clip_mean[c], s = c_clip_std[c];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (f[e] - m) / s;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(patches + row * K + col) = o;
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+template <int NV>
+__device__ __forceinline__ void row_stats(const float4 (&v)[NV], int W, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) / static_cast<float>(W);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) / static_cast<float>(W);  // biased variance
+  rstd = 1.0f / sqrtf(var + LN_EPS);
+}
+
+template <int NV>
+__device__ __forceinline__ void normalize_row(float4 (&v)[NV], float mean, float rstd, const float* __restrict__ g,
+                                              const float* __restrict__ b, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
+    v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
+    v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
+    v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void store_row_bf16(const float4 (&v)[NV], __nv_bfloat16* __restrict__ y, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint2 o;
+    o.x = pack_bf16x2(v[i].x, v[i].y);
+    o.y = pack_bf16x2(v[i].z, v[i].w);
+    reinterpret_cast<uint2*>(y)[lane + 32 * i] = o;
+  }
+}
+
+constexpr int LN_WARPS = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_kernel(const float* __restrict__ x, long long rows, const float* __restrict__ g,
+                 const float* __restrict__ b, __nv_bfloat16* __restrict__ y) {
+  constexpr int W = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV];
+  const float4* xr = reinterpret_cast<const float4*>(x + row * W);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  float mean, rstd;
+  row_stats<NV>(v, W, mean, rstd);
+  normalize_row<NV>(v, mean, rstd, g, b, lane);
+  store_row_bf16<NV>(v, y + row * W, lane);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* __restrict__ cls,
+                const float* __restrict__ pos, const float* __restrict__ g_pre, const float* __restrict__ b_pre,
+                const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y) {
+  constexpr int W = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = static_cast<int>(row % T);
+  float4 v[NV];
+  float4* xr = reinterpret_cast<float4*>(tokens + row * W);
+  if (t == 0) {
+    // class token: class_embedding + positional_embedding[0]   (jclip/model.py:109-114)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cls) + lane + 32 * i);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + lane + 32 * i);
+      v[i] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];  // patch embedding + pos (GEMM epilogue)
+  }
+  float mean, rstd;
+  row_stats<NV>(v, W, mean, rstd);
+  normalize_row<NV>(v, mean, rstd, g_pre, b_pre, lane);  // ln_pre -> residual stream
+#pragma unroll
+  for (int i = 0; i < NV; ++i) xr[lane + 32 * i] = v[i];
+  row_stats<NV>(v, W, mean, rstd);
+  normalize_row<NV>(v, mean, rstd, g1, b1, lane);        // layer 0's ln_1
+  store_row_bf16<NV>(v, y + row * W, lane);
+}
+
+// ------------------------------------------------------------------------------------------ tail
+constexpr int TAIL_VIEWS = 8;
+constexpr int TAIL_THREADS = 256;
+
+template <int NV, int E>
+__global__ void __launch_bounds__(TAIL_THREADS)
+tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const float* __restrict__ g,
+            const float* __restrict__ b, const float* __restrict__ proj, int normalize, float* __restrict__ out) {
+  constexpr int W = NV * 128;
+  constexpr int EPT = E / TAIL_THREADS;  // outputs per thread
+  __shared__ __align__(16) float s_x[TAIL_VIEWS][W];
+  __shared__ float s_part[TAIL_VIEWS][TAIL_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long v0 = static_cast<long long>(blockIdx.x) * TAIL_VIEWS;
+  {  // ln_post on the CLS row of view v0 + warp  (jclip/model.py:121)
+    const long long view = v0 + warp;
+    float4 v[NV];
+    if (view < n_views) {
+      const float4* xr = reinterpret_cast<const float4*>(tokens + view * T * W);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+      float mean, rstd;
+      row_stats<NV>(v, W, mean, rstd);
+      normalize_row<NV>(v, mean, rstd, g, b, lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(s_x[warp])[lane + 32 * i] = v[i];
+  }
+  __syncthreads();
+  float acc[TAIL_VIEWS][EPT];
+#pragma unroll
+  for (int v = 0; v < TAIL_VIEWS; ++v)
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc[v][e] = 0.f;
+  for (int k = 0; k < W; ++k) {  // x @ proj  (jclip/model.py:123-124), fp32
+    float pw[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) pw[e] = __ldg(proj + static_cast<long long>(k) * E + threadIdx.x + e * TAIL_THREADS);
+#pragma unroll
+    for (int v = 0; v < TAIL_VIEWS; ++v) {
+      const float xv = s_x[v][k];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) acc[v][e] = fmaf(xv, pw[e], acc[v][e]);
+    }
+  }
+  // f / ||f||_2  (test.py:1706)
+#pragma unroll
+  for (int v = 0; v < TAIL_VIEWS; ++v) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) s += acc[v][e] * acc[v][e];
+    s = warp_sum(s);
+    if (lane == 0) s_part[v][warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < TAIL_VIEWS; ++v) {
+    const long long view = v0 + v;
+    if (view >= n_views) break;
+    float inv = 1.0f;
+    if (normalize) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < TAIL_THREADS / 32; ++w) s += s_part[v][w];
+      inv = 1.0f / sqrtf(s);
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) out[view * E + threadIdx.x + e * TAIL_THREADS] = acc[v][e] * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ packing
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// dst = bf16(W + scaling * B @ A), fp32 accumulation: the merge the reference's eval path is
+// mathematically equal to (test.py:388-398 applies W x + s x (BA)^T un-merged).
+__global__ void merge_lora_cast_kernel(const float* __restrict__ W, const float* __restrict__ A,
+                                       const float* __restrict__ B, int rows, int cols, int r, float scaling,
+                                       __nv_bfloat16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int o = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  float d = 0.f;
+  for (int k = 0; k < r; ++k) d = fmaf(B[o * r + k], A[k * cols + c], d);
+  dst[i] = __float2bfloat16_rn(W[i] + scaling * d);
+}
+
+}  // namespace
+
+cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
+                          int apply_norm, __nv_bfloat16* patches, cudaStream_t stream) {
+  if (resolution % patch != 0 || patch % 8 != 0) return cudaErrorInvalidValue;
+  const int G = resolution / patch;
+  const long long total = n_views * G * G * (3 * patch * patch / 8);
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  switch (img_dtype) {
+    case IMG_F32: im2col_kernel<IMG_F32><<<grid, 256, 0, stream>>>(images, n_views, resolution, patch, apply_norm, patches); break;
+    case IMG_BF16: im2col_kernel<IMG_BF16><<<grid, 256, 0, stream>>>(images, n_views, resolution, patch, apply_norm, patches); break;
+    case IMG_U8: im2col_kernel<IMG_U8><<<grid, 256, 0, stream>>>(images, n_views, resolution, patch, apply_norm, patches); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+#define JCB_DISPATCH_NV(W, CALL)               \
+  switch ((W) / 128) {                         \
+    case 4: { constexpr int NV = 4; CALL; } break; \
+    case 6: { constexpr int NV = 6; CALL; } break; \
+    case 8: { constexpr int NV = 8; CALL; } break; \
+    default: return cudaErrorInvalidValue;     \
+  }
+
+cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
+                             __nv_bfloat16* y, cudaStream_t stream) {
+  if (W % 128 != 0) return cudaErrorInvalidValue;
+  if (rows == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
+  JCB_DISPATCH_NV(W, (layernorm_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(x, rows, g, b, y)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
+                            const float* g_pre, const float* b_pre, const float* g1, const float* b1,
+                            __nv_bfloat16* y, cudaStream_t stream) {
+  if (W % 128 != 0) return cudaErrorInvalidValue;
+  const long long rows = n_views * T;
+  if (rows == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
+  JCB_DISPATCH_NV(W, (embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(tokens, rows, T, cls, pos, g_pre,
+                                                                           b_pre, g1, b1, y)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, const float* g, const float* b,
+                        const float* proj, int E, int normalize, float* out, cudaStream_t stream) {
+  if (W % 128 != 0 || E != 512) return cudaErrorInvalidValue;
+  if (n_views == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((n_views + TAIL_VIEWS - 1) / TAIL_VIEWS);
+  JCB_DISPATCH_NV(W, (tail_kernel<NV, 512><<<grid, TAIL_THREADS, 0, stream>>>(tokens, n_views, T, g, b, proj,
+                                                                             normalize, out)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_lora_cast(const float* W, const float* A, const float* B, int rows, int cols, int r,
+                                   float scaling, __nv_bfloat16* dst, cudaStream_t stream) {
+  const long long n = static_cast<long long>(rows) * cols;
+  if (n == 0) return cudaSuccess;
+  merge_lora_cast_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(W, A, B, rows, cols, r,
+                                                                                    scaling, dst);
+  return cudaGetLastError();
+}
+
+}  // namespace jcb

@@ -1,0 +1,157 @@
+"""The whole hot path for a shard of images in one native call, and the batched forms of the
+reference's per-image evaluation loops.
+
+The reference iterates `for image in loader:` with batch size 1 and, per image, runs encode_image on
+the 1+N views, three `solve_mta`, two `channel_lp`, three `logit_normalize`, three cosine-logit
+matmuls, the fusion and `topk(5)` -- each a handful of Jittor kernels plus a host sync
+(test.py:1692-1742, :1759-1779, ood.py:867-883).  `HotPath.evaluate_base` does the same arithmetic
+for I images at once with ONE C-ABI call (jcb_pipeline): the image tower over I*(N+1) views in
+L2-sized chunks, one MTA launch (3 problems per image), one head launch.
+"""
+import re
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import check
+from .methods import Channel_LP, cosine_topk, solve_mta_batched
+from .runtime import as_torch, dev_f32, get_context, img_dtype_code, ptr
+
+OOD_BASE_MAX = 372   # reference ood.py:880 routes `pred <= 372` to the base list (bug-compatible, SURVEY C-2)
+
+
+class TextBank:
+    """The cached text embeddings of the hot path, resident on the device in both orientations:
+    T [C, D] for the cosine logits (test.py:1729-1731) and T^T [D, C] for solve_mta (test.py:1708)."""
+
+    def __init__(self, text_pt, text_hand, text_zs, device):
+        self.device = torch.device(device)
+        self.pt, self.hand, self.zs = (dev_f32(t, self.device) for t in (text_pt, text_hand, text_zs))
+        self.pt_t, self.hand_t, self.zs_t = (t.t().contiguous() for t in (self.pt, self.hand, self.zs))
+        self.num_classes, self.dim = self.pt.shape
+
+
+class HotPath:
+    """encode_image -> L2 normalise -> solve_mta x3 -> Channel_LP / logit_normalize / fusion -> top-k."""
+
+    def __init__(self, clip_model, text_bank, channel_lp, clip_model_zs=None, rank_by="cs5", k=5,
+                 apply_clip_norm=True):
+        self.model, self.model_zs = clip_model, clip_model_zs
+        self.text, self.lp = text_bank, channel_lp
+        self.rank_by, self.k, self.apply_clip_norm = rank_by, k, apply_clip_norm
+
+    def _args(self, images, I, V, on_host, out_topk, out_feats, out_scores, device):
+        a = _capi.PipelineArgs()
+        a.images = images.data_ptr()
+        a.img_dtype = img_dtype_code(images)
+        a.images_on_host = int(on_host)
+        a.n_images, a.n_views = I, V
+        a.apply_clip_norm = int(self.apply_clip_norm)
+        tb = self.text
+        a.text_pt_dev, a.text_hand_dev, a.text_zs_dev = tb.pt.data_ptr(), tb.hand.data_ptr(), tb.zs.data_ptr()
+        a.text_pt_t_dev, a.text_hand_t_dev, a.text_zs_t_dev = tb.pt_t.data_ptr(), tb.hand_t.data_ptr(), tb.zs_t.data_ptr()
+        a.lp = self.lp.head_struct(device)
+        a.n_classes = tb.num_classes
+        a.rank_by = _capi.SCORE_INDEX[self.rank_by]
+        a.k = self.k
+        a.topk_on_host = int(not out_topk.is_cuda)
+        a.out_topk = out_topk.data_ptr()
+        a.out_feats_dev = out_feats.data_ptr() if out_feats is not None else None
+        a.out_scores_dev = out_scores.data_ptr() if out_scores is not None else None
+        return a
+
+    def evaluate_base(self, images, return_feats=False, return_scores=False, topk_to_host=None):
+        """images [I, V, 3, R, R] (V = N+1 views, view 0 un-augmented; reference test.py:1700), float32 /
+        bfloat16 / uint8, on the device or in (pinned) host memory.  Returns int32 top-k [I, k] -- on the
+        host when the images were on the host (the end-to-end call), else on the device."""
+        t = as_torch(images)
+        if t.dim() != 5:
+            raise ValueError(f"expected images [I, V, 3, R, R], got {tuple(t.shape)}")
+        t = t.contiguous()
+        I, V = t.shape[0], t.shape[1]
+        on_host = not t.is_cuda
+        device = self.text.device
+        if topk_to_host is None:
+            topk_to_host = on_host
+        with torch.cuda.device(device):
+            ctx, vit = self.model.visual._engine(device)
+            vit_zs = self.model_zs.visual._engine(device)[1] if self.model_zs is not None else None
+            ctx.bind_current_stream()
+            topk = torch.empty((I, self.k), dtype=torch.int32, device="cpu" if topk_to_host else device,
+                               pin_memory=topk_to_host)
+            feats = torch.empty((I * V, self.text.dim), dtype=torch.float32, device=device) if return_feats else None
+            scores = torch.empty((I, self.text.num_classes), dtype=torch.float32, device=device) if return_scores else None
+            a = self._args(t, I, V, on_host, topk, feats, scores, device)
+            check(ctx.lib.jcb_pipeline(vit, vit_zs, _capi.byref(a)), ctx.handle)
+        out = [topk]
+        if return_feats:
+            out.append(feats.view(I, V, -1))
+        if return_scores:
+            out.append(scores)
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def evaluate_new(self, images, text_zs=None):
+        """evaluate_new (test.py:1759-1779): zero-shot tower -> solve_mta -> 100 f T^T -> top-5."""
+        model = self.model_zs if self.model_zs is not None else self.model
+        return evaluate_new_batch(model, images, self.text.zs if text_zs is None else text_zs, k=self.k,
+                                  apply_clip_norm=self.apply_clip_norm)
+
+
+def _encode_views(model, images, apply_clip_norm):
+    t = as_torch(images)
+    I, V = t.shape[0], t.shape[1]
+    f = model.visual(t.reshape(I * V, *t.shape[2:]), apply_clip_norm=apply_clip_norm, normalize=True)
+    return as_torch(f).view(I, V, -1)
+
+
+def evaluate_new_batch(model, images, text_zs, k=5, apply_clip_norm=True):
+    feats = _encode_views(model, images, apply_clip_norm)
+    if not feats.is_cuda:
+        feats = feats.cuda()
+    tz = dev_f32(text_zs, feats.device)
+    mode = solve_mta_batched(feats, tz.t().contiguous())
+    return cosine_topk(mode, tz, k=k)
+
+
+def split_ood_batch(model, images, text_features, apply_clip_norm=False):
+    """split_ood (ood.py:857-883): zero-shot MTA logits -> argmax -> base/new routing.
+    Returns (pred [I] int32, is_base [I] bool) with `is_base = pred <= 372` exactly as ood.py:880.
+    ood.py normalises in the PIL transform, hence apply_clip_norm defaults to False here."""
+    feats = _encode_views(model, images, apply_clip_norm)
+    if not feats.is_cuda:
+        feats = feats.cuda()
+    tz = dev_f32(text_features, feats.device)
+    mode = solve_mta_batched(feats, tz.t().contiguous())
+    pred = cosine_topk(mode, tz, k=1)[:, 0]
+    return pred, pred <= OOD_BASE_MAX
+
+
+# ---- result files (reference test.py:1738-1747, :1788-1796, :1837-1849; ood.py:866-883) ----------
+def format_result_line(impath, labels):
+    """`f"{impath} {top5_str}"` where impath is the batch-1 loader's list repr, e.g. "['a/b.jpg'] 1 2 3 4 5"."""
+    return f"{impath} {' '.join(map(str, [int(x) for x in labels]))}"
+
+
+def process_line(line):
+    """test.py:1788-1796: replace "['dir/file.jpg']" by "file.jpg"."""
+    m = re.search(r"\['(.*?)'\]", line)
+    if m:
+        line = line.replace(m.group(0), m.group(1).split('/')[-1])
+    return line
+
+
+def write_results(path, impaths, topk, clean=False):
+    topk = as_torch(topk).cpu().numpy()
+    with open(path, "w") as f:
+        for p, row in zip(impaths, topk):
+            line = format_result_line([p] if not isinstance(p, list) else p, row)
+            f.write((process_line(line) if clean else line) + "\n")
+
+
+def write_ood_split(base_path, new_path, impaths, is_base):
+    """ood.py:879-883: one path per line into TestSetB_1.txt (base) / TestSetB_2.txt (new)."""
+    is_base = as_torch(is_base).cpu().numpy().astype(bool)
+    with open(base_path, "w") as fb, open(new_path, "w") as fn:
+        for p, b in zip(impaths, is_base):
+            (fb if b else fn).write(f"{p}\n")

@@ -1,0 +1,177 @@
+"""GPU parity of `encode_image` (CLIP ViT-B/32 image tower, LoRA on q/k/v/o) against the fp32 CPU
+oracle, through the reference-facing Python API (`build_model`, `apply_lora`, `model.encode_image`).
+
+Tolerances (north_star): embedding cosine similarity >= 0.999 against the fp32 oracle.  The GEMM
+operands are bf16 (fp32 accumulate, fp32 residual stream / LayerNorm / softmax), so element-wise
+differences of the unnormalised 512-d embedding are bounded here at 3 % of its RMS, and the
+measured cosine is asserted at >= 0.9995 (tighter than the north-star bound).
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(params=("q", "k", "v"), encoder="vision"):
+    return types.SimpleNamespace(encoder=encoder, position="all", params=list(params), r=4, alpha=1,
+                                 dropout_rate=0.25, backbone="ViT-B/32")
+
+
+def _cos(a, b):
+    a, b = a.double(), b.double()
+    return (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1))
+
+
+@pytest.fixture(scope="module")
+def tower(jb):
+    sd = jb.synth.make_vit_state_dict(seed=0)
+    return sd, jb.jclip.build_model(sd)
+
+
+def test_encode_image_zero_shot_matches_oracle(jb, cuda_dev, tower):
+    from oracle import vit_encode_image
+    sd, model = tower
+    imgs = jb.synth.clip_normalize(jb.synth.make_views(3, 2, 4).reshape(8, 3, 224, 224))
+    ref = vit_encode_image(sd, imgs)
+    out = model.encode_image(torch.from_numpy(imgs).to(cuda_dev)).cpu()
+    assert out.shape == (8, 512) and out.dtype == torch.float32
+    cos = _cos(out, ref)
+    assert cos.min() >= 0.9995, cos
+    rms = ref.pow(2).mean().sqrt()
+    assert (out - ref).abs().max() <= 0.03 * rms
+
+
+def test_tokens_before_ln_post(jb, cuda_dev, tower):
+    """Residual stream after 12 blocks, every token (not only CLS): catches attention / layout bugs the
+    CLS-only embedding could hide."""
+    from oracle import vit_encode_image
+    sd, model = tower
+    imgs = jb.synth.clip_normalize(jb.synth.make_views(4, 1, 3).reshape(3, 3, 224, 224))
+    ref = vit_encode_image(sd, imgs, return_tokens=True)
+    out = model.visual.debug_tokens(torch.from_numpy(imgs).to(cuda_dev)).cpu()
+    assert out.shape == ref.shape == (3, 50, 768)
+    cos = _cos(out.reshape(-1, 768), ref.reshape(-1, 768))
+    assert cos.min() >= 0.9995, cos.min()
+
+
+@pytest.mark.parametrize("params", [("q", "k", "v"), ("q", "v"), ("q", "k", "v", "o")])
+def test_encode_image_lora_matches_oracle(jb, cuda_dev, params):
+    """LoRA applied un-merged in the oracle (reference eval path, test.py:388-398) vs merged in fp32
+    then cast to bf16 on the device."""
+    from oracle import vit_encode_image
+    sd = jb.synth.make_vit_state_dict(seed=1)
+    model = jb.jclip.build_model(sd)
+    layers = jb.apply_lora(_args(params), model)
+    assert len(layers) == 12
+    lora = jb.synth.make_lora(seed=7, params=[p for p in params], b_std=0.02)
+    for i, layer in enumerate(layers):
+        for name, (A, B) in lora[i].items():
+            getattr(layer, name).w_lora_A.data = A
+            getattr(layer, name).w_lora_B.data = B
+    imgs = jb.synth.make_views(5, 1, 6).reshape(6, 3, 224, 224)
+    ref = vit_encode_image(sd, imgs, lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    ref0 = vit_encode_image(sd, imgs, lora=None, apply_clip_norm=True, normalize=True)
+    x = torch.from_numpy(imgs).to(cuda_dev)
+    out = model.visual(x, apply_clip_norm=True, normalize=True).cpu()
+    cos = _cos(out, ref)
+    assert cos.min() >= 0.9995, cos
+    assert (out.norm(dim=-1) - 1).abs().max() < 1e-5
+    # the adapters must actually matter for this test to mean anything
+    assert _cos(ref, ref0).min() < 0.9999
+    assert (_cos(out, ref) > _cos(out, ref0)).all()
+
+
+def test_lora_update_refreshes_packed_weights(jb, cuda_dev, tower):
+    sd, _ = tower
+    model = jb.jclip.build_model(sd)
+    layers = jb.apply_lora(_args(), model)
+    x = torch.from_numpy(jb.synth.make_views(6, 1, 2).reshape(2, 3, 224, 224)).to(cuda_dev)
+    f0 = model.visual(x, apply_clip_norm=True, normalize=True).clone()      # B = 0 -> no-op adapters
+    rng = np.random.default_rng(0)
+    layers[3].q_proj.w_lora_B.data = (0.05 * rng.standard_normal((768, 4))).astype(np.float32)
+    f1 = model.visual(x, apply_clip_norm=True, normalize=True)
+    assert not torch.allclose(f0, f1, atol=1e-4)
+    layers[3].q_proj.w_lora_B.data = np.zeros((768, 4), np.float32)
+    f2 = model.visual(x, apply_clip_norm=True, normalize=True)
+    assert torch.equal(f0, f2)
+
+
+@pytest.mark.parametrize("dtype", ["u8", "bf16"])
+def test_image_dtypes(jb, cuda_dev, tower, dtype):
+    from oracle import vit_encode_image
+    sd, model = tower
+    img = jb.synth.make_views(7, 1, 3).reshape(3, 3, 224, 224)
+    if dtype == "u8":
+        q = np.round(img * 255).astype(np.uint8)
+        ref_in, x = q.astype(np.float32) / 255.0, torch.from_numpy(q)
+    else:
+        x = torch.from_numpy(img).to(torch.bfloat16)
+        ref_in = x.float().numpy()
+    ref = vit_encode_image(sd, ref_in, apply_clip_norm=True, normalize=True)
+    out = model.visual(x.to(cuda_dev), apply_clip_norm=True, normalize=True).cpu()
+    assert _cos(out, ref).min() >= 0.9995
+
+
+def test_host_entry_point_and_chunking(jb, cuda_dev, tower):
+    """jcb_encode_image_host (pinned host in, host out, chunks double-buffered on a copy stream) must
+    equal the device-resident call bit for bit, for a view count that is not a multiple of the chunk."""
+    sd, model = tower
+    img = jb.synth.make_views(8, 1, 23).reshape(23, 3, 224, 224)
+    dev_out = model.visual(torch.from_numpy(img).to(cuda_dev), apply_clip_norm=True, normalize=True).cpu()
+    ctx = jb.get_context(cuda_dev)
+    ctx.set_chunk_views(5)
+    try:
+        host_out = model.visual(torch.from_numpy(img).pin_memory(), apply_clip_norm=True, normalize=True)
+        np_out = model.visual(img, apply_clip_norm=True, normalize=True)
+    finally:
+        ctx.set_chunk_views(2048)
+    assert not host_out.is_cuda and isinstance(np_out, np.ndarray)
+    assert torch.equal(host_out, dev_out)
+    assert np.array_equal(np_out, dev_out.numpy())
+
+
+def test_dlpack_entry_point(jb, cuda_dev, tower):
+    sd, model = tower
+    x = torch.from_numpy(jb.synth.make_views(9, 1, 4).reshape(4, 3, 224, 224)).to(cuda_dev)
+    ref = model.visual(x, apply_clip_norm=True, normalize=True)
+    out = torch.zeros(4, 512, device=cuda_dev)
+    model.visual.execute_dlpack(x, out, apply_clip_norm=True, normalize=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+
+
+def test_empty_and_bad_inputs(jb, cuda_dev, tower):
+    sd, model = tower
+    out = model.encode_image(torch.zeros(0, 3, 224, 224, device=cuda_dev))
+    assert out.shape == (0, 512)
+    with pytest.raises(ValueError):
+        model.encode_image(torch.zeros(2, 3, 200, 224, device=cuda_dev))
+    with pytest.raises(TypeError):
+        model.encode_image(torch.zeros(2, 3, 224, 224, dtype=torch.int32, device=cuda_dev))
+
+
+def test_real_lora_pickle_if_present(jb, cuda_dev, tmp_path):
+    """The LoRA pickle layout: round-trip through save_lora / load_lora with
+    encoder='both' (text layers first, vision layers 12..23), then encode."""
+    sd = jb.synth.make_vit_state_dict(seed=2, text_layers=12)
+    model = jb.jclip.build_model(sd)
+    args = _args(encoder="both")
+    layers = jb.apply_lora(args, model)
+    assert len(layers) == 24
+    rng = np.random.default_rng(3)
+    for layer in layers:
+        for name in ("q_proj", "k_proj", "v_proj"):
+            lin = getattr(layer, name)
+            lin.w_lora_B.data = (0.01 * rng.standard_normal(lin.w_lora_B.shape)).astype(np.float32)
+    args.filename = "t"
+    path = jb.save_lora(args, 0, layers, save_dir=str(tmp_path))
+    x = torch.from_numpy(jb.synth.make_views(10, 1, 2).reshape(2, 3, 224, 224)).to(cuda_dev)
+    f_a = model.visual(x, apply_clip_norm=True, normalize=True).clone()
+    model2 = jb.jclip.build_model(sd)
+    layers2 = jb.apply_lora(args, model2)
+    jb.load_lora(args, layers2, path)
+    f_b = model2.visual(x, apply_clip_norm=True, normalize=True)
+    assert torch.equal(f_a, f_b)
