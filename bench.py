@@ -309,7 +309,7 @@ def main():
                         f"top-5 of 403 classes",
             "images_per_gpu_per_step": I, "views_per_image": V, "parallelism": f"image-sharded dp{world}",
             "l2_policy": f"inputs larger than L2 ({images.numel() * images.element_size() / 2**20:.0f} MiB of views per step)",
-            "chunk_views": args.chunk_views or 2048, "gflop_per_view": GFLOP_PER_VIEW,
+            "chunk_views": args.chunk_views or 8192, "gflop_per_view": GFLOP_PER_VIEW,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

@@ -69,7 +69,8 @@ int jcb_ctx_create(int device, jcb_ctx** out);
 int jcb_ctx_destroy(jcb_ctx* ctx);
 /* Use the caller's CUDA stream (a cudaStream_t / CUstream cast to void*), e.g. torch's current stream. */
 int jcb_ctx_set_stream(jcb_ctx* ctx, void* cuda_stream);
-/* Views processed per pass through the tower (workspace = ~1.2 MB per view).  Default 2048. */
+/* Views processed per pass through the tower (workspace = ~1.2 MB per view).  Default 8192:
+ * measured on B200, larger chunks are faster (fewer partial waves); L2 residency does not pay at any size. */
 int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
 /* Wait for the context's stream and report any device-side kernel status. */
 int jcb_sync(jcb_ctx* ctx);

@@ -23,7 +23,7 @@ struct jcb_ctx {
   cudaEvent_t compute_done[2] = {nullptr, nullptr};
   int num_sms = 0, cc_major = 0, cc_minor = 0;
   int* dev_status = nullptr;
-  int64_t chunk_views = 2048;
+  int64_t chunk_views = 8192;
   void* ws = nullptr;
   size_t ws_bytes = 0;
   void* stage[2] = {nullptr, nullptr};  // device staging for host images

@@ -27,7 +27,7 @@ def _np32(x):
         return x.detach().to("cpu", torch.float32).numpy()
     if hasattr(x, "numpy") and not isinstance(x, np.ndarray):   # jittor.Var
         x = x.numpy()
-    return np.ascontiguousarray(np.asarray(x), dtype=np.float32)
+    return np.require(np.asarray(x), dtype=np.float32, requirements="C")
 
 
 class Param:
