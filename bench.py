@@ -27,6 +27,8 @@ import threading
 import time
 import types
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -46,6 +48,9 @@ def parse():
     ap.add_argument("--images-per-gpu", type=int, default=128, help="images per step on every rank")
     ap.add_argument("--crops", type=int, default=64, help="N random crops per image (views = N + 1)")
     ap.add_argument("--chunk-views", type=int, default=0, help="views per pass through the tower (0 = library default)")
+    ap.add_argument("--img-dtype", default="u8", choices=["u8", "f32"],
+                    help="pixel format of the views: u8 (0..255, what an image decoder / the reference's PIL pipeline "
+                         "produces before ToTensor; scaled by 1/255 on the device, bit-identical to ToTensor) or f32 in [0,1]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -196,6 +201,8 @@ def main():
 
     # this rank's shard of the step's images: I images x V views, generated on the device
     images = jb.synth.make_views_torch(1000 + rank, I, V, dev)
+    if args.img_dtype == "u8":
+        images = (images * 255.0).round_().to(torch.uint8)
     n_total = I * world
 
     def step_device():
@@ -285,7 +292,9 @@ def main():
         torch.set_num_threads(cores)
         sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
         lp_t = tuple(torch.from_numpy(a) for a in lp_np)
-        imgs_np = images[:4].cpu().numpy()
+        imgs_np = images[:4].cpu().float().numpy()
+        if args.img_dtype == "u8":
+            imgs_np = imgs_np / np.float32(255.0)          # == T.ToTensor on uint8 pixels
         t0 = time.perf_counter()
         cpu_oracle_image(torch, sd_t, lora, texts, lp_t, imgs_np[0])       # warm-up (thread pools, allocator)
         t_first = time.perf_counter() - t0
@@ -305,11 +314,12 @@ def main():
         "data": "synthetic",
         "config": {
             "workload": f"ViT-B/32 LoRA(r=4 on q,k,v, merged) encode_image over {I} images x {V} views (N={args.crops} crops + "
-                        f"centre) per GPU per step, fp32 224x224 inputs + fused CLIP normalisation, MTA x3, LP++ head, "
+                        f"centre) per GPU per step, {'uint8' if args.img_dtype == 'u8' else 'fp32'} 224x224 pixels (ToTensor scaling + CLIP "
+                        f"normalisation fused on the device), MTA x3, LP++ head, "
                         f"top-5 of 403 classes",
             "images_per_gpu_per_step": I, "views_per_image": V, "parallelism": f"image-sharded dp{world}",
             "l2_policy": f"inputs larger than L2 ({images.numel() * images.element_size() / 2**20:.0f} MiB of views per step)",
-            "chunk_views": args.chunk_views or 8192, "gflop_per_view": GFLOP_PER_VIEW,
+            "chunk_views_bound": args.chunk_views or 16384, "img_dtype": args.img_dtype, "gflop_per_view": GFLOP_PER_VIEW,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

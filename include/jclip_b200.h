@@ -69,8 +69,10 @@ int jcb_ctx_create(int device, jcb_ctx** out);
 int jcb_ctx_destroy(jcb_ctx* ctx);
 /* Use the caller's CUDA stream (a cudaStream_t / CUstream cast to void*), e.g. torch's current stream. */
 int jcb_ctx_set_stream(jcb_ctx* ctx, void* cuda_stream);
-/* Views processed per pass through the tower (workspace = ~1.2 MB per view).  Default 8192:
- * measured on B200, larger chunks are faster (fewer partial waves); L2 residency does not pay at any size. */
+/* Upper bound on the views processed per pass through the tower (workspace = ~1.2 MB per view); a batch
+ * is split into the fewest equal passes that respect it.  Default 16384 for device-resident input
+ * (measured on B200: larger passes are faster, intermediates never fit L2 anyway) and min(2048, bound)
+ * for host input, so that the copy of pass i+1 overlaps the compute of pass i. */
 int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
 /* Wait for the context's stream and report any device-side kernel status. */
 int jcb_sync(jcb_ctx* ctx);

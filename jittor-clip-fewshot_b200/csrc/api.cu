@@ -23,7 +23,8 @@ struct jcb_ctx {
   cudaEvent_t compute_done[2] = {nullptr, nullptr};
   int num_sms = 0, cc_major = 0, cc_minor = 0;
   int* dev_status = nullptr;
-  int64_t chunk_views = 8192;
+  int64_t chunk_views = 16384;       // upper bound of views per pass through the tower (device-resident input)
+  int64_t host_chunk_views = 2048;   // same for host input: smaller, so copies of chunk i+1 overlap compute of chunk i
   void* ws = nullptr;
   size_t ws_bytes = 0;
   void* stage[2] = {nullptr, nullptr};  // device staging for host images
@@ -281,6 +282,12 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   return JCB_OK;
 }
 
+int64_t balanced_chunk(int64_t n, int64_t bound) {
+  if (n <= bound) return n;
+  const int64_t passes = (n + bound - 1) / bound;
+  return (n + passes - 1) / passes;
+}
+
 int check_vit(jcb_vit* v) {
   if (!v) return JCB_E_INVALID;
   if (!v->finalized) return fail(v->ctx, JCB_E_STATE, "jcb_vit_finalize has not been called");
@@ -296,7 +303,9 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
   if (n < 0) return fail(ctx, JCB_E_INVALID, "negative view count");
   if (n == 0) return JCB_OK;
   if (!images || !out_dev) return fail(ctx, JCB_E_INVALID, "null image / output pointer");
-  const int64_t chunk = std::min<int64_t>(ctx->chunk_views, n);
+  // balanced chunks: the fewest passes that respect the bound, all (nearly) the same size, so no pass
+  // runs the 148 SMs on a sliver of work
+  const int64_t chunk = balanced_chunk(n, on_host ? std::min(ctx->host_chunk_views, ctx->chunk_views) : ctx->chunk_views);
   int rc = ws_reserve(ctx, ws_extra + tower_ws_bytes(v, chunk));
   if (rc) return rc;
   Bump b(static_cast<uint8_t*>(ctx->ws) + ws_extra);
@@ -664,7 +673,7 @@ int jcb_encode_image_host(jcb_vit* v, const void* images_host, int img_dtype, in
   if (n_views == 0) return JCB_OK;
   if (n_views < 0 || !out_host) return fail(ctx, JCB_E_INVALID, "bad arguments");
   const size_t out_bytes = align_up(static_cast<size_t>(n_views) * v->cfg.embed_dim * 4);
-  if ((rc = ws_reserve(ctx, out_bytes + tower_ws_bytes(v, std::min<int64_t>(ctx->chunk_views, n_views))))) return rc;
+  if ((rc = ws_reserve(ctx, out_bytes + tower_ws_bytes(v, balanced_chunk(n_views, std::min(ctx->host_chunk_views, ctx->chunk_views)))))) return rc;
   float* out_dev = static_cast<float*>(ctx->ws);
   if ((rc = encode_views(v, images_host, img_dtype, true, n_views, apply_clip_norm, normalize, out_dev, out_bytes)))
     return rc;
@@ -785,7 +794,7 @@ int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
   const size_t scratch_b = align_up(mta_scratch_bytes(3 * I, V, C, E));
   const bool own_feats = a->out_feats_dev == nullptr;
   const size_t head_bytes = (own_feats ? feats_b : 0) + (vit_zs ? feats_b : 0) + 3 * modes_b + topk_b + scratch_b;
-  if ((rc = ws_reserve(ctx, head_bytes + tower_ws_bytes(vit, std::min<int64_t>(ctx->chunk_views, NV))))) return rc;
+  if ((rc = ws_reserve(ctx, head_bytes + tower_ws_bytes(vit, balanced_chunk(NV, a->images_on_host ? std::min(ctx->host_chunk_views, ctx->chunk_views) : ctx->chunk_views))))) return rc;
   Bump b(ctx->ws);
   float* feats = own_feats ? b.take<float>(static_cast<size_t>(NV) * E) : a->out_feats_dev;
   float* feats_zs = vit_zs ? b.take<float>(static_cast<size_t>(NV) * E) : feats;
@@ -887,7 +896,11 @@ int jcb_encode_image_dlpack(jcb_vit* v, void* images_dlmanaged, void* out_dlmana
   else return fail(ctx, JCB_E_INVALID, "unsupported image dtype (code %d, bits %d)", in.dtype.code, in.dtype.bits);
   const int R = v->cfg.resolution;
   if (in.ndim != 4 || in.shape[1] != 3 || in.shape[2] != R || in.shape[3] != R || !dl_contiguous(in))
-    return fail(ctx, JCB_E_INVALID, "images must be contiguous [n, 3, %d, %d]", R, R);
+    return fail(ctx, JCB_E_INVALID, "images must be contiguous [n, 3, %d, %d] (got ndim %d, shape [%lld, %lld, %lld, %lld], strides [%lld, %lld, %lld, %lld])",
+                R, R, in.ndim, in.ndim > 0 ? (long long)in.shape[0] : -1LL, in.ndim > 1 ? (long long)in.shape[1] : -1LL,
+                in.ndim > 2 ? (long long)in.shape[2] : -1LL, in.ndim > 3 ? (long long)in.shape[3] : -1LL,
+                in.strides && in.ndim > 0 ? (long long)in.strides[0] : -1LL, in.strides && in.ndim > 1 ? (long long)in.strides[1] : -1LL,
+                in.strides && in.ndim > 2 ? (long long)in.strides[2] : -1LL, in.strides && in.ndim > 3 ? (long long)in.strides[3] : -1LL);
   if (out.ndim != 2 || out.shape[0] != in.shape[0] || out.shape[1] != v->cfg.embed_dim || out.dtype.code != kDLFloat ||
       out.dtype.bits != 32 || !dl_contiguous(out))
     return fail(ctx, JCB_E_INVALID, "out must be contiguous float32 [n, %d]", v->cfg.embed_dim);

@@ -9,6 +9,8 @@
 //
 // Reference: jclip/mha.py:55-83 scaled_dot_product_attention (attn_mask None for the vision tower,
 // jclip/model.py:99; dropout 0 in eval), head split jclip/mha.py:351-362 / test.py:584-590.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -19,13 +21,17 @@ namespace {
 constexpr int HD = 64;              // head dim
 constexpr int TP = 64;              // padded token count
 constexpr int LDS = HD + 8;         // smem row stride (bf16): 144 B, conflict-free for ldmatrix
-constexpr int HEADS_PER_CTA = 4;
-constexpr int ATT_THREADS = HEADS_PER_CTA * 2 * 32;
 constexpr int TILE_ELEMS = TP * LDS;
-constexpr int ATT_SMEM = HEADS_PER_CTA * 3 * TILE_ELEMS * 2;  // 110592 B
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// HEADS_PER_CTA heads of one view per CTA (2 warps per head).  Fewer heads per CTA = smaller shared-memory
+// footprint = more resident CTAs per SM, whose load and compute phases overlap each other: the kernel is
+// bound by streaming qkv (6 B/element) in and the output (2 B/element) out.
+// MT = 16-row query tiles per warp (2 -> 2 warps per head, 1 -> 4 warps per head with half the registers).
+template <int HEADS_PER_CTA, int MT>
+__global__ void __launch_bounds__(HEADS_PER_CTA * (4 / MT) * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_bfloat16* __restrict__ out) {
+  constexpr int WPH = 4 / MT;  // warps per head
+  constexpr int ATT_THREADS = HEADS_PER_CTA * WPH * 32;
   extern __shared__ __align__(16) uint8_t att_smem[];
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_smem);
   const int W = heads * HD;
@@ -52,25 +58,25 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   cp_async_commit_wait_all();
   __syncthreads();
 
-  const int h = warp >> 1;          // head within the group
-  const int r0 = (warp & 1) * 32;   // first query row of this warp
+  const int h = warp / WPH;                 // head within the group
+  const int r0 = (warp % WPH) * (16 * MT);  // first query row of this warp
   const uint32_t sQ = smem_u32(sm + (h * 3 + 0) * TILE_ELEMS);
   const uint32_t sK = smem_u32(sm + (h * 3 + 1) * TILE_ELEMS);
   const uint32_t sV = smem_u32(sm + (h * 3 + 2) * TILE_ELEMS);
 
   // ---- S = Q K^T : 2 m-tiles x 8 n-tiles (keys) x 4 k-steps (head dim)
-  float s[2][8][4];
+  float s[MT][8][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    uint32_t a[2][4];
+    uint32_t a[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       const int row = r0 + mt * 16 + (lane & 15);
       const int col = kk * 16 + ((lane >> 4) << 3);
       ldmatrix_x4(a[mt], sQ + (row * LDS + col) * 2);
@@ -82,7 +88,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       const int col = kk * 16 + (((lane >> 3) & 1) << 3);
       ldmatrix_x4(b, sK + (krow * LDS + col) * 2);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         mma_bf16_16816(s[mt][2 * np], a[mt], b[0], b[1]);
         mma_bf16_16816(s[mt][2 * np + 1], a[mt], b[2], b[3]);
       }
@@ -91,10 +97,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
 
   // ---- softmax over keys (fp32); thread holds rows g and g+8 of each m-tile, cols nt*8 + 2*(lane&3) + {0,1}
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  float inv_sum[2][2];
-  uint32_t pfrag[2][8][2];  // P as bf16 pairs: [mt][nt][row half]
+  float inv_sum[MT][2];
+  uint32_t pfrag[MT][8][2];  // P as bf16 pairs: [mt][nt][row half]
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -130,18 +136,18 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   }
 
   // ---- O = P V : 2 m-tiles x 8 d-tiles x 4 k-steps (keys)
-  float o[2][8][4];
+  float o[MT][8][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[mt][dt][e] = 0.f;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[2][4];
+    uint32_t a[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       a[mt][0] = pfrag[mt][2 * ks][0];
       a[mt][1] = pfrag[mt][2 * ks][1];
       a[mt][2] = pfrag[mt][2 * ks + 1][0];
@@ -154,7 +160,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       const int col = dp * 16 + ((lane >> 4) << 3);
       ldmatrix_x4_trans(b, sV + (krow * LDS + col) * 2);
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         mma_bf16_16816(o[mt][2 * dp], a[mt], b[0], b[1]);
         mma_bf16_16816(o[mt][2 * dp + 1], a[mt], b[2], b[3]);
       }
@@ -165,7 +171,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   __nv_bfloat16* stage = sm + (h * 3 + 0) * TILE_ELEMS;
   __syncwarp();
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const int row = r0 + mt * 16 + (lane >> 2);
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
@@ -188,19 +194,38 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
 
 }  // namespace
 
-cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream) {
-  if (T < 1 || T > TP || heads % HEADS_PER_CTA != 0) return cudaErrorInvalidValue;
-  if (n_views == 0) return cudaSuccess;
+template <int HPC, int MT>
+cudaError_t launch_attention_hpc(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                                 cudaStream_t stream) {
+  constexpr int SMEM = HPC * 3 * TILE_ELEMS * 2;  // 27648 B per head
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HPC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const long long grid = n_views * (heads / HEADS_PER_CTA);
-  attention_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM, stream>>>(qkv, T, heads, out);
+  const long long grid = n_views * (heads / HPC);
+  attention_kernel<HPC, MT><<<static_cast<unsigned>(grid), HPC * (4 / MT) * 32, SMEM, stream>>>(qkv, T, heads, out);
   return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                             cudaStream_t stream) {
+  if (T < 1 || T > TP || heads % 4 != 0) return cudaErrorInvalidValue;
+  if (n_views == 0) return cudaSuccess;
+  static int cfg = 0;  // heads per CTA * 10 + query tiles per warp
+  if (cfg == 0) {
+    const char* env = getenv("JCB_ATT_CFG");
+    cfg = env ? atoi(env) : 11;  // measured on B200 (tools/bench_kernel.py attention): 11 -> 4.4 TB/s, 42 -> 2.5 TB/s
+  }
+  switch (cfg) {
+    case 12: return launch_attention_hpc<1, 2>(qkv, n_views, T, heads, out, stream);
+    case 22: return launch_attention_hpc<2, 2>(qkv, n_views, T, heads, out, stream);
+    case 41: return launch_attention_hpc<4, 1>(qkv, n_views, T, heads, out, stream);
+    case 42: return launch_attention_hpc<4, 2>(qkv, n_views, T, heads, out, stream);
+    case 21: return launch_attention_hpc<2, 1>(qkv, n_views, T, heads, out, stream);
+    default: return launch_attention_hpc<1, 1>(qkv, n_views, T, heads, out, stream);
+  }
 }
 
 }  // namespace jcb

@@ -1,11 +1,20 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:   C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)
 //
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a STAGES-deep smem ring
-//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, bf16 -> fp32)
-//                                accumulating in TMEM; tcgen05.commit releases smem slots / publishes tiles
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (bf16 -> fp32) accumulating in TMEM;
+//                                tcgen05.commit releases smem slots / publishes accumulator stages
 //   warps 2..5  epilogue       : tcgen05.ld TMEM -> registers, bias / QuickGELU / residual / pos-embed,
 //                                vectorised global stores; TMEM accumulators are double buffered so the
 //                                epilogue of tile i overlaps the main loop of tile i+1
+//
+// Two tile configurations of the same kernel (template parameter CTAS):
+//   CTAS = 2 (default)  CTA pairs (cluster 2x1x1, tcgen05 cta_group::2): UMMA 256 x BN x 16 across two SMs.
+//                       Each CTA stages its 128 rows of A and HALF of the B tile (BN/2 rows); the tensor core
+//                       reads both halves.  Per CTA and k-block that is 32 KB of TMA writes + 8 KB/MMA of
+//                       operand reads = 128 B/cycle, exactly the shared-memory bandwidth of an SM.
+//   CTAS = 1            UMMA 128 x BN x 16 from one CTA: 48 KB written + 12 KB/MMA read = 192 B/cycle demanded of
+//                       a 128 B/cycle SMEM -> the tensor pipe cannot exceed ~66 % (measured 64 %, profiles/r01a).
+//                       Kept selectable (JCB_GEMM_CTAS=1) as the A/B baseline.
 //
 // This replaces the reference's fp32 `nn.Linear` calls on the hot path: packed QKV projection
 // (jclip/mha.py:129-146, test.py:557-559), attention out-proj (jclip/mha.py:461, test.py:594), MLP
@@ -13,6 +22,7 @@
 // (jclip/model.py:105-108).  Residual adds (jclip/model.py:60-61), QuickGELU (jclip/model.py:27) and the
 // positional-embedding add (jclip/model.py:114) are fused into the epilogues.
 #include <cstdio>
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 #include "kernels.h"
@@ -22,21 +32,23 @@ namespace jcb {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int BLOCK_M = 128;  // rows of A (and of the accumulator) per CTA
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARPS = 4;
-constexpr int SMEM_BUDGET = 196608;  // operand ring; barriers + bias tile come on top
+constexpr int SMEM_BUDGET = 163840;  // operand ring; epilogue staging, bias tile and barriers come on top
+constexpr int STAGING_BYTES = EPI_WARPS * 2 * 4096;  // per epilogue warp: two 32-row x 128-B swizzled chunks
 
-template <int BN>
+template <int BN, int CTAS>
 struct TileCfg {
+  static constexpr int B_ROWS = BN / CTAS;  // rows of the B tile this CTA stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; power of two for BN in {128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * BN * 4 + 256 + 1024;  // + per-warp bias + barriers + align slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 4 * BN * 4 + 256 + 1024;  // + per-warp bias + barriers + align slack
 };
 
 struct GemmDev {
@@ -50,33 +62,42 @@ struct GemmDev {
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)  (reference jclip/model.py:27)
-  return __fdividef(x, 1.0f + __expf(-1.702f * x));
+  // x * sigmoid(1.702 x)  (reference jclip/model.py:27) = 0.5 x (1 + tanh(0.851 x)): one MUFU op per element
+  // (tanh.approx, rel. error 2^-11, below the bf16 rounding of the output) instead of ex2 + rcp
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(0.851f * x), h);
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmDev p) {
-  using Cfg = TileCfg<BN>;
+template <int BN, int EPI, int CTAS>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                                          const GemmDev& p) {
+  using Cfg = TileCfg<BN, CTAS>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool PAIR = CTAS == 2;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment in the shared address space.
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* ring = smem;
-  float* s_bias_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 4 * BN * 4);
-  uint64_t* full_bar = bars;                   // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;         // [STAGES]  MMA -> TMA
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;      // [2]  MMA -> epilogue
-  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2; // [2]  epilogue -> MMA
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;   // 1024-B aligned (STAGE_BYTES is a multiple of 1024)
+  float* s_bias_all = reinterpret_cast<float*>(staging + STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + 4 * BN * 4);
+  uint64_t* full_bar = bars;                         // [STAGES]  TMA -> MMA       (the leader CTA's copy is used)
+  uint64_t* empty_bar = bars + STAGES;               // [STAGES]  MMA -> TMA       (each CTA its own)
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]  MMA -> epilogue       (each CTA its own)
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]  epilogue -> MMA       (the leader CTA's copy is used)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // one work unit = one (CTA or CTA pair) x one output tile of (CTAS * 128) x BN
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int TILE_M = BLOCK_M * CTAS;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int n_tiles = p.N / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / BLOCK_K;
@@ -84,54 +105,70 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI != EPI_PATCH_F32) tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], EPI_WARPS);
+      mbar_init(&tmem_empty_bar[s], EPI_WARPS * CTAS);
     }
     fence_mbar_init();
     fence_proxy_async_smem();
   }
-  if (warp_idx == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+  if (warp_idx == 1) {  // the same warp of BOTH CTAs of a pair takes part in a cta_group::2 allocation
+    if (PAIR) {
+      tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
 
   if (warp_idx == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (every CTA)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles && ok; tile += num_units) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int m0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.status, JCB_DEV_TIMEOUT_PRODUCER)) { ok = false; break; }
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+          if (PAIR) {
+            // the leader's barrier collects the bytes of BOTH CTAs; a complete_tx that lands before the
+            // leader's expect_tx just drives the transaction count negative for a moment
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
+            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ===================================================================== MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, BN);
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < num_tiles && ok; tile += num_units, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         if (!mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, p.status, JCB_DEV_TIMEOUT_MMA)) { ok = false; break; }
@@ -146,24 +183,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // +32 B per UMMA_K step inside the 128-B swizzle atom = +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            if (PAIR)
+              umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs) once these MMAs have read it
+          if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (ok) umma_commit(&tmem_full_bar[as]);  // accumulator complete -> epilogue
+        if (ok) {  // accumulator complete -> epilogue warps of both CTAs
+          if (PAIR) umma_commit_pair(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
+        }
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..5, every CTA)
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
     // Each epilogue warp keeps a private copy of the tile's bias slice: no cross-warp barrier in
     // the epilogue, so a warp that abandons its loop on a pipeline error cannot strand the others.
     float* s_bias = s_bias_all + q * BN;
+    const uint32_t empty_addr0 = smem_u32(&tmem_empty_bar[0]) & (PAIR ? PEER_BIT_MASK : 0xFFFFFFFFu);
     int it = 0;
+    int chunks_issued = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < num_tiles && ok; tile += num_units, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -176,120 +222,178 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (!ok) break;
       tc_fence_after();
 
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool valid = row < p.M;
-      long long orow = row;
-      int tok = 0;
-      if (EPI == EPI_PATCH_F32) {
-        tok = row % p.tokens_in + 1;
-        orow = static_cast<long long>(row / p.tokens_in) * p.tokens_out + tok;
-      }
+      const int row0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;  // this warp's 32 rows
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      if (EPI == EPI_PATCH_F32) {
+        // conv1 output rows scatter to token rows 1..T-1 of each view (+ positional embedding): direct stores
+        const int row = row0 + lane;
+        const bool valid = row < p.M;
+        const int tok = row % p.tokens_in + 1;
+        const long long orow = static_cast<long long>(row / p.tokens_in) * p.tokens_out + tok;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
-        const int n0 = n_blk * BN + c * 32;
-        if (EPI == EPI_BIAS_RESID_F32) {
-          // prefetch the residual row segment while the TMEM load is in flight
-          float4 r[8];
-          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + n0);
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = dst[j];
-          }
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * j);
-              r[j].x += __uint_as_float(v[4 * j + 0]) + b.x;
-              r[j].y += __uint_as_float(v[4 * j + 1]) + b.y;
-              r[j].z += __uint_as_float(v[4 * j + 2]) + b.z;
-              r[j].w += __uint_as_float(v[4 * j + 3]) + b.w;
-              dst[j] = r[j];
-            }
-          }
-        } else if (EPI == EPI_PATCH_F32 || EPI == EPI_F32) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+          const int n0 = n_blk * BN + c * 32;
           tmem_ld_wait();
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + n0);
-            const float4* pe = reinterpret_cast<const float4*>(
-                EPI == EPI_PATCH_F32 ? p.pos + static_cast<long long>(tok) * p.N + n0 : nullptr);
+            const float4* pe = reinterpret_cast<const float4*>(p.pos + static_cast<long long>(tok) * p.N + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * j);
+              const float4 e = __ldg(pe + j);
               float4 o;
-              o.x = __uint_as_float(v[4 * j + 0]) + b.x;
-              o.y = __uint_as_float(v[4 * j + 1]) + b.y;
-              o.z = __uint_as_float(v[4 * j + 2]) + b.z;
-              o.w = __uint_as_float(v[4 * j + 3]) + b.w;
-              if (EPI == EPI_PATCH_F32) {
-                const float4 e = __ldg(pe + j);
-                o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-              }
-              dst[j] = o;
-            }
-          }
-        } else {
-          tmem_ld_wait();
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = __uint_as_float(v[8 * j + e]) + s_bias[c * 32 + 8 * j + e];
-                if (EPI == EPI_BIAS_GELU_BF16) f[e] = quick_gelu(f[e]);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
+              o.x = __uint_as_float(v[4 * j + 0]) + b.x + e.x;
+              o.y = __uint_as_float(v[4 * j + 1]) + b.y + e.y;
+              o.z = __uint_as_float(v[4 * j + 2]) + b.z + e.z;
+              o.w = __uint_as_float(v[4 * j + 3]) + b.w + e.w;
               dst[j] = o;
             }
           }
         }
+      } else {
+        // TMEM -> registers -> (+bias, activation, rounding) -> 128B-swizzled smem chunk of 32 rows x 128 B ->
+        // one TMA store (or fp32 reduce-add for the residual epilogues) per chunk: fully coalesced, asynchronous,
+        // and the residual stream is never read into the SM.  Rows >= M are clipped by the tensor map.
+        constexpr bool OUT_BF16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16;
+        constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;
+        constexpr int NCH = BN / CHUNK_COLS;
+        uint8_t* my_stage = staging + q * 8192;
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
+        uint32_t v[2][CHUNK_COLS];
+        auto load_chunk = [&](int c, uint32_t (&dst)[CHUNK_COLS]) {
+          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * CHUNK_COLS), *reinterpret_cast<uint32_t(*)[32]>(&dst[0]));
+          if (OUT_BF16)
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * CHUNK_COLS + 32),
+                               *reinterpret_cast<uint32_t(*)[32]>(&dst[CHUNK_COLS - 32]));
+        };
+        load_chunk(0, v[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t(&cur)[CHUNK_COLS] = v[c & 1];
+          tmem_ld_wait();  // chunk c is in registers
+          if (c + 1 < NCH) {
+            load_chunk(c + 1, v[(c + 1) & 1]);
+          } else {
+            // every TMEM read of this tile has completed: hand the accumulator stage back to the MMA issuer
+            // (leader CTA) before the last chunk is even converted
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8));
+              else mbar_arrive(&tmem_empty_bar[as]);
+            }
+          }
+          uint8_t* buf = my_stage + (chunks_issued & 1) * 4096;
+          // the TMA store that last used this buffer (two chunks ago) must have finished reading it
+          if (lane == 0 && chunks_issued >= 2) bulk_wait_read<1>();
+          __syncwarp();
+          const float* bsrc = s_bias + c * CHUNK_COLS;
+          uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 16-byte piece j of this thread's 128-byte row, XOR-swizzled by row % 8
+            uint4 o;
+            if (OUT_BF16) {
+              float f[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(bsrc + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 8 * j + 4);
+              f[0] = __uint_as_float(cur[8 * j + 0]) + b0.x; f[1] = __uint_as_float(cur[8 * j + 1]) + b0.y;
+              f[2] = __uint_as_float(cur[8 * j + 2]) + b0.z; f[3] = __uint_as_float(cur[8 * j + 3]) + b0.w;
+              f[4] = __uint_as_float(cur[8 * j + 4]) + b1.x; f[5] = __uint_as_float(cur[8 * j + 5]) + b1.y;
+              f[6] = __uint_as_float(cur[8 * j + 6]) + b1.z; f[7] = __uint_as_float(cur[8 * j + 7]) + b1.w;
+              if (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
+              }
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            } else {
+              const float4 b = *reinterpret_cast<const float4*>(bsrc + 4 * j);
+              o.x = __float_as_uint(__uint_as_float(cur[4 * j + 0]) + b.x);
+              o.y = __float_as_uint(__uint_as_float(cur[4 * j + 1]) + b.y);
+              o.z = __float_as_uint(__uint_as_float(cur[4 * j + 2]) + b.z);
+              o.w = __float_as_uint(__uint_as_float(cur[4 * j + 3]) + b.w);
+            }
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (EPI == EPI_BIAS_RESID_F32) tma_reduce_add_2d(&tmOut, buf, n_blk * BN + c * CHUNK_COLS, row0);
+            else tma_store_2d(&tmOut, buf, n_blk * BN + c * CHUNK_COLS, row0);
+            bulk_commit();
+          }
+          ++chunks_issued;
+        }
       }
-      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (EPI == EPI_PATCH_F32) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8));
+          else mbar_arrive(&tmem_empty_bar[as]);
+        }
+      }
     }
+    if (lane == 0) bulk_wait<0>();  // every TMA store / reduce of this warp has been performed
   }
 
   tc_fence_before();
-  __syncthreads();
+  // a CTA of a pair must not retire while its partner can still touch its smem / TMEM / barriers
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmOut, const GemmDev p) {
+  gemm_body<BN, EPI, 1>(tmA, tmB, tmOut, p);
+}
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const __grid_constant__ CUtensorMap tmOut, const GemmDev p) {
+  gemm_body<BN, EPI, 2>(tmA, tmB, tmOut, p);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
 char g_driver_err[256] = {0};
+int g_ctas = 0;  // 0 = not decided yet
 
-bool make_tmap_bf16_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                       uint32_t box_rows, uint32_t box_cols) {
+// 2-D row-major tensor [rows, cols] with leading dimension ld_elems, 128B-swizzled boxes of box_rows x box_cols
+bool make_tmap_2d(CUtensorMap* tm, bool bf16, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                  uint32_t box_rows, uint32_t box_cols) {
+  const uint64_t esz = bf16 ? 2 : 4;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode_tiled(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
-  CUtensorMap tmA, tmB;
-  if (!make_tmap_bf16_2d(&tmA, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16_2d(&tmB, a.B, a.N, a.K, a.ldb, BN, BLOCK_K)) return cudaErrorInvalidValue;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  using Cfg = TileCfg<BN, CTAS>;
+  CUtensorMap tmA, tmB, tmOut;
+  if (!make_tmap_2d(&tmA, true, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K)) return cudaErrorInvalidValue;
+  if (!make_tmap_2d(&tmB, true, a.B, a.N, a.K, a.ldb, Cfg::B_ROWS, BLOCK_K)) return cudaErrorInvalidValue;
+  constexpr bool OUT_BF16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16;
+  if (EPI == EPI_PATCH_F32) {
+    tmOut = tmA;  // unused by the scatter epilogue
+  } else if (!make_tmap_2d(&tmOut, OUT_BF16, a.out, a.M, a.N, a.ldo, 32, OUT_BF16 ? 64 : 32)) {
+    return cudaErrorInvalidValue;
+  }
+  auto kern = CTAS == 2 ? gemm_bf16_tcgen05_2cta_kernel<BN, EPI> : gemm_bf16_tcgen05_kernel<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -300,21 +404,22 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.pos = a.pos;
   p.tokens_in = a.tokens_in; p.tokens_out = a.tokens_out; p.status = dev_status;
-  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-  const int tiles = m_tiles * (a.N / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int tile_m = BLOCK_M * CTAS;
+  const int tiles = ((a.M + tile_m - 1) / tile_m) * (a.N / BN);
+  const int units = num_sms / CTAS;                       // CTAs or CTA pairs that fit the chip
+  const int grid = (tiles < units ? tiles : units) * CTAS;
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, p);
   return cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, int CTAS>
 cudaError_t launch_bn(const GemmArgs& a, int* st, int sms, cudaStream_t s) {
   switch (a.epilogue) {
-    case EPI_BIAS_BF16: return launch_cfg<BN, EPI_BIAS_BF16>(a, st, sms, s);
-    case EPI_BIAS_GELU_BF16: return launch_cfg<BN, EPI_BIAS_GELU_BF16>(a, st, sms, s);
-    case EPI_BIAS_RESID_F32: return launch_cfg<BN, EPI_BIAS_RESID_F32>(a, st, sms, s);
-    case EPI_PATCH_F32: return launch_cfg<BN, EPI_PATCH_F32>(a, st, sms, s);
-    case EPI_F32: return launch_cfg<BN, EPI_F32>(a, st, sms, s);
+    case EPI_BIAS_BF16: return launch_cfg<BN, EPI_BIAS_BF16, CTAS>(a, st, sms, s);
+    case EPI_BIAS_GELU_BF16: return launch_cfg<BN, EPI_BIAS_GELU_BF16, CTAS>(a, st, sms, s);
+    case EPI_BIAS_RESID_F32: return launch_cfg<BN, EPI_BIAS_RESID_F32, CTAS>(a, st, sms, s);
+    case EPI_PATCH_F32: return launch_cfg<BN, EPI_PATCH_F32, CTAS>(a, st, sms, s);
+    case EPI_F32: return launch_cfg<BN, EPI_F32, CTAS>(a, st, sms, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -332,6 +437,8 @@ const char* gemm_init_driver_api() {
     return g_driver_err;
   }
   g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  const char* env = getenv("JCB_GEMM_CTAS");
+  g_ctas = (env && env[0] == '1') ? 1 : 2;
   return nullptr;
 }
 
@@ -339,11 +446,15 @@ cudaError_t launch_gemm(const GemmArgs& a, int* dev_status, int num_sms, cudaStr
   if (!g_encode_tiled) return cudaErrorNotReady;
   if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.K % BLOCK_K != 0 || a.N % 128 != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.lda % 8) ||
-      (a.ldb % 8) || (a.ldo % 8))
+      (a.ldb % 8) || (a.ldo % 8) || (reinterpret_cast<uintptr_t>(a.out) & 15))
     return cudaErrorInvalidValue;
-  // 128 x 256 tiles whenever N allows it; 128 x 128 otherwise (only used by generic/test shapes).
-  if (a.N % 256 == 0) return launch_bn<256>(a, dev_status, num_sms, stream);
-  return launch_bn<128>(a, dev_status, num_sms, stream);
+  // BN = 256 whenever N allows it; 128 otherwise (only used by generic/test shapes).
+  if (g_ctas == 2) {
+    if (a.N % 256 == 0) return launch_bn<256, 2>(a, dev_status, num_sms, stream);
+    return launch_bn<128, 2>(a, dev_status, num_sms, stream);
+  }
+  if (a.N % 256 == 0) return launch_bn<256, 1>(a, dev_status, num_sms, stream);
+  return launch_bn<128, 1>(a, dev_status, num_sms, stream);
 }
 
 }  // namespace jcb

@@ -29,6 +29,7 @@ struct MtaDev {
   long long I;
   int V, C, D, ldA, k;
   MtaParams p;
+  const float* P;       // [n_sets, I*V, C] row-softmaxed logits from mta_probs_kernel (nullptr: compute here)
   float* scratch;       // per image: region R (max(V*C, V*D)) + A (V*ldA), only used when !in_smem
   long long scratch_stride;
   int in_smem;
@@ -75,6 +76,123 @@ __device__ __forceinline__ void density_step(const float* __restrict__ X, const 
   __syncthreads();
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// P = softmax_rows(100 * X T / temperature) for every view of every image of every (feats, text) set:
+// one smem-tiled fp32 SIMT GEMM over all rows at once instead of each image's CTA streaming the text
+// bank from L2 (which was ~half of the solver's time).  fp32 on purpose: the logits are O(10..100) and
+// feed a softmax whose output defines the affinity matrix; bf16 tensor-core inputs would move the
+// modes by ~1e-3, far outside the parity tolerance.
+//   CTA = 64 rows x all C classes (C <= 416), 256 threads: warp w owns rows 8w..8w+7, lane l owns
+//   classes l, l+32, ... (13 per lane); K is consumed in chunks of 32 staged by cp.async, two stages.
+constexpr int PB_ROWS = 64, PB_KC = 32, PB_NC = 13, PB_CPAD = PB_NC * 32;  // 416 >= 403
+constexpr int PB_XS = PB_ROWS * PB_KC;                                      // floats per X stage
+constexpr int PB_TS = PB_KC * PB_CPAD;                                      // floats per T stage
+constexpr int PB_SMEM = 2 * (PB_XS + PB_TS) * 4;                            // 122880 B
+
+struct ProbsDev {
+  MtaSet sets[MTA_MAX_SETS];
+  long long rows;   // I * V
+  int C, D;
+  float scale;
+  float* P;         // [n_sets, rows, C]
+};
+
+__global__ void __launch_bounds__(256, 1) mta_probs_kernel(const ProbsDev a) {
+  extern __shared__ __align__(16) float pb_smem[];
+  float* Xs = pb_smem;                 // [2][PB_ROWS][PB_KC]
+  float* Ts = pb_smem + 2 * PB_XS;     // [2][PB_KC][PB_CPAD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const MtaSet& set = a.sets[blockIdx.y];
+  const long long row0 = static_cast<long long>(blockIdx.x) * PB_ROWS;
+  const float* __restrict__ X = set.feats;
+  const float* __restrict__ T = set.text;
+  const int C = a.C, D = a.D;
+
+  // columns >= C of the T stages are never written by cp.async: zero them once
+  for (int i = tid; i < 2 * PB_TS; i += 256) {
+    const int c = i % PB_CPAD;
+    if (c >= C) Ts[i] = 0.f;
+  }
+  auto load_stage = [&](int stage, int k0) {
+    // X: 64 rows x 32 k = 512 x 16-byte pieces; rows past the end re-read the last valid row
+    for (int i = tid; i < PB_ROWS * (PB_KC / 4); i += 256) {
+      const int r = i / (PB_KC / 4), p4 = i % (PB_KC / 4);
+      long long gr = row0 + r;
+      if (gr >= a.rows) gr = a.rows - 1;
+      cp_async_16(smem_u32(Xs + stage * PB_XS + r * PB_KC + p4 * 4), X + gr * D + k0 + p4 * 4);
+    }
+    // T: 32 k x C classes, 4-byte pieces (row stride C = 403 floats is not 16-byte aligned)
+    for (int i = tid; i < PB_KC * C; i += 256) {
+      const int k = i / C, c = i % C;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(Ts + stage * PB_TS + k * PB_CPAD + c)),
+                   "l"(T + static_cast<long long>(k0 + k) * C + c)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][PB_NC];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < PB_NC; ++j) acc[i][j] = 0.f;
+
+  const int nk = D / PB_KC;
+  load_stage(0, 0);
+  for (int kc = 0; kc < nk; ++kc) {
+    if (kc + 1 < nk) {
+      load_stage((kc + 1) & 1, (kc + 1) * PB_KC);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* xs = Xs + (kc & 1) * PB_XS + warp * 8 * PB_KC;
+    const float* ts = Ts + (kc & 1) * PB_TS + lane;
+#pragma unroll 4
+    for (int k = 0; k < PB_KC; ++k) {
+      float t[PB_NC], x[8];
+#pragma unroll
+      for (int j = 0; j < PB_NC; ++j) t[j] = ts[k * PB_CPAD + 32 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = xs[i * PB_KC + k];  // warp-uniform address: broadcast
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < PB_NC; ++j) acc[i][j] = fmaf(x[i], t[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // row softmax (test.py:1411 `(logits/temperature).softmax(1)`), one warp per row
+  float* Pout = a.P + static_cast<long long>(blockIdx.y) * a.rows * C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long gr = row0 + warp * 8 + i;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < PB_NC; ++j) {
+      acc[i][j] *= a.scale;
+      if (lane + 32 * j < C) mx = fmaxf(mx, acc[i][j]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PB_NC; ++j) {
+      const float e = (lane + 32 * j < C) ? expf(acc[i][j] - mx) : 0.f;
+      acc[i][j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    if (gr < a.rows) {
+#pragma unroll
+      for (int j = 0; j < PB_NC; ++j)
+        if (lane + 32 * j < C) Pout[gr * C + lane + 32 * j] = acc[i][j] * inv;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   extern __shared__ __align__(16) float mta_smem[];
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA;
@@ -102,55 +220,63 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   float* R = a.in_smem ? big : a.scratch + problem * a.scratch_stride;
   float* A = a.in_smem ? big + ((r_elems + 3) & ~3LL) : a.scratch + problem * a.scratch_stride + ((r_elems + 3) & ~3LL);
 
-  // ---- 1. logits = 100 * X T / temperature -> R[v*C + c]      (test.py:1393)
-  {
-    const float scale = 100.0f / a.p.temperature;
-    for (int c0 = 0; c0 < C; c0 += MTA_THREADS) {
-      const int c = c0 + tid;
-      const int cc = c < C ? c : C - 1;
-      for (int v0 = 0; v0 < V; v0 += VB) {
-        float acc[VB];
-#pragma unroll
-        for (int j = 0; j < VB; ++j) acc[j] = 0.f;
-        for (int d = 0; d < D; d += 4) {
-          float t[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) t[e] = __ldg(Tt + static_cast<long long>(d + e) * C + cc);
-#pragma unroll
-          for (int j = 0; j < VB; ++j) {
-            const int v = v0 + j < V ? v0 + j : V - 1;
-            const float4 x = __ldg(reinterpret_cast<const float4*>(Xg + v * D + d));  // warp-uniform address
-            acc[j] = fmaf(x.x, t[0], acc[j]);
-            acc[j] = fmaf(x.y, t[1], acc[j]);
-            acc[j] = fmaf(x.z, t[2], acc[j]);
-            acc[j] = fmaf(x.w, t[3], acc[j]);
+  if (a.P != nullptr) {
+    // ---- 1+2. probabilities were computed for the whole batch by mta_probs_kernel: bring this problem's
+    //           V x C block on chip (or use it in place when the problem does not fit in shared memory)
+    const float* Pg = a.P + (static_cast<long long>(blockIdx.y) * a.I + img) * V * C;
+    for (int i = tid; i < V * C; i += MTA_THREADS) R[i] = __ldg(Pg + i);
+    __syncthreads();
+  } else {
+    // ---- 1. logits = 100 * X T / temperature -> R[v*C + c]      (test.py:1393)
+    {
+      const float scale = 100.0f / a.p.temperature;
+      for (int c0 = 0; c0 < C; c0 += MTA_THREADS) {
+        const int c = c0 + tid;
+        const int cc = c < C ? c : C - 1;
+        for (int v0 = 0; v0 < V; v0 += VB) {
+          float acc[VB];
+  #pragma unroll
+          for (int j = 0; j < VB; ++j) acc[j] = 0.f;
+          for (int d = 0; d < D; d += 4) {
+            float t[4];
+  #pragma unroll
+            for (int e = 0; e < 4; ++e) t[e] = __ldg(Tt + static_cast<long long>(d + e) * C + cc);
+  #pragma unroll
+            for (int j = 0; j < VB; ++j) {
+              const int v = v0 + j < V ? v0 + j : V - 1;
+              const float4 x = __ldg(reinterpret_cast<const float4*>(Xg + v * D + d));  // warp-uniform address
+              acc[j] = fmaf(x.x, t[0], acc[j]);
+              acc[j] = fmaf(x.y, t[1], acc[j]);
+              acc[j] = fmaf(x.z, t[2], acc[j]);
+              acc[j] = fmaf(x.w, t[3], acc[j]);
+            }
           }
-        }
-        if (c < C) {
-#pragma unroll
-          for (int j = 0; j < VB; ++j)
-            if (v0 + j < V) R[(v0 + j) * C + c] = acc[j] * scale;
+          if (c < C) {
+  #pragma unroll
+            for (int j = 0; j < VB; ++j)
+              if (v0 + j < V) R[(v0 + j) * C + c] = acc[j] * scale;
+          }
         }
       }
     }
-  }
-  __syncthreads();
-  // ---- 2. row softmax in place
-  for (int v = warp; v < V; v += MTA_WARPS) {
-    float mx = -INFINITY;
-    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, R[v * C + c]);
-    mx = warp_max(mx);
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float e = expf(R[v * C + c] - mx);
-      R[v * C + c] = e;
-      s += e;
+    __syncthreads();
+    // ---- 2. row softmax in place
+    for (int v = warp; v < V; v += MTA_WARPS) {
+      float mx = -INFINITY;
+      for (int c = lane; c < C; c += 32) mx = fmaxf(mx, R[v * C + c]);
+      mx = warp_max(mx);
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float e = expf(R[v * C + c] - mx);
+        R[v * C + c] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      const float inv = 1.0f / s;
+      for (int c = lane; c < C; c += 32) R[v * C + c] *= inv;
     }
-    s = warp_sum(s);
-    const float inv = 1.0f / s;
-    for (int c = lane; c < C; c += 32) R[v * C + c] *= inv;
+    __syncthreads();
   }
-  __syncthreads();
   // ---- 3. affinity A = P P^T                                    (test.py:1411)
   for (int idx = tid; idx < V * V; idx += MTA_THREADS) {
     const int i = idx / V, j = idx % V;
@@ -304,9 +430,14 @@ static bool mta_fits_smem(int V, int C, int D) {
   return small_state_bytes(V, D) + static_cast<size_t>(big_elems(V, C, D, V | 1)) * sizeof(float) <= MTA_SMEM_LIMIT;
 }
 
+static bool mta_use_probs_kernel(int C, int D) { return C <= PB_CPAD && D % PB_KC == 0; }
+
 size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D) {
-  if (mta_fits_smem(V, C, D)) return 0;
-  return static_cast<size_t>(n_problems) * static_cast<size_t>(big_elems(V, C, D, V | 1)) * sizeof(float);
+  size_t b = 0;
+  if (mta_use_probs_kernel(C, D)) b += (static_cast<size_t>(n_problems) * V * C * sizeof(float) + 255) / 256 * 256;
+  if (!mta_fits_smem(V, C, D))
+    b += static_cast<size_t>(n_problems) * static_cast<size_t>(big_elems(V, C, D, V | 1)) * sizeof(float);
+  return b;
 }
 
 cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, int D, const MtaParams& p,
@@ -327,6 +458,27 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
   const size_t small = small_state_bytes(V, D);
   const long long be = big_elems(V, C, D, a.ldA);
   a.in_smem = mta_fits_smem(V, C, D) ? 1 : 0;
+  a.P = nullptr;
+  if (mta_use_probs_kernel(C, D)) {
+    if (scratch == nullptr) return cudaErrorInvalidValue;
+    const size_t p_bytes = (static_cast<size_t>(n_sets) * I * V * C * sizeof(float) + 255) / 256 * 256;
+    ProbsDev pd;
+    for (int s2 = 0; s2 < MTA_MAX_SETS; ++s2) pd.sets[s2] = a.sets[s2];
+    pd.rows = static_cast<long long>(I) * V;
+    pd.C = C; pd.D = D; pd.scale = 100.0f / p.temperature; pd.P = scratch;
+    static bool pattr = false;
+    if (!pattr) {
+      cudaError_t e = cudaFuncSetAttribute(mta_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM);
+      if (e != cudaSuccess) return e;
+      pattr = true;
+    }
+    dim3 pgrid(static_cast<unsigned>((pd.rows + PB_ROWS - 1) / PB_ROWS), static_cast<unsigned>(n_sets));
+    mta_probs_kernel<<<pgrid, 256, PB_SMEM, stream>>>(pd);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    a.P = scratch;
+    scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + p_bytes);
+  }
   if (!a.in_smem && scratch == nullptr) return cudaErrorInvalidValue;
   a.scratch = scratch;
   a.scratch_stride = be;

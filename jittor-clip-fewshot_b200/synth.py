@@ -120,7 +120,7 @@ def make_views(seed, n_images, n_views, resolution=224, noise=0.5):
     pert[:, 0] = 0
     img = _upsample_bilinear(base, resolution) + _upsample_bilinear(pert, resolution)
     img = 1.0 / (1.0 + np.exp(-1.5 * img))
-    return img.astype(np.float32)
+    return np.ascontiguousarray(img, dtype=np.float32)
 
 
 def clip_normalize(images):

@@ -58,15 +58,17 @@ def test_solve_mta_large_view_count_uses_global_scratch(jb, cuda_dev):
 
 
 def test_solve_mta_identical_views(jb, cuda_dev):
-    """All views equal: distances 0, bandwidth 0 in the reference -> 0/0.  The kernel must not hang or
-    write out of range; the result is NaN exactly as the oracle's is."""
-    from oracle import solve_mta as o_mta
-    v = torch.nn.functional.normalize(torch.randn(1, 512), dim=-1)
+    """All views equal: every pairwise distance is 0 up to rounding, so the reference's bandwidth is 0 or
+    ~1e-4 depending on which way `x.x - 2 x.x + x.x` rounds -> the density is 0/0 = NaN or exactly 1.
+    Both outcomes occur in the fp32 oracle (it is a coin flip on rounding noise); the kernel must not hang
+    or write out of range, and must land on one of the two: all-NaN, or the common view itself."""
+    g = torch.Generator().manual_seed(123)
+    v = torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1)
     feats = v.repeat(9, 1)
     T = _texts(jb, 1)[0]
     m = jb.solve_mta(feats.to(cuda_dev), T.t().to(cuda_dev)).cpu()
-    ref = o_mta(feats, T.t())
-    assert torch.isnan(ref).all() == torch.isnan(m).all()
+    assert m.shape == (1, 512)
+    assert torch.isnan(m).all() or (m - v).abs().max() < 1e-5
 
 
 def test_channel_lp_and_logit_normalize(jb, cuda_dev):

@@ -127,7 +127,7 @@ def test_host_entry_point_and_chunking(jb, cuda_dev, tower):
         host_out = model.visual(torch.from_numpy(img).pin_memory(), apply_clip_norm=True, normalize=True)
         np_out = model.visual(img, apply_clip_norm=True, normalize=True)
     finally:
-        ctx.set_chunk_views(8192)
+        ctx.set_chunk_views(16384)
     assert not host_out.is_cuda and isinstance(np_out, np.ndarray)
     assert torch.equal(host_out, dev_out)
     assert np.array_equal(np_out, dev_out.numpy())

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of single kernels through the C-ABI (CUDA events, inputs larger than L2).
+    python tools/bench_kernel.py attention|layernorm|mta|gemm [n_views]"""
+import os
+import sys
+from ctypes import c_void_p
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import jclip_b200 as jb  # noqa: E402
+
+what = sys.argv[1]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+dev = torch.device("cuda", 0)
+ctx = jb.get_context(dev)
+ctx.bind_current_stream()
+lib, h = ctx.lib, ctx.handle
+P = lambda t: c_void_p(t.data_ptr())
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+if what == "attention":
+    T, H = 50, 12
+    qkv = torch.randn(n * T, 3 * 768, device=dev).to(torch.bfloat16)
+    out = torch.empty(n * T, 768, dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: jb._capi.check(lib.jcb_attention_bf16(h, P(qkv), n, T, H, P(out)), h))
+    gb = n * T * 768 * 8 / 1e9
+    print(f"attention cfg={os.environ.get('JCB_ATT_CFG', 'default')} n={n}: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+elif what == "layernorm":
+    x = torch.randn(n * 50, 768, device=dev)
+    g, b = torch.ones(768, device=dev), torch.zeros(768, device=dev)
+    y = torch.empty(n * 50, 768, dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: jb._capi.check(lib.jcb_layernorm_bf16(h, P(x), n * 50, 768, P(g), P(b), P(y)), h))
+    print(f"layernorm n={n}: {ms:.3f} ms  {n * 50 * 768 * 6 / 1e9 / ms * 1e3:.0f} GB/s")
+elif what == "mta":
+    I, V = n, 65
+    feats = torch.from_numpy(jb.synth.make_unit_views(0, I, V)).to(dev)
+    T = torch.from_numpy(jb.synth.make_text_features(seed=1)).t().contiguous().to(dev)
+    ms = timeit(lambda: jb.solve_mta_batched(feats, T), iters=5, warm=2)
+    print(f"mta I={I} V={V}: {ms:.3f} ms  ({ms / I * 1e3:.2f} us/image)")
+elif what == "gemm":
+    shapes = {"qkv": (2304, 768, 0), "out": (768, 768, 2), "fc1": (3072, 768, 1), "fc2": (768, 3072, 2)}
+    M = n * 50
+    for name, (N, K, epi) in shapes.items():
+        A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        B = (torch.randn(N, K, device=dev) * K ** -0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 2 else torch.bfloat16)
+        ms = timeit(lambda: jb._capi.check(lib.jcb_gemm_bf16(h, P(A), P(B), M, N, K, P(bias), epi, P(out), N), h))
+        print(f"gemm {name} M={M} N={N} K={K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")

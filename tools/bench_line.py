@@ -1,0 +1,14 @@
+#!/usr/bin/env python
+"""One-line digest of a bench.py JSON line (stdin or file)."""
+import json
+import sys
+d = json.loads((open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin).read().strip().splitlines()[-1])
+pk = d["roofline"]["per_kernel"]
+e2e = d["e2e"]["value"] if d.get("e2e") else float("nan")
+print("%.1f img/s | e2e %.1f | %.2f ms/step | gemm %.0f TF/s frac %.3f | step frac %.3f" % (
+    d["value"], e2e, d["ms_per_step"], d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline"]["whole_step_frac"]))
+print("  " + " ".join("%s=%.2f(%s)" % (k, v["ms_per_step"], ("%.0fTF" % v["tflops"]) if "tflops" in v else ("%.0fGB/s" % v.get("gbs", 0)))
+                      for k, v in pk.items()))
+print("  clocks", d["clocks"], "launches", d["gpu_launches"])
+if d.get("cpu_baseline"):
+    print("  cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], d["cpu_baseline"].get("top5_agreement_with_gpu"))
