@@ -113,6 +113,8 @@ typedef struct jcb_vit_config {
   int32_t patch;       /* 32   visual.conv1.weight.shape[-1]                 jclip/model.py:244 */
   int32_t resolution;  /* 224  patch * sqrt(pos_emb rows - 1)                jclip/model.py:245-247 */
   int32_t embed_dim;   /* 512  visual.proj.shape[1] */
+  int32_t vpt_tokens;  /* 0, or 4 for the IVLP / VPT tower of `clip1.load_vlp` (jclip/model1.py:161-164, :192-196):
+                          learnable tokens `visual.VPT` appended after the positional embedding, before ln_pre */
 } jcb_vit_config;
 
 /* Stands in for `build_model(state_dict)` restricted to the image tower (jclip/model.py:235-285). */

@@ -28,7 +28,7 @@ _ERR_NAMES = {-1: "JCB_E_INVALID", -2: "JCB_E_CUDA", -3: "JCB_E_STATE", -4: "JCB
 
 class VitConfig(Structure):
     _fields_ = [("layers", c_int32), ("width", c_int32), ("patch", c_int32), ("resolution", c_int32),
-                ("embed_dim", c_int32)]
+                ("embed_dim", c_int32), ("vpt_tokens", c_int32)]
 
 
 class MtaParams(Structure):

@@ -173,6 +173,7 @@ struct jcb_vit {
   void* arena = nullptr;                            // device weights
   size_t arena_bytes = 0;
   __nv_bfloat16* conv_w = nullptr;
+  float *vpt = nullptr;
   float *cls = nullptr, *pos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr,
         *ln_post_b = nullptr, *proj = nullptr;
   std::vector<LayerDev> layers;
@@ -187,7 +188,8 @@ void build_expected(jcb_vit* v) {
   auto& e = v->expected;
   e["visual.conv1.weight"] = W * 3 * P * P;
   e["visual.class_embedding"] = W;
-  e["visual.positional_embedding"] = T * W;
+  e["visual.positional_embedding"] = (T - v->cfg.vpt_tokens) * W;
+  if (v->cfg.vpt_tokens > 0) e["visual.VPT"] = static_cast<int64_t>(v->cfg.vpt_tokens) * W;
   e["visual.ln_pre.weight"] = W;
   e["visual.ln_pre.bias"] = W;
   e["visual.ln_post.weight"] = W;
@@ -263,7 +265,7 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
                     v->pos, GG, T);
   if (rc) return rc;
   // class token + ln_pre (residual stream) + layer 0's ln_1
-  LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
+  LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->vpt, v->cfg.vpt_tokens, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
                               v->layers[0].ln1_b, w.ln_out, s));
   for (int l = 0; l < v->cfg.layers; ++l) {
     const LayerDev& L = v->layers[l];
@@ -498,14 +500,15 @@ int jcb_vit_create(jcb_ctx* ctx, const jcb_vit_config* cfg, jcb_vit** out) {
   if (cfg->layers < 1 || cfg->layers > 64) return fail(ctx, JCB_E_INVALID, "layers=%d unsupported", cfg->layers);
   if (cfg->width % 256 != 0 || cfg->width > 1024 || cfg->width < 256)
     return fail(ctx, JCB_E_INVALID, "width=%d unsupported (need a multiple of 256 in [256, 1024])", cfg->width);
-  if (cfg->patch % 8 != 0 || cfg->resolution % cfg->patch != 0)
+  if (cfg->patch % 16 != 0 || cfg->resolution % cfg->patch != 0)
     return fail(ctx, JCB_E_INVALID, "patch=%d / resolution=%d unsupported", cfg->patch, cfg->resolution);
   if (cfg->embed_dim != 512) return fail(ctx, JCB_E_INVALID, "embed_dim=%d unsupported (512 only)", cfg->embed_dim);
+  if (cfg->vpt_tokens < 0 || cfg->vpt_tokens > 14) return fail(ctx, JCB_E_INVALID, "vpt_tokens=%d unsupported", cfg->vpt_tokens);
   jcb_vit* v = new jcb_vit();
   v->ctx = ctx;
   v->cfg = *cfg;
   v->grid = cfg->resolution / cfg->patch;
-  v->tokens = v->grid * v->grid + 1;
+  v->tokens = v->grid * v->grid + 1 + cfg->vpt_tokens;
   v->heads = cfg->width / 64;  // jclip/model.py:152
   v->kpatch = 3 * cfg->patch * cfg->patch;
   if (v->tokens > 64 || v->heads % 4 != 0 || v->kpatch % 64 != 0) {
@@ -568,7 +571,7 @@ int jcb_vit_finalize(jcb_vit* v) {
   const size_t W = v->cfg.width, E = v->cfg.embed_dim, T = v->tokens, KP = v->kpatch, L = v->cfg.layers;
   // arena: bf16 GEMM operands, then fp32 vectors
   size_t bytes = align_up(W * KP * 2) + L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2));
-  bytes += 8 * align_up(std::max(W * E, T * W) * 4) + L * 8 * align_up(4 * W * 4);
+  bytes += 9 * align_up(std::max(W * E, T * W) * 4) + L * 8 * align_up(4 * W * 4);
   const size_t tmp_elems = 4 * W * W;  // largest single tensor (c_fc / c_proj / conv1 for P=32)
   const size_t tmp_bytes = align_up(std::max(tmp_elems, W * KP) * 4) + 2 * align_up(256 * W * 4);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -621,6 +624,7 @@ int jcb_vit_finalize(jcb_vit* v) {
   if ((rc = up_bf16("visual.conv1.weight", W, KP, &v->conv_w, {}))) return rc;
   if ((rc = up_f32("visual.class_embedding", &v->cls))) return rc;
   if ((rc = up_f32("visual.positional_embedding", &v->pos))) return rc;
+  if (v->cfg.vpt_tokens > 0 && (rc = up_f32("visual.VPT", &v->vpt))) return rc;
   if ((rc = up_f32("visual.ln_pre.weight", &v->ln_pre_g))) return rc;
   if ((rc = up_f32("visual.ln_pre.bias", &v->ln_pre_b))) return rc;
   if ((rc = up_f32("visual.ln_post.weight", &v->ln_post_g))) return rc;

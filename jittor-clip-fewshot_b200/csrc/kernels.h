@@ -40,11 +40,12 @@ const char* gemm_init_driver_api();
 enum ImageDtype : int { IMG_F32 = 0, IMG_BF16 = 1, IMG_U8 = 2 };
 cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
                           int apply_norm, __nv_bfloat16* patches, cudaStream_t stream);
-// tokens [B*T, W] fp32: row t==0 of each view := cls + pos[0] (rows t>0 already hold patch+pos);
+// tokens [B*T, W] fp32: row t==0 of each view := cls + pos[0]; rows 1..T-1-n_vpt already hold patch+pos;
+// the last n_vpt rows := vpt[0..n_vpt) (IVLP / VPT prompt tokens, no positional embedding);
 // then x := ln_pre(x) written back in place (the residual stream), and y := ln_1(x) as bf16.
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
-                            const float* g_pre, const float* b_pre, const float* g1, const float* b1,
-                            __nv_bfloat16* y, cudaStream_t stream);
+                            const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
+                            const float* b1, __nv_bfloat16* y, cudaStream_t stream);
 // y_bf16[r,:] = LayerNorm(x_f32[r,:]) * g + b   (eps 1e-5, biased variance), W == 768 or any W % 128 == 0 <= 1024
 cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
                              __nv_bfloat16* y, cudaStream_t stream);

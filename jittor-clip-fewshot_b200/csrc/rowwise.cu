@@ -18,18 +18,21 @@ __constant__ float c_clip_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
 // ------------------------------------------------------------------------------------------ im2col
+// One thread converts EPT consecutive pixels of one image row segment (a patch row is P = 32 pixels, so a
+// segment never crosses a patch): 16 B loaded per thread whatever the pixel type (4 fp32, 8 bf16, 16 u8).
 template <int DT>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const void* __restrict__ images, long long n_views, int R, int P, int apply_norm,
               __nv_bfloat16* __restrict__ patches) {
+  constexpr int EPT = DT == IMG_F32 ? 8 : (DT == IMG_BF16 ? 8 : 16);
   const int G = R / P;
   const int K = 3 * P * P;
-  const int chunks_per_row = K / 8;
+  const int chunks_per_row = K / EPT;
   const long long total = n_views * G * G * chunks_per_row;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const long long row = idx / chunks_per_row;         // (view, py, px)
-  const int col = static_cast<int>(idx % chunks_per_row) * 8;  // (c, i, j) with j % 8 == 0
+  const long long row = idx / chunks_per_row;                    // (view, py, px)
+  const int col = static_cast<int>(idx % chunks_per_row) * EPT;  // (c, i, j) with j % EPT == 0
   const int c = col / (P * P);
   const int i = (col % (P * P)) / P;
   const int j = col % P;
@@ -37,7 +40,7 @@ im2col_kernel(const void* __restrict__ images, long long n_views, int R, int P, 
   const int pidx = static_cast<int>(row % (G * G));
   const int py = pidx / G, px = pidx % G;
   const long long src = ((b * 3 + c) * R + (py * P + i)) * R + px * P + j;
-  float f[8];
+  float f[EPT];
   if (DT == IMG_F32) {
     const float4* s = reinterpret_cast<const float4*>(static_cast<const float*>(images) + src);
     const float4 a = __ldg(s), d = __ldg(s + 1);
@@ -48,20 +51,24 @@ im2col_kernel(const void* __restrict__ images, long long n_views, int R, int P, 
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
   } else {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(images) + src));
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(images) + src));
     const uint8_t* u = reinterpret_cast<const uint8_t*>(&a);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = static_cast<float>(u[e]) * (1.0f / 255.0f);
+    for (int e = 0; e < EPT; ++e) f[e] = static_cast<float>(u[e]) * (1.0f / 255.0f);
   }
   if (apply_norm) {
     const float m = c_clip_mean[c], s = c_clip_std[c];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = (f[e] - m) / s;
+    for (int e = 0; e < EPT; ++e) f[e] = (f[e] - m) / s;
   }
-  uint4 o;
-  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-  *reinterpret_cast<uint4*>(patches + row * K + col) = o;
+  uint4* dst = reinterpret_cast<uint4*>(patches + row * K + col);
+#pragma unroll
+  for (int h = 0; h < EPT / 8; ++h) {
+    uint4 o;
+    o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]); o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
+    o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]); o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
+    dst[h] = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
@@ -129,7 +136,8 @@ layernorm_kernel(const float* __restrict__ x, long long rows, const float* __res
 template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* __restrict__ cls,
-                const float* __restrict__ pos, const float* __restrict__ g_pre, const float* __restrict__ b_pre,
+                const float* __restrict__ pos, const float* __restrict__ vpt, int n_vpt,
+                const float* __restrict__ g_pre, const float* __restrict__ b_pre,
                 const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y) {
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
@@ -146,6 +154,11 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
       const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + lane + 32 * i);
       v[i] = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
     }
+  } else if (t >= T - n_vpt) {
+    // IVLP / VPT prompt tokens, appended after the positional embedding  (jclip/model1.py:192-196)
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      v[i] = __ldg(reinterpret_cast<const float4*>(vpt + static_cast<long long>(t - (T - n_vpt)) * W) + lane + 32 * i);
   } else {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];  // patch embedding + pos (GEMM epilogue)
@@ -257,9 +270,10 @@ __global__ void merge_lora_cast_kernel(const float* __restrict__ W, const float*
 
 cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
                           int apply_norm, __nv_bfloat16* patches, cudaStream_t stream) {
-  if (resolution % patch != 0 || patch % 8 != 0) return cudaErrorInvalidValue;
+  if (resolution % patch != 0 || patch % 16 != 0) return cudaErrorInvalidValue;
   const int G = resolution / patch;
-  const long long total = n_views * G * G * (3 * patch * patch / 8);
+  const int ept = img_dtype == IMG_U8 ? 16 : 8;
+  const long long total = n_views * G * G * (3 * patch * patch / ept);
   if (total == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   switch (img_dtype) {
@@ -289,14 +303,14 @@ cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g
 }
 
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
-                            const float* g_pre, const float* b_pre, const float* g1, const float* b1,
-                            __nv_bfloat16* y, cudaStream_t stream) {
+                            const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
+                            const float* b1, __nv_bfloat16* y, cudaStream_t stream) {
   if (W % 128 != 0) return cudaErrorInvalidValue;
   const long long rows = n_views * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
-  JCB_DISPATCH_NV(W, (embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(tokens, rows, T, cls, pos, g_pre,
-                                                                           b_pre, g1, b1, y)));
+  JCB_DISPATCH_NV(W, (embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(tokens, rows, T, cls, pos, vpt,
+                                                                           n_vpt, g_pre, b_pre, g1, b1, y)));
   return cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ import torch
 
 from .model import build_model
 
-__all__ = ["available_models", "load", "tokenize"]
+__all__ = ["available_models", "load", "load_vlp", "tokenize"]
 
 _MODELS = {   # names of reference jclip/clip.py:19-38 -> checkpoint file name
     "RN50": "RN50.pt", "RN101": "RN101.pt", "RN50x4": "RN50x4.pt", "RN50x16": "RN50x16.pt", "RN50x64": "RN50x64.pt",
@@ -133,7 +133,15 @@ def load_state_dict(path):
     return sd
 
 
-def load(name, download_root=None, mode='vit'):
+IVLP_DESIGN = {"trainer": "IVLP", "vision_depth": 3, "language_depth": 3, "vision_ctx": 4, "language_ctx": 4}
+
+
+def load_vlp(name, download_root=None, mode='vit'):
+    """reference jclip/clip1.py:189-213: the IVLP / VPT model (54-token image tower)."""
+    return load(name, download_root, mode, design_details=dict(IVLP_DESIGN))
+
+
+def load(name, download_root=None, mode='vit', design_details=None):
     """reference jclip/clip.py:170-187."""
     if name in _MODELS:
         root = download_root or os.path.expanduser("~/.cache/clip")
@@ -147,7 +155,7 @@ def load(name, download_root=None, mode='vit'):
         raise RuntimeError(f"Model {name} not found; available models = {available_models()}")
     if mode != 'vit':
         raise NotImplementedError("mode != 'vit' (ModifiedResNet, jclip/model_res.py) is outside the hot path")
-    model = build_model(load_state_dict(model_path))
+    model = build_model(load_state_dict(model_path), design_details)
     n_px = model.visual.input_resolution
     return model, _transform1(n_px), _transform2(n_px), tfm_train_base(n_px), tfm_train_base1(n_px)
 

@@ -193,10 +193,20 @@ _LORA_PROJ = (("q_proj", _capi.PROJ_Q), ("k_proj", _capi.PROJ_K), ("v_proj", _ca
 class VisionTransformer(Module):
     """Parameter container + native engine of the image tower (reference jclip/model.py:80-126)."""
 
-    def __init__(self, sd, input_resolution, patch_size, width, layers, heads, output_dim):
+    def __init__(self, sd, input_resolution, patch_size, width, layers, heads, output_dim, design_details=None):
         super().__init__()
         self.input_resolution, self.output_dim = input_resolution, output_dim
         self.patch_size, self.width, self.layers, self.heads = patch_size, width, layers, heads
+        # IVLP / VPT tower (reference jclip/model1.py:161-164, :192-196): n_ctx learnable tokens appended after
+        # the positional embedding.  The vision transformer is built with prompts_needed=0 (model1.py:175),
+        # so there are no per-layer prompts: `visual.VPT` is the only extra parameter.
+        n_ctx = int((design_details or {}).get("vision_ctx", 0)) if "visual.VPT" not in sd else int(sd["visual.VPT"].shape[0])
+        self.n_ctx = n_ctx
+        if n_ctx > 0:
+            vpt = sd.get("visual.VPT")
+            if vpt is None:   # normal_(ctx_vectors, std=0.02), model1.py:163
+                vpt = (np.random.default_rng(0).standard_normal((n_ctx, width)) * 0.02).astype(np.float32)
+            self.VPT = Param(vpt, self)
         self.conv1 = Conv2d(sd["visual.conv1.weight"], self)
         self.class_embedding = Param(sd["visual.class_embedding"], self)
         self.positional_embedding = Param(sd["visual.positional_embedding"], self)
@@ -218,7 +228,8 @@ class VisionTransformer(Module):
         if self._vit is not None and self._ctx is not ctx:
             self.release()
         if self._vit is None:
-            cfg = _capi.VitConfig(self.layers, self.width, self.patch_size, self.input_resolution, self.output_dim)
+            cfg = _capi.VitConfig(self.layers, self.width, self.patch_size, self.input_resolution, self.output_dim,
+                                  self.n_ctx)
             h = c_void_p()
             check(ctx.lib.jcb_vit_create(ctx.handle, byref(cfg), byref(h)), ctx.handle)
             self._vit, self._ctx, self._dirty = h, ctx, True
@@ -307,7 +318,7 @@ class VisionTransformer(Module):
         with torch.cuda.device(t.device):
             ctx, vit = self._engine(t.device)
             ctx.bind_current_stream()
-            T = (self.input_resolution // self.patch_size) ** 2 + 1
+            T = (self.input_resolution // self.patch_size) ** 2 + 1 + self.n_ctx
             out = torch.empty((t.shape[0], T, self.width), dtype=torch.float32, device=t.device)
             check(ctx.lib.jcb_vit_debug_tokens(vit, ptr(t), img_dtype_code(t), t.shape[0], int(apply_clip_norm), ptr(out)),
                   ctx.handle)
@@ -324,12 +335,13 @@ class CLIP(Module):
     """reference jclip/model.py:129-232."""
 
     def __init__(self, sd, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size,
-                 context_length, vocab_size, transformer_width, transformer_heads, transformer_layers):
+                 context_length, vocab_size, transformer_width, transformer_heads, transformer_layers,
+                 design_details=None):
         super().__init__()
         self.context_length = context_length
         vision_heads = vision_width // 64                         # jclip/model.py:152
         self.visual = VisionTransformer(sd, image_resolution, vision_patch_size, vision_width, vision_layers,
-                                        vision_heads, embed_dim)
+                                        vision_heads, embed_dim, design_details)
         self.transformer = Transformer(sd, "transformer.", transformer_width, transformer_layers, transformer_heads,
                                        None, attn_mask=self.build_attention_mask())
         self.vocab_size = vocab_size
@@ -423,8 +435,9 @@ def _text_attention(attn, x, mask, dev):
     return y
 
 
-def build_model(state_dict: Dict[str, np.ndarray]):
-    """Shape inference from state-dict keys, exactly as the reference does (jclip/model.py:235-285)."""
+def build_model(state_dict: Dict[str, np.ndarray], design_details=None):
+    """Shape inference from state-dict keys, exactly as the reference does (jclip/model.py:235-285).
+    With `design_details` (or a `visual.VPT` key) this is jclip/model1.py:322-374, the IVLP variant."""
     if "visual.proj" not in state_dict:
         raise NotImplementedError("only ViT checkpoints are supported on this path (mode='vit'); the ResNet "
                                   "variant jclip/model_res.py is outside the hot path")
@@ -441,5 +454,5 @@ def build_model(state_dict: Dict[str, np.ndarray]):
     transformer_heads = transformer_width // 64
     transformer_layers = len(set(k.split(".")[2] for k in sd if k.startswith("transformer.resblocks")))
     model = CLIP(sd, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, context_length,
-                 vocab_size, transformer_width, transformer_heads, transformer_layers)
+                 vocab_size, transformer_width, transformer_heads, transformer_layers, design_details)
     return model.eval()

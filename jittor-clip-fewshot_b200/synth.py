@@ -16,7 +16,7 @@ EMBED_DIM = 512
 
 
 def make_vit_state_dict(seed=0, layers=12, width=768, patch=32, resolution=224, embed_dim=EMBED_DIM,
-                        with_text_stub=True, text_layers=1):
+                        with_text_stub=True, text_layers=1, vpt_tokens=0):
     """Random-init CLIP state dict (numpy fp32) with the reference's key names (vision tower + the
     few text-side keys `build_model` reads shapes from)."""
     rng = np.random.default_rng(seed)
@@ -37,6 +37,8 @@ def make_vit_state_dict(seed=0, layers=12, width=768, patch=32, resolution=224, 
         "visual.ln_post.bias": n((width,), 0.02),
         "visual.proj": n((width, embed_dim), scale),
     }
+    if vpt_tokens:
+        sd["visual.VPT"] = n((vpt_tokens, width), 0.02)      # reference jclip/model1.py:161-164
     for i in range(layers):
         p = f"visual.transformer.resblocks.{i}."
         sd[p + "attn.in_proj_weight"] = n((3 * width, width), attn_std)

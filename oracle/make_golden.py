@@ -7,7 +7,8 @@ Run in the build container only (it reads /root/reference, which does not exist 
     python oracle/make_golden.py [--reference /root/reference] [--out tests/golden/ref_on_shim.npz]
 
 What is executed, unmodified, from the reference checkout:
-  * jclip/mha.py and jclip/model.py (imported as modules): build_model -> CLIP.encode_image
+  * jclip/mha.py, jclip/model.py and jclip/model1.py (imported as modules): build_model -> CLIP.encode_image,
+    for the plain tower and for the 54-token IVLP / VPT tower
   * from test.py, by source extraction (the file cannot be imported: it reads `text_template/` and
     dataset files at import time): LoRALayer, LinearLoRA, _canonical_mask,
     scaled_dot_product_attention, _none_or_dtype, PlainMultiheadAttentionLoRA, apply_lora,
@@ -61,7 +62,7 @@ def load_ref_jclip(ref):
     pkg = types.ModuleType("_refjclip")
     pkg.__path__ = [os.path.join(ref, "jclip")]
     sys.modules["_refjclip"] = pkg
-    for name in ("mha", "model"):
+    for name in ("mha", "model", "model1"):
         spec = importlib.util.spec_from_file_location(f"_refjclip.{name}", os.path.join(ref, "jclip", f"{name}.py"))
         mod = importlib.util.module_from_spec(spec)
         sys.modules[f"_refjclip.{name}"] = mod
@@ -140,6 +141,14 @@ def main():
         model2.eval()
         with torch.no_grad():
             out["tower_lora_qkvo"] = model2.encode_image(jt.array(imgs)).numpy()
+
+        # ---------------- IVLP / VPT image tower of `clip1.load_vlp` (jclip/model1.py): 54 tokens
+        sd_vlp = synth.make_vit_state_dict(seed=25, layers=2, vpt_tokens=4)
+        out["tower_vlp_sd_checksum"] = checksum(np.concatenate([sd_vlp[k].ravel() for k in sorted(sd_vlp)]))
+        design = {"trainer": "IVLP", "vision_depth": 3, "language_depth": 3, "vision_ctx": 4, "language_ctx": 4}
+        model_vlp = refpkg.model1.build_model({k: jt.array(v) for k, v in sd_vlp.items()}, design)
+        with torch.no_grad():
+            out["tower_vlp"] = model_vlp.encode_image(jt.array(imgs)).numpy()
 
         # ---------------- solve_mta (test.py) and its ood.py twin
         T = synth.make_text_features(seed=31)

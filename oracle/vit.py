@@ -126,6 +126,11 @@ def vit_encode_image(sd, images, lora=None, scaling=0.5, apply_clip_norm=False, 
     cls = g("visual.class_embedding").view(1, 1, -1).expand(x.shape[0], 1, -1)
     x = torch.cat([cls, x], dim=1)                                       # :109-113
     x = x + g("visual.positional_embedding")                             # :114
+    if "visual.VPT" in sd:
+        # IVLP / VPT tower (jclip/model1.py:192-196): prompt tokens appended after pos-embed, before ln_pre;
+        # the vision transformer has prompts_needed=0 (model1.py:175) so no layer replaces them
+        vpt = g("visual.VPT")
+        x = torch.cat([x, vpt.unsqueeze(0).expand(x.shape[0], -1, -1)], dim=1)
     x = layer_norm(x, g("visual.ln_pre.weight"), g("visual.ln_pre.bias"))  # :115
     for i in range(layers):                                              # :117-119 (layout permutes are no-ops here)
         p = f"visual.transformer.resblocks.{i}."

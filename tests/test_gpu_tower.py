@@ -84,6 +84,34 @@ def test_encode_image_lora_matches_oracle(jb, cuda_dev, params):
     assert (_cos(out, ref) > _cos(out, ref0)).all()
 
 
+def test_ivlp_vpt_tower_matches_oracle(jb, cuda_dev):
+    """54-token IVLP / VPT tower (`clip1.load_vlp`, jclip/model1.py:161-196) with LoRA on q,k,v: what test.py's
+    primary `clip_model` is (test.py:1855)."""
+    from oracle import vit_encode_image
+    sd = jb.synth.make_vit_state_dict(seed=3, vpt_tokens=4)
+    sd["visual.VPT"] = sd["visual.VPT"] * 25.0          # make the prompt tokens count (0.5 instead of 0.02 std)
+    model = jb.jclip.build_model(sd, dict(jb.clip.IVLP_DESIGN))
+    assert model.visual.n_ctx == 4
+    layers = jb.apply_lora(_args(), model)
+    lora = jb.synth.make_lora(seed=8, b_std=0.3)
+    for i, layer in enumerate(layers):
+        for name, (A, B) in lora[i].items():
+            getattr(layer, name).w_lora_A.data = A
+            getattr(layer, name).w_lora_B.data = B
+    imgs = jb.synth.make_views(13, 1, 5).reshape(5, 3, 224, 224)
+    x = torch.from_numpy(imgs).to(cuda_dev)
+    ref_tok = vit_encode_image(sd, imgs, lora=lora, scaling=0.5, apply_clip_norm=True, return_tokens=True)
+    tok = model.visual.debug_tokens(x, apply_clip_norm=True).cpu()
+    assert tok.shape == ref_tok.shape == (5, 54, 768)
+    assert _cos(tok.reshape(-1, 768), ref_tok.reshape(-1, 768)).min() >= 0.9995
+    ref = vit_encode_image(sd, imgs, lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    out = model.visual(x, apply_clip_norm=True, normalize=True).cpu()
+    assert _cos(out, ref).min() >= 0.9995
+    sd0 = {k: v for k, v in sd.items() if k != "visual.VPT"}
+    ref0 = vit_encode_image(sd0, imgs, lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    assert _cos(ref, ref0).min() < 0.9999 and (_cos(out, ref) > _cos(out, ref0)).all()
+
+
 def test_lora_update_refreshes_packed_weights(jb, cuda_dev, tower):
     sd, _ = tower
     model = jb.jclip.build_model(sd)

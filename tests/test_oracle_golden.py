@@ -52,6 +52,18 @@ def test_tower_lora(jb, g, tower_inputs):
     assert np.abs(f2 - g["tower_lora_qkvo"]).max() <= 2e-5
 
 
+def test_tower_ivlp_vpt(jb, g, tower_inputs):
+    """The 54-token IVLP / VPT tower (reference jclip/model1.py via clip1.load_vlp)."""
+    from oracle import vit_encode_image
+    _, imgs = tower_inputs
+    sd = jb.synth.make_vit_state_dict(seed=25, layers=2, vpt_tokens=4)
+    assert np.allclose(_checksum(np.concatenate([sd[k].ravel() for k in sorted(sd)])), g["tower_vlp_sd_checksum"], rtol=1e-6)
+    f = vit_encode_image(sd, imgs).numpy()
+    assert np.abs(f - g["tower_vlp"]).max() <= 2e-5
+    sd0 = {k: v for k, v in sd.items() if k != "visual.VPT"}
+    assert np.abs(vit_encode_image(sd0, imgs).numpy() - g["tower_vlp"]).max() > 1e-3     # the prompt tokens matter
+
+
 def test_merged_equals_applied(jb, tower_inputs):
     """W' = W + s B A (what the device packs) == the reference's un-merged eval math."""
     from oracle import merge_lora_into_state_dict, vit_encode_image
