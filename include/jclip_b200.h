@@ -100,7 +100,8 @@ int64_t jcb_ctx_launch_count(const jcb_ctx* ctx);
 #define JCB_KC_MTA 10
 #define JCB_KC_HEAD 11
 #define JCB_KC_OTHER 12
-#define JCB_KC_COUNT 13
+#define JCB_KC_TTA 13
+#define JCB_KC_COUNT 14
 int jcb_ctx_profile(jcb_ctx* ctx, int enable);
 int jcb_ctx_profile_read(const jcb_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches,
                          int64_t* timed_launches, double* flops, double* bytes);
@@ -149,6 +150,29 @@ int jcb_encode_image_host(jcb_vit* vit, const void* images_host, int img_dtype, 
 /* Final token tensor of the tower [n_views * tokens, width] fp32 before ln_post (tests / debugging). */
 int jcb_vit_debug_tokens(jcb_vit* vit, const void* images_dev, int img_dtype, int64_t n_views, int apply_clip_norm,
                          float* tokens_out_dev);
+
+/* ---------------------------------------------------------------- TTA views ------------------ */
+/* The step upstream of encode_image: the reference builds, per test image, 1 centre view + N random crops on
+ * the CPU with PIL (JtDataset.__getitem__, test.py:1547-1560; transforms test.py:1898-1903, ood.py:1084-1089,
+ * jclip/clip.py:102-135).  A view = take a box of a decoded uint8 image, resample it (Pillow's ImagingResample,
+ * reproduced bit for bit), keep an S x S window, optionally mirror it. */
+typedef struct jcb_src_image {
+  int64_t offset;             /* byte offset of this image ([height, width, 3] uint8, RGB interleaved) in src_dev */
+  int32_t height, width;
+} jcb_src_image;
+#define JCB_FILTER_BILINEAR 0 /* PIL.Image.BILINEAR: RandomResizedCrop's interpolation */
+#define JCB_FILTER_BICUBIC 1  /* PIL.Image.BICUBIC : Resize(256) of the centre view, jclip/clip.py:130-135 */
+typedef struct jcb_view_job {
+  int32_t image;                      /* index into images[] */
+  int32_t top, left, crop_h, crop_w;  /* `img.crop((left, top, left + crop_w, top + crop_h))` */
+  int32_t out_h, out_w;               /* `.resize((out_w, out_h), filter)` */
+  int32_t off_y, off_x;               /* window kept of the resized crop: CenterCrop offsets, 0 for random crops */
+  int32_t filter, flip, reserved;
+} jcb_view_job;
+/* out_dev [n_jobs, 3, size, size] uint8 (planar, the layout jcb_encode_image / jcb_pipeline take with
+ * JCB_IMG_U8).  images / jobs are host arrays; they are validated and copied. */
+int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+                  const jcb_view_job* jobs, int64_t n_jobs, int32_t size, uint8_t* out_dev);
 
 /* ---------------------------------------------------------------- MTA ------------------------ */
 typedef struct jcb_mta_params {

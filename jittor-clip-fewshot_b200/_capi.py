@@ -19,7 +19,8 @@ IMG_F32, IMG_BF16, IMG_U8 = 0, 1, 2
 PROJ_Q, PROJ_K, PROJ_V, PROJ_O = 0, 1, 2, 3
 SCORE_NAMES = ("logits", "cs", "cs1", "cs2", "cs3", "cs4", "cs5")
 SCORE_INDEX = {n: i for i, n in enumerate(SCORE_NAMES)}
-KC_COUNT = 13
+KC_COUNT = 14
+FILTER_BILINEAR, FILTER_BICUBIC = 0, 1
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 0, 1, 2, 3, 4
 
 _ERR_NAMES = {-1: "JCB_E_INVALID", -2: "JCB_E_CUDA", -3: "JCB_E_STATE", -4: "JCB_E_NO_DEVICE", -5: "JCB_E_KERNEL",
@@ -38,6 +39,16 @@ class MtaParams(Structure):
 
 class HeadWeights(Structure):
     _fields_ = [("scale1", c_void_p), ("bias1", c_void_p), ("fc_w", c_void_p), ("fc_b", c_void_p)]
+
+
+class SrcImage(Structure):
+    _fields_ = [("offset", c_int64), ("height", c_int32), ("width", c_int32)]
+
+
+class ViewJob(Structure):
+    _fields_ = [("image", c_int32), ("top", c_int32), ("left", c_int32), ("crop_h", c_int32), ("crop_w", c_int32),
+                ("out_h", c_int32), ("out_w", c_int32), ("off_y", c_int32), ("off_x", c_int32), ("filter", c_int32),
+                ("flip", c_int32), ("reserved", c_int32)]
 
 
 class PipelineArgs(Structure):
@@ -76,6 +87,8 @@ PROTOTYPES = {
     "jcb_encode_image": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "jcb_encode_image_host": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "jcb_vit_debug_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "jcb_tta_views": (c_int, [c_void_p, c_void_p, POINTER(SrcImage), c_int32, POINTER(ViewJob), c_int64, c_int32,
+                              c_void_p]),
     "jcb_mta_default_params": (None, [POINTER(MtaParams)]),
     "jcb_mta": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, POINTER(MtaParams),
                         c_void_p, c_void_p]),

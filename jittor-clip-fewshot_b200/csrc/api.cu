@@ -489,7 +489,7 @@ int jcb_ctx_profile_read(const jcb_ctx* ctx, int kernel_class, double* total_ms,
 
 const char* jcb_kernel_class_name(int kernel_class) {
   static const char* names[JCB_KC_COUNT] = {"im2col", "gemm_patch", "embed_ln", "gemm_qkv", "attention", "gemm_out",
-                                            "layernorm", "gemm_fc1", "gemm_fc2", "tail", "mta", "head", "other"};
+                                            "layernorm", "gemm_fc1", "gemm_fc2", "tail", "mta", "head", "other", "tta_views"};
   return kernel_class >= 0 && kernel_class < JCB_KC_COUNT ? names[kernel_class] : "?";
 }
 
@@ -699,6 +699,42 @@ int jcb_vit_debug_tokens(jcb_vit* v, const void* images_dev, int img_dtype, int6
   if ((rc = tower_forward(v, images_dev, img_dtype, n_views, apply_clip_norm, w))) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(tokens_out_dev, w.tokens, static_cast<size_t>(n_views) * v->tokens * v->cfg.width * 4,
                                 cudaMemcpyDeviceToDevice, ctx->stream));
+  return JCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+                  const jcb_view_job* jobs, int64_t n_jobs, int32_t size, uint8_t* out_dev) {
+  if (!ctx) return JCB_E_INVALID;
+  if (n_jobs < 0 || n_images < 0 || size < 8 || size > 1024) return fail(ctx, JCB_E_INVALID, "jcb_tta_views: bad sizes");
+  if (n_jobs == 0) return JCB_OK;
+  if (!src_dev || !images || !jobs || !out_dev) return fail(ctx, JCB_E_INVALID, "jcb_tta_views: null pointer");
+  static_assert(sizeof(jcb_src_image) == sizeof(TtaImage) && sizeof(jcb_view_job) == sizeof(TtaJob), "ABI structs");
+  DeviceGuard g(ctx->device);
+  const int64_t BATCH = 16384;   // views per launch pair (grid.y limit; bounds the intermediate scratch)
+  for (int64_t j0 = 0; j0 < n_jobs; j0 += BATCH) {
+    const int64_t nj = std::min(BATCH, n_jobs - j0);
+    std::vector<uint8_t> plan;
+    int kh = 0, kv = 0, mr = 0;
+    const char* err = nullptr;
+    const size_t tmp_bytes = tta_plan(reinterpret_cast<const TtaImage*>(images), n_images,
+                                      reinterpret_cast<const TtaJob*>(jobs + j0), nj, size, &plan, &kh, &kv, &mr, &err);
+    if (tmp_bytes == SIZE_MAX) return fail(ctx, JCB_E_INVALID, "jcb_tta_views: %s", err ? err : "invalid job");
+    const size_t plan_b = align_up(plan.size());
+    int rc = ws_reserve(ctx, plan_b + tmp_bytes);
+    if (rc) return rc;
+    uint8_t* plan_dev = static_cast<uint8_t*>(ctx->ws);
+    uint8_t* tmp = plan_dev + plan_b;
+    // the plan lives in pageable host memory: a synchronous-with-respect-to-host copy on the stream
+    CUDA_TRY(ctx, cudaMemcpyAsync(plan_dev, plan.data(), plan.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double macs = 0;
+    for (int64_t i = 0; i < nj; ++i) macs += 3.0 * size * (jobs[j0 + i].crop_h + size);
+    LAUNCH_P(ctx, JCB_KC_TTA, 0, static_cast<double>(nj) * 3 * size * size,
+             launch_tta(src_dev, plan_dev, nj, size, kh, kv, mr, tmp, out_dev + j0 * 3LL * size * size, ctx->stream));
+    ++ctx->launches;  // two kernels per call
+    (void)macs;
+  }
   return JCB_OK;
 }
 

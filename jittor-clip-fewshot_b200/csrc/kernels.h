@@ -1,6 +1,8 @@
 // Host-side launchers of the sm_100a kernels behind the C-ABI (include/jclip_b200.h).
 #pragma once
+#include <cstddef>
 #include <cstdint>
+#include <vector>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -101,5 +103,24 @@ cudaError_t launch_channel_lp(const float* feats, int64_t n, int C, int D, const
 cudaError_t launch_logit_normalize(const float* in, int64_t n, int C, float* out, cudaStream_t stream);
 cudaError_t launch_cosine_topk(const float* feats, const float* text, int64_t n, int C, int D, float scale, int k,
                                int32_t* out_topk, float* out_scores, cudaStream_t stream);
+
+
+// ---- TTA view generator (tta.cu) ---------------------------------------------------------------
+struct TtaImage {            // == jcb_src_image
+  int64_t offset;            // byte offset of the HWC uint8 image in the packed source buffer
+  int32_t height, width;
+};
+struct TtaJob {              // == jcb_view_job
+  int32_t image;
+  int32_t top, left, crop_h, crop_w;
+  int32_t out_h, out_w, off_y, off_x;
+  int32_t filter, flip, reserved;
+};
+// Validates the jobs and builds the device-side plan (opaque bytes to upload); returns the bytes of
+// intermediate scratch the two passes need, or SIZE_MAX with *err set.
+size_t tta_plan(const TtaImage* images, int n_images, const TtaJob* jobs, int64_t n_jobs, int S,
+                std::vector<uint8_t>* plan_bytes, int* kmax_h, int* kmax_v, int* max_rows, const char** err);
+cudaError_t launch_tta(const uint8_t* src, const void* plan_dev, int64_t n_jobs, int S, int kmax_h, int kmax_v,
+                       int max_rows, uint8_t* tmp, uint8_t* out, cudaStream_t stream);
 
 }  // namespace jcb

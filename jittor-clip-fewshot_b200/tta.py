@@ -1,0 +1,133 @@
+"""GPU test-time-augmentation view generator: decoded uint8 images -> the [I, 1+N, 3, 224, 224] uint8
+view batch `HotPath.evaluate_base` consumes ("next" row f1).
+
+Replaces `JtDataset.__getitem__` (reference test.py:1547-1560), which builds per test image
+
+    transformed_img  = [preprocess(img)]                         # Resize(256, BICUBIC) + CenterCrop(224)   jclip/clip.py:130-135
+    transformed_imgs = [transform_s(img) for _ in range(512)]    # RandomResizedCrop(224, scale=(0.2|0.5, 1)) + RandomHorizontalFlip(0.5)
+                                                                 # test.py:1898-1903, ood.py:1084-1089
+
+with PIL on the CPU (8 DataLoader workers).  Here the host only draws the crop boxes (a few floats
+per view) and uploads the decoded image once; cropping, resampling (Pillow's ImagingResample,
+reproduced bit for bit on uint8) and mirroring run in `jcb_tta_views`, so a 65-view batch costs one
+image of PCIe traffic instead of 65.  ToTensor's 1/255 and `tfm_clip` stay fused in the tower.
+
+The random stream is numpy's (Jittor's is not reproducible here); boxes are explicit and can be
+supplied by the caller for exact replay.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import check
+from .runtime import get_context, ptr
+
+
+def centre_view_params(W, H, resize=256, size=224):
+    """`Resize(256)` keeps the aspect ratio with the long side truncated by int() (jclip/clip.py:115-124);
+    `CenterCrop(224)` rounds its offsets.  Returns (new_w, new_h, left, top)."""
+    short, long = (W, H) if W <= H else (H, W)
+    if short == resize:
+        new_w, new_h = W, H
+    else:
+        new_short, new_long = resize, int(resize * long / short)
+        new_w, new_h = (new_short, new_long) if W <= H else (new_long, new_short)
+    return new_w, new_h, int(round((new_w - size) / 2.0)), int(round((new_h - size) / 2.0))
+
+
+def random_resized_crop_params(rng, W, H, scale=(0.5, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0)):
+    """`RandomResizedCrop.get_params`: 10 attempts of (area, log-uniform aspect) sampling, then the central-crop
+    fallback.  Returns (top, left, h, w)."""
+    area = H * W
+    lo, hi = math.log(ratio[0]), math.log(ratio[1])
+    for _ in range(10):
+        target_area = rng.uniform(scale[0], scale[1]) * area
+        aspect = math.exp(rng.uniform(lo, hi))
+        w = int(round(math.sqrt(target_area * aspect)))
+        h = int(round(math.sqrt(target_area / aspect)))
+        if 0 < w <= W and 0 < h <= H:
+            return int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1)), h, w
+    in_ratio = W / H
+    if in_ratio < min(ratio):
+        w, h = W, int(round(W / min(ratio)))
+    elif in_ratio > max(ratio):
+        h, w = H, int(round(H * max(ratio)))
+    else:
+        w, h = W, H
+    return (H - h) // 2, (W - w) // 2, h, w
+
+
+class TTAViews:
+    """images (list of [H, W, 3] uint8 arrays, any sizes) -> torch.uint8 [I, 1 + n_crops, 3, size, size] on the GPU;
+    view 0 is the centre view (reference test.py:1700 concatenates it first)."""
+
+    def __init__(self, n_crops=64, scale=(0.5, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), size=224, resize=256, flip_p=0.5,
+                 seed=0, device=None):
+        self.n_crops, self.scale, self.ratio = n_crops, scale, ratio
+        self.size, self.resize, self.flip_p = size, resize, flip_p
+        self.rng = np.random.default_rng(seed)
+        self.device = device
+
+    def draw_jobs(self, shapes):
+        """One centre job + n_crops crop jobs per (H, W): a (ViewJob * n) ctypes array."""
+        V = 1 + self.n_crops
+        jobs = (_capi.ViewJob * (len(shapes) * V))()
+        S = self.size
+        for i, (H, W) in enumerate(shapes):
+            if min(H, W) < 1:
+                raise ValueError("empty image")
+            new_w, new_h, left, top = centre_view_params(W, H, self.resize, S)
+            if new_w < S or new_h < S:
+                raise ValueError(f"image {i}: {W}x{H} resizes to {new_w}x{new_h}, smaller than the {S}-pixel centre crop")
+            j = jobs[i * V]
+            j.image, j.top, j.left, j.crop_h, j.crop_w = i, 0, 0, H, W
+            j.out_h, j.out_w, j.off_y, j.off_x = new_h, new_w, top, left
+            j.filter, j.flip = _capi.FILTER_BICUBIC, 0
+            for c in range(self.n_crops):
+                t, l, h, w = random_resized_crop_params(self.rng, W, H, self.scale, self.ratio)
+                j = jobs[i * V + 1 + c]
+                j.image, j.top, j.left, j.crop_h, j.crop_w = i, t, l, h, w
+                j.out_h, j.out_w, j.off_y, j.off_x = S, S, 0, 0
+                j.filter, j.flip = _capi.FILTER_BILINEAR, int(self.rng.random() < self.flip_p)
+        return jobs
+
+    def __call__(self, images, jobs=None):
+        imgs = [np.ascontiguousarray(np.asarray(im), dtype=np.uint8) for im in images]
+        for im in imgs:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError(f"expected [H, W, 3] uint8 RGB images, got {im.shape}")
+        shapes = [im.shape[:2] for im in imgs]
+        if jobs is None:
+            jobs = self.draw_jobs(shapes)
+        n_jobs = len(jobs)
+        if not torch.cuda.is_available():
+            raise RuntimeError("TTAViews runs on a B200 GPU only; there is no CPU fallback")
+        ctx = get_context(self.device)
+        dev = torch.device("cuda", ctx.device)
+        # pack the decoded images into one pinned buffer (16-byte aligned starts) and upload once
+        descs = (_capi.SrcImage * len(imgs))()
+        off = 0
+        for i, im in enumerate(imgs):
+            descs[i].offset, descs[i].height, descs[i].width = off, im.shape[0], im.shape[1]
+            off += (im.size + 15) // 16 * 16
+        host = torch.empty(max(off, 16), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        for d, im in zip(descs, imgs):
+            hv[d.offset:d.offset + im.size] = im.reshape(-1)
+        with torch.cuda.device(dev):
+            ctx.bind_current_stream()
+            src = host.to(dev, non_blocking=True)
+            out = torch.empty((n_jobs, 3, self.size, self.size), dtype=torch.uint8, device=dev)
+            check(ctx.lib.jcb_tta_views(ctx.handle, ptr(src), descs, len(imgs), jobs, n_jobs, self.size, ptr(out)),
+                  ctx.handle)
+        if len(imgs) and n_jobs % len(imgs) == 0:
+            return out.view(len(imgs), n_jobs // len(imgs), 3, self.size, self.size)
+        return out
+
+
+def jobs_to_tuples(jobs):
+    """[(image, top, left, crop_h, crop_w, out_h, out_w, off_y, off_x, filter, flip)] for tests / replay."""
+    return [(j.image, j.top, j.left, j.crop_h, j.crop_w, j.out_h, j.out_w, j.off_y, j.off_x, j.filter, j.flip) for j in jobs]

@@ -1,0 +1,100 @@
+"""GPU parity of the TTA view generator (jcb_tta_views) against Pillow itself, BIT FOR BIT on uint8:
+centre view = Resize(256, BICUBIC) + CenterCrop(224) (jclip/clip.py:130-135), crops = RandomResizedCrop
+(BILINEAR) + RandomHorizontalFlip (test.py:1898-1903)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _img(rng, H, W, smooth=True):
+    a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    if smooth:
+        a = (np.cumsum(np.cumsum(a.astype(np.float64), 0), 1) % 256).astype(np.uint8)
+    return a
+
+
+def _check(jb, imgs, gen):
+    from oracle import crops as C
+    jobs = gen.draw_jobs([im.shape[:2] for im in imgs])
+    out = gen(imgs, jobs=jobs).cpu().numpy()
+    out = out.reshape(-1, 3, gen.size, gen.size)
+    bad = 0
+    for k, j in enumerate(jb.tta.jobs_to_tuples(jobs)):
+        im = imgs[j[0]]
+        if j[9] == 1:
+            ref = C.pil_centre_view(im, gen.resize, gen.size)
+        else:
+            ref = C.pil_crop_view(im, j[1], j[2], j[3], j[4], j[10], gen.size)
+        if not np.array_equal(out[k], ref):
+            bad += 1
+            d = np.abs(out[k].astype(int) - ref.astype(int))
+            print("job", k, j, "max diff", d.max(), "frac", (d > 0).mean())
+    return bad, len(jobs)
+
+
+def test_views_match_pillow_bit_for_bit(jb, cuda_dev):
+    rng = np.random.default_rng(0)
+    imgs = [_img(rng, 375, 500), _img(rng, 500, 333), _img(rng, 256, 256), _img(rng, 240, 1000, smooth=False),
+            _img(rng, 1200, 900)]
+    gen = jb.TTAViews(n_crops=12, scale=(0.2, 1.0), seed=5)
+    bad, n = _check(jb, imgs, gen)
+    assert n == 5 * 13 and bad == 0
+
+
+def test_upscaling_and_tiny_crops(jb, cuda_dev):
+    """scale 0.05: crops far smaller than 224 px are magnified (filterscale = 1, two taps) -- reference
+    lora_train_vlp.py uses scale=(0.05, 1)."""
+    rng = np.random.default_rng(1)
+    imgs = [_img(rng, 120, 160), _img(rng, 300, 300, smooth=False)]
+    bad, n = _check(jb, imgs, jb.TTAViews(n_crops=20, scale=(0.05, 0.3), seed=9))
+    assert bad == 0 and n == 42
+
+
+def test_explicit_boxes_on_the_image_border(jb, cuda_dev):
+    from oracle import crops as C
+    rng = np.random.default_rng(2)
+    im = _img(rng, 400, 600)
+    gen = jb.TTAViews(n_crops=0)
+    boxes = [(0, 0, 400, 600, 0), (0, 0, 224, 224, 1), (176, 376, 224, 224, 0), (399 - 50, 599 - 70, 51, 71, 1),
+             (0, 0, 1, 1, 0), (10, 20, 300, 225, 1)]
+    jobs = (jb._capi.ViewJob * len(boxes))()
+    for j, (t, l, h, w, f) in zip(jobs, boxes):
+        j.image, j.top, j.left, j.crop_h, j.crop_w = 0, t, l, h, w
+        j.out_h, j.out_w, j.off_y, j.off_x, j.filter, j.flip = 224, 224, 0, 0, 0, f
+    out = gen([im], jobs=jobs).cpu().numpy().reshape(-1, 3, 224, 224)
+    for k, (t, l, h, w, f) in enumerate(boxes):
+        assert np.array_equal(out[k], C.pil_crop_view(im, t, l, h, w, f)), boxes[k]
+
+
+def test_rejects_bad_jobs(jb, cuda_dev):
+    im = np.zeros((100, 100, 3), np.uint8)
+    gen = jb.TTAViews(n_crops=0)
+    jobs = (jb._capi.ViewJob * 1)()
+    j = jobs[0]
+    j.image, j.top, j.left, j.crop_h, j.crop_w, j.out_h, j.out_w = 0, 50, 50, 60, 60, 224, 224   # box leaves the image
+    with pytest.raises(jb.JcbError):
+        gen([im], jobs=jobs)
+
+
+def test_views_feed_the_hot_path(jb, cuda_dev):
+    """images -> TTAViews -> HotPath.evaluate_base equals feeding the Pillow-built views (as uint8/255 floats)."""
+    from oracle import crops as C
+    rng = np.random.default_rng(3)
+    imgs = [_img(rng, 300, 400), _img(rng, 420, 380)]
+    gen = jb.TTAViews(n_crops=6, seed=2)
+    jobs = gen.draw_jobs([im.shape[:2] for im in imgs])
+    views = gen(imgs, jobs=jobs)
+    assert views.shape == (2, 7, 3, 224, 224) and views.dtype == torch.uint8 and views.is_cuda
+    ref = np.stack([C.pil_centre_view(imgs[j[0]]) if j[9] == 1 else C.pil_crop_view(imgs[j[0]], j[1], j[2], j[3], j[4], j[10])
+                    for j in jb.tta.jobs_to_tuples(jobs)]).reshape(2, 7, 3, 224, 224)
+    sd = jb.synth.make_vit_state_dict(seed=4, layers=2)
+    model = jb.jclip.build_model(sd)
+    Ts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = jb.synth.make_head(2, Ts[2].numpy())
+    hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp)
+    a = hp.evaluate_base(views)
+    b = hp.evaluate_base(torch.from_numpy(ref.astype(np.float32) / 255.0).to(cuda_dev))
+    assert torch.equal(a, b)
