@@ -11,9 +11,9 @@
 // a horizontal pass into a uint8 intermediate, then a vertical pass (the checker is Pillow itself,
 // tests/test_gpu_tta.py; numpy restatement in oracle/crops.py).
 //
-//   resample_h_kernel   one CTA = 32 intermediate rows x S columns of one view; weights for the S columns are
+//   resample_h_kernel   one CTA = 128 intermediate rows x S columns of one view; weights for the S columns are
 //                       computed once per CTA in fp64 (explicitly rounded ops: no FMA contraction) into smem
-//   resample_v_kernel   one CTA = 32 output rows x S columns of one view; reads the planar uint8 intermediate
+//   resample_v_kernel   one CTA = all S output rows x S columns of one view; reads the planar uint8 intermediate
 //                       coalesced, writes the planar [3, S, S] uint8 view (mirrored if asked)
 #include <cmath>
 #include <cstdint>
@@ -28,7 +28,8 @@ namespace jcb {
 namespace {
 
 constexpr int PREC = 32 - 8 - 2;  // Pillow PRECISION_BITS
-constexpr int RB = 32;            // rows per CTA in both passes
+constexpr int RBH = 128;          // intermediate rows per CTA in the horizontal pass (amortises the fp64 weight set-up)
+constexpr int RBV = 256;          // output rows per CTA in the vertical pass: the whole view, one weight set per thread
 
 struct AxisDev {          // one axis of one view, as Pillow's precompute_coeffs sees it
   double scale, ss, support;   // in/out ratio, 1 / filterscale, filter support * filterscale
@@ -92,7 +93,7 @@ resample_h_kernel(const uint8_t* __restrict__ src, const ViewDev* __restrict__ v
                   uint8_t* __restrict__ tmp) {
   extern __shared__ __align__(16) int rs_smem[];
   const ViewDev v = views[blockIdx.y];
-  const int r_begin = blockIdx.x * RB;
+  const int r_begin = blockIdx.x * RBH;
   if (r_begin >= v.n_rows) return;
   int* kk = rs_smem;                 // [S][kmax]
   int* xmin = kk + S * kmax;         // [S]
@@ -104,7 +105,7 @@ resample_h_kernel(const uint8_t* __restrict__ src, const ViewDev* __restrict__ v
     cnt[xx] = n;
   }
   __syncthreads();
-  const int r_end = min(r_begin + RB, v.n_rows);
+  const int r_end = min(r_begin + RBH, v.n_rows);
   const long long pitch = 3LL * v.src_w;
   const long long plane = static_cast<long long>(v.n_rows) * S;
   for (int p = threadIdx.x; p < (r_end - r_begin) * S; p += blockDim.x) {
@@ -132,12 +133,12 @@ resample_v_kernel(const uint8_t* __restrict__ tmp, const ViewDev* __restrict__ v
                   uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) int rs_smem[];
   const ViewDev v = views[blockIdx.y];
-  const int y_begin = blockIdx.x * RB;
+  const int y_begin = blockIdx.x * RBV;
   if (y_begin >= S) return;
-  const int rows = min(RB, S - y_begin);
-  int* kk = rs_smem;                 // [RB][kmax]
-  int* ymin = kk + RB * kmax;        // [RB]
-  int* cnt = ymin + RB;              // [RB]
+  const int rows = min(RBV, S - y_begin);
+  int* kk = rs_smem;                 // [RBV][kmax]
+  int* ymin = kk + RBV * kmax;       // [RBV]
+  int* cnt = ymin + RBV;             // [RBV]
   for (int yy = threadIdx.x; yy < rows; yy += blockDim.x) {
     int lo, n;
     axis_coeffs(v.v, v.filter, y_begin + yy + v.v.off, kk + yy * kmax, lo, n);
@@ -237,20 +238,25 @@ cudaError_t launch_tta(const uint8_t* src, const void* views_dev, int64_t n_jobs
                        int max_rows, uint8_t* tmp, uint8_t* out, cudaStream_t stream) {
   if (n_jobs == 0) return cudaSuccess;
   const size_t smem_h = static_cast<size_t>(S) * (kmax_h + 2) * sizeof(int);
-  const size_t smem_v = static_cast<size_t>(RB) * (kmax_v + 2) * sizeof(int);
+  const size_t smem_v = static_cast<size_t>(RBV) * (kmax_v + 2) * sizeof(int);
   if (smem_h > 200 * 1024 || smem_v > 200 * 1024 || n_jobs > 65535) return cudaErrorInvalidValue;
-  static size_t attr_h = 0;
+  static size_t attr_h = 0, attr_v = 0;
   if (smem_h > 48 * 1024 && smem_h > attr_h) {
     cudaError_t e = cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_h));
     if (e != cudaSuccess) return e;
     attr_h = smem_h;
   }
+  if (smem_v > 48 * 1024 && smem_v > attr_v) {
+    cudaError_t e = cudaFuncSetAttribute(resample_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_v));
+    if (e != cudaSuccess) return e;
+    attr_v = smem_v;
+  }
   const ViewDev* views = static_cast<const ViewDev*>(views_dev);
-  dim3 gh(static_cast<unsigned>((max_rows + RB - 1) / RB), static_cast<unsigned>(n_jobs));
+  dim3 gh(static_cast<unsigned>((max_rows + RBH - 1) / RBH), static_cast<unsigned>(n_jobs));
   resample_h_kernel<<<gh, 256, smem_h, stream>>>(src, views, S, kmax_h, tmp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  dim3 gv(static_cast<unsigned>((S + RB - 1) / RB), static_cast<unsigned>(n_jobs));
+  dim3 gv(static_cast<unsigned>((S + RBV - 1) / RBV), static_cast<unsigned>(n_jobs));
   resample_v_kernel<<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, out);
   return cudaGetLastError();
 }

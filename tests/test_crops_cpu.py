@@ -69,3 +69,22 @@ def test_draw_jobs_layout(jb):
     assert t[6][0] == 1 and t[6][9] == 1 and all(x[9] == 0 and x[5:9] == (224, 224, 0, 0) for x in t[1:6])
     with pytest.raises(ValueError):
         jb.TTAViews(n_crops=1, resize=200).draw_jobs([(100, 2000)])   # Resize(200) cannot hold a 224-pixel centre crop
+
+
+def test_fast_job_draw_has_the_same_layout_and_bounds(jb):
+    import time
+    gen = jb.TTAViews(n_crops=64, seed=3)
+    shapes = [(375, 500)] * 64 + [(600, 400)] * 64
+    t0 = time.perf_counter()
+    jobs = gen.draw_jobs_fast(shapes)
+    dt = time.perf_counter() - t0
+    assert jobs.shape == (128 * 65,) and jobs.dtype == jb.tta.JOB_DTYPE and dt < 1.0
+    t = jb.tta.jobs_to_tuples(jobs)
+    assert t[0] == (0, 0, 0, 375, 500, 256, 341, 16, 58, 1, 0) and t[65 * 64][3:5] == (600, 400)
+    for (img, top, left, h, w, oh, ow, oy, ox, filt, flip) in t:
+        H, W = shapes[img]
+        assert 0 <= top and 0 <= left and top + h <= H and left + w <= W and h > 0 and w > 0
+        if filt == 0:
+            assert (oh, ow, oy, ox) == (224, 224, 0, 0) and 0.45 <= h * w / (H * W) <= 1.0
+    flips = np.mean([x[10] for x in t if x[9] == 0])
+    assert 0.4 < flips < 0.6

@@ -62,3 +62,23 @@ elif what == "gemm":
         out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 2 else torch.bfloat16)
         ms = timeit(lambda: jb._capi.check(lib.jcb_gemm_bf16(h, P(A), P(B), M, N, K, P(bias), epi, P(out), N), h))
         print(f"gemm {name} M={M} N={N} K={K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
+elif what == "tta":
+    import numpy as np
+    I = n
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I)]
+    gen = jb.TTAViews(n_crops=64, seed=0)
+    jobs = gen.draw_jobs([im.shape[:2] for im in imgs])
+    import time
+    out = gen(imgs, jobs=jobs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out = gen(imgs, jobs=jobs)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    ctx.profile_start()
+    out = gen(imgs, jobs=jobs)
+    prof = ctx.profile_stop()
+    print(f"tta I={I} x 65 views of 500x375: {dt * 1e3:.2f} ms per call incl. host packing + H2D ({I / dt:.0f} images/s); "
+          f"kernels {prof['tta_views']['ms']:.2f} ms")
