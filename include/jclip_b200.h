@@ -39,6 +39,7 @@ extern "C" {
 
 typedef struct jcb_ctx jcb_ctx;
 typedef struct jcb_vit jcb_vit;
+typedef struct jcb_text jcb_text;
 
 /* image element types accepted by the encoder */
 #define JCB_IMG_F32 0   /* float32, the reference's dtype (T.ToTensor -> float32) */
@@ -150,6 +151,30 @@ int jcb_encode_image_host(jcb_vit* vit, const void* images_host, int img_dtype, 
 /* Final token tensor of the tower [n_views * tokens, width] fp32 before ln_post (tests / debugging). */
 int jcb_vit_debug_tokens(jcb_vit* vit, const void* images_dev, int img_dtype, int64_t n_views, int apply_clip_norm,
                          float* tokens_out_dev);
+
+/* ---------------------------------------------------------------- text tower ----------------- */
+/* `CLIP.encode_text` (jclip/model.py:202-215), SURVEY.md section 8 "next" row f3: it runs once per run to build the
+ * cached text embeddings (clip_classifier, test.py:920-940: 403 classes x the templates), reusing the image
+ * tower's kernels with a causal attention mask. */
+typedef struct jcb_text_config {
+  int32_t layers;          /* 12  number of transformer.resblocks.*                jclip/model.py:269-273 */
+  int32_t width;           /* 512 ln_final.weight.shape[0]                         jclip/model.py:267 */
+  int32_t context_length;  /* 77  positional_embedding.shape[0]                    jclip/model.py:265 */
+  int32_t vocab_size;      /* 49408 token_embedding.weight.shape[0]                jclip/model.py:266 */
+  int32_t embed_dim;       /* 512 text_projection.shape[1]                         jclip/model.py:264 */
+} jcb_text_config;
+int jcb_text_create(jcb_ctx* ctx, const jcb_text_config* cfg, jcb_text** out);
+int jcb_text_destroy(jcb_text* text);
+/* keys: token_embedding.weight, positional_embedding, transformer.resblocks.{i}.*, ln_final.{weight,bias},
+ * text_projection (jclip/model.py:235-285) */
+int jcb_text_set_param(jcb_text* text, const char* name, const float* data, int64_t numel);
+/* LoRA on the text blocks (apply_lora with encoder 'text' / 'both', test.py:611-623) */
+int jcb_text_set_lora(jcb_text* text, int layer, int proj, const float* A, const float* B, int r, float scaling);
+int jcb_text_clear_lora(jcb_text* text);
+int jcb_text_finalize(jcb_text* text);
+/* tokens_dev [n_seq, context_length] int64 (what `clip.tokenize` returns); out_dev [n_seq, embed_dim] float32;
+ * normalize != 0 fuses `/ norm(dim=-1)` (test.py:929) */
+int jcb_encode_text(jcb_text* text, const int64_t* tokens_dev, int64_t n_seq, int normalize, float* out_dev);
 
 /* ---------------------------------------------------------------- TTA views ------------------ */
 /* The step upstream of encode_image: the reference builds, per test image, 1 centre view + N random crops on

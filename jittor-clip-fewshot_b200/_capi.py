@@ -32,6 +32,11 @@ class VitConfig(Structure):
                 ("embed_dim", c_int32), ("vpt_tokens", c_int32)]
 
 
+class TextConfig(Structure):
+    _fields_ = [("layers", c_int32), ("width", c_int32), ("context_length", c_int32), ("vocab_size", c_int32),
+                ("embed_dim", c_int32)]
+
+
 class MtaParams(Structure):
     _fields_ = [("lambda_y", c_float), ("lambda_q", c_float), ("th", c_float), ("temperature", c_float),
                 ("k_frac", c_double), ("max_iter", c_int32), ("reserved", c_int32)]
@@ -87,6 +92,13 @@ PROTOTYPES = {
     "jcb_encode_image": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "jcb_encode_image_host": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "jcb_vit_debug_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "jcb_text_create": (c_int, [c_void_p, POINTER(TextConfig), POINTER(c_void_p)]),
+    "jcb_text_destroy": (c_int, [c_void_p]),
+    "jcb_text_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "jcb_text_set_lora": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float]),
+    "jcb_text_clear_lora": (c_int, [c_void_p]),
+    "jcb_text_finalize": (c_int, [c_void_p]),
+    "jcb_encode_text": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "jcb_tta_views": (c_int, [c_void_p, c_void_p, POINTER(SrcImage), c_int32, POINTER(ViewJob), c_int64, c_int32,
                               c_void_p]),
     "jcb_mta_default_params": (None, [POINTER(MtaParams)]),

@@ -162,26 +162,61 @@ struct LayerDev {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
 };
 
-struct jcb_vit {
+// What the image tower and the text tower share: a stack of pre-LN transformer blocks with packed-QKV
+// attention (+ LoRA adapters merged at pack time), the fp32 staging of the reference state dict and the
+// device arena the packed weights live in.
+struct TowerBase {
   jcb_ctx* ctx = nullptr;
-  jcb_vit_config cfg{};
-  int grid = 0, tokens = 0, heads = 0, kpatch = 0;
+  int W = 0, L = 0, heads = 0, tokens = 0;           // width, blocks, heads (W / 64), tokens per sequence
+  std::string prefix;                                // state-dict prefix of the blocks
   std::map<std::string, std::vector<float>> host;   // fp32 staging by reference key name
   std::map<std::string, int64_t> expected;          // key -> numel
   std::map<int, LoraAdapter> lora;                  // layer * 4 + proj
   bool finalized = false;
   void* arena = nullptr;                            // device weights
   size_t arena_bytes = 0;
+  std::vector<LayerDev> layers;
+};
+
+struct jcb_vit : TowerBase {
+  jcb_vit_config cfg{};
+  int grid = 0, kpatch = 0;
   __nv_bfloat16* conv_w = nullptr;
   float *vpt = nullptr;
   float *cls = nullptr, *pos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr,
         *ln_post_b = nullptr, *proj = nullptr;
-  std::vector<LayerDev> layers;
+};
+
+struct jcb_text : TowerBase {
+  jcb_text_config cfg{};
+  float *tok_emb = nullptr, *pos = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr, *text_projection = nullptr;
 };
 
 namespace {
 
-std::string blk(int i, const char* tail) { return "visual.transformer.resblocks." + std::to_string(i) + "." + tail; }
+int tower_set_param(TowerBase* t, const char* name, const float* data, int64_t numel);
+int tower_set_lora(TowerBase* t, int layer, int proj, const float* A, const float* B, int r, float scaling);
+
+std::string blk(const TowerBase* t, int i, const char* tail) { return t->prefix + std::to_string(i) + "." + tail; }
+
+void expect_blocks(TowerBase* t) {
+  const int64_t W = t->W;
+  auto& e = t->expected;
+  for (int i = 0; i < t->L; ++i) {
+    e[blk(t, i, "attn.in_proj_weight")] = 3 * W * W;
+    e[blk(t, i, "attn.in_proj_bias")] = 3 * W;
+    e[blk(t, i, "attn.out_proj.weight")] = W * W;
+    e[blk(t, i, "attn.out_proj.bias")] = W;
+    e[blk(t, i, "ln_1.weight")] = W;
+    e[blk(t, i, "ln_1.bias")] = W;
+    e[blk(t, i, "ln_2.weight")] = W;
+    e[blk(t, i, "ln_2.bias")] = W;
+    e[blk(t, i, "mlp.c_fc.weight")] = 4 * W * W;
+    e[blk(t, i, "mlp.c_fc.bias")] = 4 * W;
+    e[blk(t, i, "mlp.c_proj.weight")] = 4 * W * W;
+    e[blk(t, i, "mlp.c_proj.bias")] = W;
+  }
+}
 
 void build_expected(jcb_vit* v) {
   const int64_t W = v->cfg.width, P = v->cfg.patch, E = v->cfg.embed_dim, T = v->tokens;
@@ -195,20 +230,7 @@ void build_expected(jcb_vit* v) {
   e["visual.ln_post.weight"] = W;
   e["visual.ln_post.bias"] = W;
   e["visual.proj"] = W * E;
-  for (int i = 0; i < v->cfg.layers; ++i) {
-    e[blk(i, "attn.in_proj_weight")] = 3 * W * W;
-    e[blk(i, "attn.in_proj_bias")] = 3 * W;
-    e[blk(i, "attn.out_proj.weight")] = W * W;
-    e[blk(i, "attn.out_proj.bias")] = W;
-    e[blk(i, "ln_1.weight")] = W;
-    e[blk(i, "ln_1.bias")] = W;
-    e[blk(i, "ln_2.weight")] = W;
-    e[blk(i, "ln_2.bias")] = W;
-    e[blk(i, "mlp.c_fc.weight")] = 4 * W * W;
-    e[blk(i, "mlp.c_fc.bias")] = 4 * W;
-    e[blk(i, "mlp.c_proj.weight")] = 4 * W * W;
-    e[blk(i, "mlp.c_proj.bias")] = W;
-  }
+  expect_blocks(v);
 }
 
 // workspace layout for one chunk of n views
@@ -219,14 +241,15 @@ struct TowerWs {
   __nv_bfloat16* qkv;     // [n*T, 3W]
   __nv_bfloat16* attn;    // [n*T, W]
 };
-size_t tower_ws_bytes(const jcb_vit* v, int64_t n) {
-  const size_t W = v->cfg.width, T = v->tokens, GG = static_cast<size_t>(v->grid) * v->grid, KP = v->kpatch;
+size_t tower_ws_bytes_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n) {
   const size_t big = std::max(n * GG * KP, n * T * 4 * W) * 2;
   return align_up(big) + align_up(n * T * W * 4) + align_up(n * T * W * 2) + align_up(n * T * 3 * W * 2) +
          align_up(n * T * W * 2);
 }
-TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
-  const size_t W = v->cfg.width, T = v->tokens, GG = static_cast<size_t>(v->grid) * v->grid, KP = v->kpatch;
+size_t tower_ws_bytes(const jcb_vit* v, int64_t n) {
+  return tower_ws_bytes_dims(v->W, v->tokens, static_cast<size_t>(v->grid) * v->grid, v->kpatch, n);
+}
+TowerWs tower_ws_carve_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n, Bump& b) {
   TowerWs w;
   w.big = b.take<__nv_bfloat16>(std::max(n * GG * KP, n * T * 4 * W));
   w.tokens = b.take<float>(n * T * W);
@@ -234,6 +257,9 @@ TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
   w.qkv = b.take<__nv_bfloat16>(n * T * 3 * W);
   w.attn = b.take<__nv_bfloat16>(n * T * W);
   return w;
+}
+TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
+  return tower_ws_carve_dims(v->W, v->tokens, static_cast<size_t>(v->grid) * v->grid, v->kpatch, n, b);
 }
 
 int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
@@ -246,6 +272,32 @@ int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16*
   const double out_b = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 ? 2.0 : (epi == EPI_BIAS_RESID_F32 ? 8.0 : 4.0);
   const double bytes = 2.0 * M * K + 2.0 * N * K + out_b * M * N;
   LAUNCH_P(ctx, cls, 2.0 * M * N * K, bytes, launch_gemm(g, ctx->dev_status, ctx->num_sms, ctx->stream));
+  return JCB_OK;
+}
+
+// L pre-LN blocks on `n` sequences of t->tokens tokens: w.ln_out holds ln_1 of block 0 on entry, w.tokens the
+// fp32 residual stream; on exit w.tokens is the output of the last block (reference jclip/model.py:59-62).
+int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
+  jcb_ctx* ctx = t->ctx;
+  cudaStream_t s = ctx->stream;
+  const int W = t->W, T = t->tokens;
+  const int M = static_cast<int>(n * T);
+  const double MW = static_cast<double>(M) * W;
+  int rc;
+  for (int l = 0; l < t->L; ++l) {
+    const LayerDev& L = t->layers[l];
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
+    LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
+             launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal));
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+    LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+    if (l + 1 < t->L) {
+      const LayerDev& Nx = t->layers[l + 1];
+      LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, Nx.ln1_g, Nx.ln1_b, w.ln_out, s));
+    }
+  }
   return JCB_OK;
 }
 
@@ -267,21 +319,7 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   // class token + ln_pre (residual stream) + layer 0's ln_1
   LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->vpt, v->cfg.vpt_tokens, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
                               v->layers[0].ln1_b, w.ln_out, s));
-  for (int l = 0; l < v->cfg.layers; ++l) {
-    const LayerDev& L = v->layers[l];
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
-    LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * v->heads * T * T * 64, MW * (6 + 2),
-             launch_attention(w.qkv, n, T, v->heads, w.attn, s));
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
-    LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
-    if (l + 1 < v->cfg.layers) {
-      const LayerDev& Nx = v->layers[l + 1];
-      LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, Nx.ln1_g, Nx.ln1_b, w.ln_out, s));
-    }
-  }
-  return JCB_OK;
+  return tower_blocks(v, n, w, 0);
 }
 
 int64_t balanced_chunk(int64_t n, int64_t bound) {
@@ -510,6 +548,9 @@ int jcb_vit_create(jcb_ctx* ctx, const jcb_vit_config* cfg, jcb_vit** out) {
   v->grid = cfg->resolution / cfg->patch;
   v->tokens = v->grid * v->grid + 1 + cfg->vpt_tokens;
   v->heads = cfg->width / 64;  // jclip/model.py:152
+  v->W = cfg->width;
+  v->L = cfg->layers;
+  v->prefix = "visual.transformer.resblocks.";
   v->kpatch = 3 * cfg->patch * cfg->patch;
   if (v->tokens > 64 || v->heads % 4 != 0 || v->kpatch % 64 != 0) {
     delete v;
@@ -530,29 +571,11 @@ int jcb_vit_destroy(jcb_vit* v) {
 }
 
 int jcb_vit_set_param(jcb_vit* v, const char* name, const float* data, int64_t numel) {
-  if (!v || !name || !data) return JCB_E_INVALID;
-  auto it = v->expected.find(name);
-  if (it == v->expected.end()) return fail(v->ctx, JCB_E_INVALID, "unknown parameter '%s'", name);
-  if (it->second != numel)
-    return fail(v->ctx, JCB_E_INVALID, "parameter '%s': expected %lld elements, got %lld", name,
-                static_cast<long long>(it->second), static_cast<long long>(numel));
-  v->host[name].assign(data, data + numel);
-  v->finalized = false;
-  return JCB_OK;
+  return tower_set_param(v, name, data, numel);
 }
 
 int jcb_vit_set_lora(jcb_vit* v, int layer, int proj, const float* A, const float* B, int r, float scaling) {
-  if (!v || !A || !B) return JCB_E_INVALID;
-  if (layer < 0 || layer >= v->cfg.layers || proj < 0 || proj > 3 || r < 1 || r > 256)
-    return fail(v->ctx, JCB_E_INVALID, "set_lora: layer=%d proj=%d r=%d out of range", layer, proj, r);
-  LoraAdapter& a = v->lora[layer * 4 + proj];
-  const int64_t W = v->cfg.width;
-  a.A.assign(A, A + r * W);
-  a.B.assign(B, B + W * r);
-  a.r = r;
-  a.scaling = scaling;
-  v->finalized = false;
-  return JCB_OK;
+  return tower_set_lora(v, layer, proj, A, B, r, scaling);
 }
 
 int jcb_vit_clear_lora(jcb_vit* v) {
@@ -562,48 +585,51 @@ int jcb_vit_clear_lora(jcb_vit* v) {
   return JCB_OK;
 }
 
-int jcb_vit_finalize(jcb_vit* v) {
-  if (!v) return JCB_E_INVALID;
-  jcb_ctx* ctx = v->ctx;
-  DeviceGuard g(ctx->device);
-  for (auto& kv : v->expected)
-    if (!v->host.count(kv.first)) return fail(ctx, JCB_E_STATE, "parameter '%s' was never set", kv.first.c_str());
-  const size_t W = v->cfg.width, E = v->cfg.embed_dim, T = v->tokens, KP = v->kpatch, L = v->cfg.layers;
-  // arena: bf16 GEMM operands, then fp32 vectors
-  size_t bytes = align_up(W * KP * 2) + L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2));
-  bytes += 9 * align_up(std::max(W * E, T * W) * 4) + L * 8 * align_up(4 * W * 4);
-  const size_t tmp_elems = 4 * W * W;  // largest single tensor (c_fc / c_proj / conv1 for P=32)
-  const size_t tmp_bytes = align_up(std::max(tmp_elems, W * KP) * 4) + 2 * align_up(256 * W * 4);
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (!v->arena || v->arena_bytes < bytes) {
-    if (v->arena) cudaFree(v->arena);
-    v->arena = nullptr;
-    cudaError_t e = cudaMalloc(&v->arena, bytes);
-    if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for weights failed: %s", bytes, cudaGetErrorString(e));
-    v->arena_bytes = bytes;
-  }
+}  // extern "C"
+
+namespace {
+
+// Uploads a tower's staged fp32 parameters into its device arena: GEMM operands as bf16 (LoRA merged in fp32
+// first: W' = W + s * B A, reference test.py:310-313 / :388-398), everything else fp32.
+struct Packer {
+  TowerBase* t;
+  jcb_ctx* ctx;
+  Bump b{nullptr};
   void* tmp = nullptr;
-  {
+  float *tmp_w = nullptr, *tmp_A = nullptr, *tmp_B = nullptr;
+  explicit Packer(TowerBase* tower) : t(tower), ctx(tower->ctx) {}
+  ~Packer() { if (tmp) cudaFree(tmp); }
+
+  int begin(size_t arena_bytes, size_t max_tensor_elems) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!t->arena || t->arena_bytes < arena_bytes) {
+      if (t->arena) cudaFree(t->arena);
+      t->arena = nullptr;
+      cudaError_t e = cudaMalloc(&t->arena, arena_bytes);
+      if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for weights failed: %s", arena_bytes, cudaGetErrorString(e));
+      t->arena_bytes = arena_bytes;
+    }
+    const size_t W = t->W;
+    const size_t tmp_bytes = align_up(max_tensor_elems * 4) + 2 * align_up(256 * W * 4);
     cudaError_t e = cudaMalloc(&tmp, tmp_bytes);
     if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for packing failed: %s", tmp_bytes, cudaGetErrorString(e));
-  }
-  struct TmpFree { void* p; ~TmpFree() { cudaFree(p); } } tmp_free{tmp};
-  float* tmp_w = static_cast<float*>(tmp);
-  float* tmp_A = reinterpret_cast<float*>(static_cast<uint8_t*>(tmp) + align_up(std::max(tmp_elems, W * KP) * 4));
-  float* tmp_B = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmp_A) + align_up(256 * W * 4));
-  cudaStream_t s = ctx->stream;
-  Bump b(v->arena);
-
-  auto up_f32 = [&](const std::string& key, float** dst) -> int {
-    const std::vector<float>& h = v->host[key];
-    *dst = b.take<float>(h.size());
-    CUDA_TRY(ctx, cudaMemcpyAsync(*dst, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    tmp_w = static_cast<float*>(tmp);
+    tmp_A = reinterpret_cast<float*>(static_cast<uint8_t*>(tmp) + align_up(max_tensor_elems * 4));
+    tmp_B = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmp_A) + align_up(256 * W * 4));
+    b = Bump(t->arena);
     return JCB_OK;
-  };
+  }
+  int up_f32(const std::string& key, float** dst) {
+    const std::vector<float>& h = t->host[key];
+    *dst = b.take<float>(h.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(*dst, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return JCB_OK;
+  }
   // bf16 weight [rows, cols]; `adapters` lists (row offset, adapter) pairs merged in fp32 before the cast
-  auto up_bf16 = [&](const std::string& key, size_t rows, size_t cols, __nv_bfloat16** dst,
-                     const std::vector<std::pair<size_t, const LoraAdapter*>>& adapters) -> int {
-    const std::vector<float>& h = v->host[key];
+  int up_bf16(const std::string& key, size_t rows, size_t cols, __nv_bfloat16** dst,
+              const std::vector<std::pair<size_t, const LoraAdapter*>>& adapters) {
+    cudaStream_t s = ctx->stream;
+    const std::vector<float>& h = t->host[key];
     *dst = b.take<__nv_bfloat16>(h.size());
     CUDA_TRY(ctx, cudaMemcpyAsync(tmp_w, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
     LAUNCH(ctx, launch_cast_bf16(tmp_w, *dst, static_cast<int64_t>(rows * cols), s));
@@ -611,52 +637,217 @@ int jcb_vit_finalize(jcb_vit* v) {
       const LoraAdapter* a = ad.second;
       CUDA_TRY(ctx, cudaMemcpyAsync(tmp_A, a->A.data(), a->A.size() * 4, cudaMemcpyHostToDevice, s));
       CUDA_TRY(ctx, cudaMemcpyAsync(tmp_B, a->B.data(), a->B.size() * 4, cudaMemcpyHostToDevice, s));
-      // rows [off, off + W) of the packed weight: W' = W + s * B A   (test.py:310-313, :388-398)
-      LAUNCH(ctx, launch_merge_lora_cast(tmp_w + ad.first * cols, tmp_A, tmp_B, static_cast<int>(W),
-                                         static_cast<int>(cols), a->r, a->scaling, *dst + ad.first * cols, s));
-      // the staging buffers are reused by the next adapter
-      CUDA_TRY(ctx, cudaStreamSynchronize(s));
+      // rows [off, off + W) of the packed weight: W' = W + s * B A
+      LAUNCH(ctx, launch_merge_lora_cast(tmp_w + ad.first * cols, tmp_A, tmp_B, t->W, static_cast<int>(cols), a->r,
+                                         a->scaling, *dst + ad.first * cols, s));
+      CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the staging buffers are reused by the next adapter
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return JCB_OK;
-  };
-  int rc;
-  if ((rc = up_bf16("visual.conv1.weight", W, KP, &v->conv_w, {}))) return rc;
-  if ((rc = up_f32("visual.class_embedding", &v->cls))) return rc;
-  if ((rc = up_f32("visual.positional_embedding", &v->pos))) return rc;
-  if (v->cfg.vpt_tokens > 0 && (rc = up_f32("visual.VPT", &v->vpt))) return rc;
-  if ((rc = up_f32("visual.ln_pre.weight", &v->ln_pre_g))) return rc;
-  if ((rc = up_f32("visual.ln_pre.bias", &v->ln_pre_b))) return rc;
-  if ((rc = up_f32("visual.ln_post.weight", &v->ln_post_g))) return rc;
-  if ((rc = up_f32("visual.ln_post.bias", &v->ln_post_b))) return rc;
-  if ((rc = up_f32("visual.proj", &v->proj))) return rc;
-  v->layers.assign(L, LayerDev());
-  for (size_t i = 0; i < L; ++i) {
-    LayerDev& Ld = v->layers[i];
-    std::vector<std::pair<size_t, const LoraAdapter*>> in_ad, out_ad;
-    for (int p = 0; p < 3; ++p) {  // packed in_proj rows: q 0:W, k W:2W, v 2W:3W  (test.py:491-501)
-      auto it = v->lora.find(static_cast<int>(i) * 4 + p);
-      if (it != v->lora.end()) in_ad.push_back({p * W, &it->second});
-    }
-    auto ito = v->lora.find(static_cast<int>(i) * 4 + JCB_PROJ_O);
-    if (ito != v->lora.end()) out_ad.push_back({0, &ito->second});
-    const int li = static_cast<int>(i);
-    if ((rc = up_bf16(blk(li, "attn.in_proj_weight"), 3 * W, W, &Ld.in_w, in_ad))) return rc;
-    if ((rc = up_bf16(blk(li, "attn.out_proj.weight"), W, W, &Ld.out_w, out_ad))) return rc;
-    if ((rc = up_bf16(blk(li, "mlp.c_fc.weight"), 4 * W, W, &Ld.fc_w, {}))) return rc;
-    if ((rc = up_bf16(blk(li, "mlp.c_proj.weight"), W, 4 * W, &Ld.proj_w, {}))) return rc;
-    if ((rc = up_f32(blk(li, "attn.in_proj_bias"), &Ld.in_b))) return rc;
-    if ((rc = up_f32(blk(li, "attn.out_proj.bias"), &Ld.out_b))) return rc;
-    if ((rc = up_f32(blk(li, "mlp.c_fc.bias"), &Ld.fc_b))) return rc;
-    if ((rc = up_f32(blk(li, "mlp.c_proj.bias"), &Ld.proj_b))) return rc;
-    if ((rc = up_f32(blk(li, "ln_1.weight"), &Ld.ln1_g))) return rc;
-    if ((rc = up_f32(blk(li, "ln_1.bias"), &Ld.ln1_b))) return rc;
-    if ((rc = up_f32(blk(li, "ln_2.weight"), &Ld.ln2_g))) return rc;
-    if ((rc = up_f32(blk(li, "ln_2.bias"), &Ld.ln2_b))) return rc;
   }
-  CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  if (b.off > v->arena_bytes) return fail(ctx, JCB_E_STATE, "internal: weight arena overflow (%zu > %zu)", b.off, v->arena_bytes);
-  v->finalized = true;
+  int pack_blocks() {
+    const size_t W = t->W;
+    t->layers.assign(t->L, LayerDev());
+    int rc;
+    for (int li = 0; li < t->L; ++li) {
+      LayerDev& Ld = t->layers[li];
+      std::vector<std::pair<size_t, const LoraAdapter*>> in_ad, out_ad;
+      for (int p = 0; p < 3; ++p) {  // packed in_proj rows: q 0:W, k W:2W, v 2W:3W  (test.py:491-501)
+        auto it = t->lora.find(li * 4 + p);
+        if (it != t->lora.end()) in_ad.push_back({p * W, &it->second});
+      }
+      auto ito = t->lora.find(li * 4 + JCB_PROJ_O);
+      if (ito != t->lora.end()) out_ad.push_back({0, &ito->second});
+      if ((rc = up_bf16(blk(t, li, "attn.in_proj_weight"), 3 * W, W, &Ld.in_w, in_ad))) return rc;
+      if ((rc = up_bf16(blk(t, li, "attn.out_proj.weight"), W, W, &Ld.out_w, out_ad))) return rc;
+      if ((rc = up_bf16(blk(t, li, "mlp.c_fc.weight"), 4 * W, W, &Ld.fc_w, {}))) return rc;
+      if ((rc = up_bf16(blk(t, li, "mlp.c_proj.weight"), W, 4 * W, &Ld.proj_w, {}))) return rc;
+      if ((rc = up_f32(blk(t, li, "attn.in_proj_bias"), &Ld.in_b))) return rc;
+      if ((rc = up_f32(blk(t, li, "attn.out_proj.bias"), &Ld.out_b))) return rc;
+      if ((rc = up_f32(blk(t, li, "mlp.c_fc.bias"), &Ld.fc_b))) return rc;
+      if ((rc = up_f32(blk(t, li, "mlp.c_proj.bias"), &Ld.proj_b))) return rc;
+      if ((rc = up_f32(blk(t, li, "ln_1.weight"), &Ld.ln1_g))) return rc;
+      if ((rc = up_f32(blk(t, li, "ln_1.bias"), &Ld.ln1_b))) return rc;
+      if ((rc = up_f32(blk(t, li, "ln_2.weight"), &Ld.ln2_g))) return rc;
+      if ((rc = up_f32(blk(t, li, "ln_2.bias"), &Ld.ln2_b))) return rc;
+    }
+    return JCB_OK;
+  }
+  int end() {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (b.off > t->arena_bytes) return fail(ctx, JCB_E_STATE, "internal: weight arena overflow (%zu > %zu)", b.off, t->arena_bytes);
+    t->finalized = true;
+    return JCB_OK;
+  }
+};
+
+size_t blocks_arena_bytes(size_t W, size_t L) {
+  return L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2) + 8 * align_up(4 * W * 4));
+}
+
+int tower_set_param(TowerBase* t, const char* name, const float* data, int64_t numel) {
+  if (!t || !name || !data) return JCB_E_INVALID;
+  auto it = t->expected.find(name);
+  if (it == t->expected.end()) return fail(t->ctx, JCB_E_INVALID, "unknown parameter '%s'", name);
+  if (it->second != numel)
+    return fail(t->ctx, JCB_E_INVALID, "parameter '%s': expected %lld elements, got %lld", name,
+                static_cast<long long>(it->second), static_cast<long long>(numel));
+  t->host[name].assign(data, data + numel);
+  t->finalized = false;
+  return JCB_OK;
+}
+
+int tower_set_lora(TowerBase* t, int layer, int proj, const float* A, const float* B, int r, float scaling) {
+  if (!t || !A || !B) return JCB_E_INVALID;
+  if (layer < 0 || layer >= t->L || proj < 0 || proj > 3 || r < 1 || r > 256)
+    return fail(t->ctx, JCB_E_INVALID, "set_lora: layer=%d proj=%d r=%d out of range", layer, proj, r);
+  LoraAdapter& a = t->lora[layer * 4 + proj];
+  const int64_t W = t->W;
+  a.A.assign(A, A + r * W);
+  a.B.assign(B, B + W * r);
+  a.r = r;
+  a.scaling = scaling;
+  t->finalized = false;
+  return JCB_OK;
+}
+
+int tower_missing(TowerBase* t) {
+  for (auto& kv : t->expected)
+    if (!t->host.count(kv.first)) return fail(t->ctx, JCB_E_STATE, "parameter '%s' was never set", kv.first.c_str());
+  return JCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jcb_vit_finalize(jcb_vit* v) {
+  if (!v) return JCB_E_INVALID;
+  jcb_ctx* ctx = v->ctx;
+  DeviceGuard g(ctx->device);
+  int rc = tower_missing(v);
+  if (rc) return rc;
+  const size_t W = v->cfg.width, E = v->cfg.embed_dim, T = v->tokens, KP = v->kpatch, L = v->cfg.layers;
+  // arena: bf16 GEMM operands, then fp32 vectors
+  const size_t bytes = align_up(W * KP * 2) + blocks_arena_bytes(W, L) + 9 * align_up(std::max(W * E, T * W) * 4);
+  Packer pk(v);
+  if ((rc = pk.begin(bytes, std::max(4 * W * W, W * KP)))) return rc;
+  if ((rc = pk.up_bf16("visual.conv1.weight", W, KP, &v->conv_w, {}))) return rc;
+  if ((rc = pk.up_f32("visual.class_embedding", &v->cls))) return rc;
+  if ((rc = pk.up_f32("visual.positional_embedding", &v->pos))) return rc;
+  if (v->cfg.vpt_tokens > 0 && (rc = pk.up_f32("visual.VPT", &v->vpt))) return rc;
+  if ((rc = pk.up_f32("visual.ln_pre.weight", &v->ln_pre_g))) return rc;
+  if ((rc = pk.up_f32("visual.ln_pre.bias", &v->ln_pre_b))) return rc;
+  if ((rc = pk.up_f32("visual.ln_post.weight", &v->ln_post_g))) return rc;
+  if ((rc = pk.up_f32("visual.ln_post.bias", &v->ln_post_b))) return rc;
+  if ((rc = pk.up_f32("visual.proj", &v->proj))) return rc;
+  if ((rc = pk.pack_blocks())) return rc;
+  return pk.end();
+}
+
+// ------------------------------------------------------------------------------------------------ text tower
+int jcb_text_create(jcb_ctx* ctx, const jcb_text_config* cfg, jcb_text** out) {
+  if (!ctx || !cfg || !out) return JCB_E_INVALID;
+  *out = nullptr;
+  if (cfg->layers < 1 || cfg->layers > 64) return fail(ctx, JCB_E_INVALID, "layers=%d unsupported", cfg->layers);
+  if (cfg->width % 128 != 0 || cfg->width < 256 || cfg->width > 1024 || (cfg->width != 512 && cfg->width != 768 && cfg->width != 1024))
+    return fail(ctx, JCB_E_INVALID, "text width=%d unsupported (512, 768 or 1024)", cfg->width);
+  if (cfg->context_length < 1 || cfg->context_length > 80)
+    return fail(ctx, JCB_E_INVALID, "context_length=%d unsupported (max 80)", cfg->context_length);
+  if (cfg->embed_dim != 512) return fail(ctx, JCB_E_INVALID, "embed_dim=%d unsupported (512 only)", cfg->embed_dim);
+  if (cfg->vocab_size < 1) return fail(ctx, JCB_E_INVALID, "vocab_size=%d", cfg->vocab_size);
+  jcb_text* t = new jcb_text();
+  t->ctx = ctx;
+  t->cfg = *cfg;
+  t->W = cfg->width;
+  t->L = cfg->layers;
+  t->heads = cfg->width / 64;                       // jclip/model.py:268 transformer_heads = width // 64
+  t->tokens = cfg->context_length;
+  t->prefix = "transformer.resblocks.";
+  const int64_t W = t->W;
+  t->expected["token_embedding.weight"] = static_cast<int64_t>(cfg->vocab_size) * W;
+  t->expected["positional_embedding"] = static_cast<int64_t>(cfg->context_length) * W;
+  t->expected["ln_final.weight"] = W;
+  t->expected["ln_final.bias"] = W;
+  t->expected["text_projection"] = W * cfg->embed_dim;
+  expect_blocks(t);
+  *out = t;
+  return JCB_OK;
+}
+
+int jcb_text_destroy(jcb_text* t) {
+  if (!t) return JCB_OK;
+  DeviceGuard g(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  if (t->arena) cudaFree(t->arena);
+  delete t;
+  return JCB_OK;
+}
+
+int jcb_text_set_param(jcb_text* t, const char* name, const float* data, int64_t numel) {
+  return tower_set_param(t, name, data, numel);
+}
+
+int jcb_text_set_lora(jcb_text* t, int layer, int proj, const float* A, const float* B, int r, float scaling) {
+  return tower_set_lora(t, layer, proj, A, B, r, scaling);
+}
+
+int jcb_text_clear_lora(jcb_text* t) {
+  if (!t) return JCB_E_INVALID;
+  t->lora.clear();
+  t->finalized = false;
+  return JCB_OK;
+}
+
+int jcb_text_finalize(jcb_text* t) {
+  if (!t) return JCB_E_INVALID;
+  jcb_ctx* ctx = t->ctx;
+  DeviceGuard g(ctx->device);
+  int rc = tower_missing(t);
+  if (rc) return rc;
+  const size_t W = t->W, E = t->cfg.embed_dim, T = t->tokens, V = t->cfg.vocab_size, L = t->L;
+  const size_t bytes = blocks_arena_bytes(W, L) + align_up(V * W * 4) + align_up(T * W * 4) + 2 * align_up(W * 4) + align_up(W * E * 4);
+  Packer pk(t);
+  if ((rc = pk.begin(bytes, 4 * W * W))) return rc;
+  if ((rc = pk.up_f32("token_embedding.weight", &t->tok_emb))) return rc;
+  if ((rc = pk.up_f32("positional_embedding", &t->pos))) return rc;
+  if ((rc = pk.up_f32("ln_final.weight", &t->ln_final_g))) return rc;
+  if ((rc = pk.up_f32("ln_final.bias", &t->ln_final_b))) return rc;
+  if ((rc = pk.up_f32("text_projection", &t->text_projection))) return rc;
+  if ((rc = pk.pack_blocks())) return rc;
+  return pk.end();
+}
+
+// `CLIP.encode_text(text)` (jclip/model.py:202-215): token + positional embedding, L causal blocks, ln_final on the
+// EOT token (the highest id of each sequence), @ text_projection.
+int jcb_encode_text(jcb_text* t, const int64_t* tokens_dev, int64_t n_seq, int normalize, float* out_dev) {
+  if (!t) return JCB_E_INVALID;
+  jcb_ctx* ctx = t->ctx;
+  if (!t->finalized) return fail(ctx, JCB_E_STATE, "jcb_text_finalize has not been called");
+  if (n_seq < 0) return fail(ctx, JCB_E_INVALID, "negative sequence count");
+  if (n_seq == 0) return JCB_OK;
+  if (!tokens_dev || !out_dev) return fail(ctx, JCB_E_INVALID, "null token / output pointer");
+  DeviceGuard g(ctx->device);
+  const int W = t->W, T = t->tokens, E = t->cfg.embed_dim;
+  const int64_t chunk = balanced_chunk(n_seq, std::max<int64_t>(1, ctx->chunk_views * 50 / T));
+  const size_t eot_b = align_up(static_cast<size_t>(chunk) * 4);
+  int rc = ws_reserve(ctx, eot_b + tower_ws_bytes_dims(W, T, 0, 0, chunk));
+  if (rc) return rc;
+  int* eot = static_cast<int*>(ctx->ws);
+  Bump b(static_cast<uint8_t*>(ctx->ws) + eot_b);
+  TowerWs w = tower_ws_carve_dims(W, T, 0, 0, chunk, b);
+  for (int64_t off = 0; off < n_seq; off += chunk) {
+    const int64_t m = std::min(chunk, n_seq - off);
+    const double MW = static_cast<double>(m) * T * W;
+    LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2),
+             launch_text_embed_ln(reinterpret_cast<const long long*>(tokens_dev) + off * T, m, T, W, t->cfg.vocab_size,
+                                  t->tok_emb, t->pos, t->layers[0].ln1_g, t->layers[0].ln1_b, w.tokens, w.ln_out, eot,
+                                  ctx->stream));
+    if ((rc = tower_blocks(t, m, w, 1))) return rc;
+    LAUNCH_P(ctx, JCB_KC_TAIL, 2.0 * m * W * E, static_cast<double>(m) * (W + E) * 4,
+             launch_tail(w.tokens, m, T, W, t->ln_final_g, t->ln_final_b, t->text_projection, E, normalize,
+                         out_dev + off * E, ctx->stream, eot));
+  }
   return JCB_OK;
 }
 

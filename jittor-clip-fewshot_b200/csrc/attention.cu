@@ -1,11 +1,14 @@
-// Fused single-tile multi-head attention for short sequences (T <= 64 tokens: 50 for ViT-B/32, 54 for
-// the VPT variant): softmax(Q K^T / sqrt(64)) V per (view, head) with Q, K and V held in shared memory,
-// scores and probabilities never leaving registers.
+// Fused single-tile multi-head attention for short sequences: softmax(Q K^T / sqrt(64)) V per (sequence, head)
+// with Q, K and V held in shared memory, scores and probabilities never leaving registers.
+//   image tower : T <= 64 tokens (50 for ViT-B/32, 54 for the VPT variant), no mask                -> TP = 64
+//   text tower  : T <= 80 tokens (77), causal mask (jclip/model.py:189-193 build_attention_mask)    -> TP = 80
 //
-// One CTA = one view x 4 heads; 8 warps, two per head (32 query rows each).  Q K^T and P V run on
-// mma.sync m16n8k16 bf16 tiles with fp32 accumulation (a 64x64x64 problem per head is far below the
-// size where a tcgen05/TMEM round trip pays; this kernel is 1 % of the tower's FLOPs and is bounded by
-// the 307 KB/view/layer it streams).  Softmax is fp32 with exp2 and the 1/8 scale folded in.
+// One CTA = one sequence x HEADS_PER_CTA heads; each warp owns MT 16-row query tiles of one head.  Q K^T and P V
+// run on mma.sync m16n8k16 bf16 tiles with fp32 accumulation (a 64x64x64 problem per head is far below the
+// size where a tcgen05/TMEM round trip pays; this kernel is 1 % of the tower's FLOPs and is bounded by the
+// 8 B/element it streams).  Softmax is fp32 with exp2 and the 1/8 scale folded in.
+// Measured on B200 (tools/bench_kernel.py attention): 1 head per CTA, 1 query tile per warp -> 4.4 TB/s;
+// the first cut (4 heads per CTA, 2 tiles per warp, 148 registers) -> 2.5 TB/s.
 //
 // Reference: jclip/mha.py:55-83 scaled_dot_product_attention (attn_mask None for the vision tower,
 // jclip/model.py:99; dropout 0 in eval), head split jclip/mha.py:351-362 / test.py:584-590.
@@ -18,20 +21,17 @@ namespace jcb {
 
 namespace {
 
-constexpr int HD = 64;              // head dim
-constexpr int TP = 64;              // padded token count
-constexpr int LDS = HD + 8;         // smem row stride (bf16): 144 B, conflict-free for ldmatrix
-constexpr int TILE_ELEMS = TP * LDS;
+constexpr int HD = 64;       // head dim
+constexpr int LDS = HD + 8;  // smem row stride (bf16): 144 B, conflict-free for ldmatrix
 
-// HEADS_PER_CTA heads of one view per CTA (2 warps per head).  Fewer heads per CTA = smaller shared-memory
-// footprint = more resident CTAs per SM, whose load and compute phases overlap each other: the kernel is
-// bound by streaming qkv (6 B/element) in and the output (2 B/element) out.
-// MT = 16-row query tiles per warp (2 -> 2 warps per head, 1 -> 4 warps per head with half the registers).
-template <int HEADS_PER_CTA, int MT>
-__global__ void __launch_bounds__(HEADS_PER_CTA * (4 / MT) * 32)
+template <int HEADS_PER_CTA, int MT, int TP, bool CAUSAL>
+__global__ void __launch_bounds__(HEADS_PER_CTA * (TP / 16 / MT) * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_bfloat16* __restrict__ out) {
-  constexpr int WPH = 4 / MT;  // warps per head
+  constexpr int WPH = TP / 16 / MT;  // warps per head
   constexpr int ATT_THREADS = HEADS_PER_CTA * WPH * 32;
+  constexpr int TILE_ELEMS = TP * LDS;
+  constexpr int NT = TP / 8;   // 8-wide key tiles
+  constexpr int KS = TP / 16;  // 16-deep key steps of P V
   extern __shared__ __align__(16) uint8_t att_smem[];
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_smem);
   const int W = heads * HD;
@@ -41,8 +41,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const __nv_bfloat16* base = qkv + view * T * (3LL * W) + hg * HEADS_PER_CTA * HD;
 
-  // ---- stage Q, K, V of 4 heads: tile (h, m) at sm + (h*3 + m) * TILE_ELEMS, rows >= T zeroed
-  constexpr int CH_PER_ROW = HEADS_PER_CTA * HD / 8;  // 32 x 16-byte chunks per (row, matrix)
+  // ---- stage Q, K, V of the CTA's heads: tile (h, m) at sm + (h*3 + m) * TILE_ELEMS, rows >= T zeroed
+  constexpr int CH_PER_ROW = HEADS_PER_CTA * HD / 8;  // 16-byte chunks per (row, matrix)
   for (int i = tid; i < 3 * TP * CH_PER_ROW; i += ATT_THREADS) {
     const int m = i / (TP * CH_PER_ROW);
     const int rem = i % (TP * CH_PER_ROW);
@@ -64,12 +64,12 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   const uint32_t sK = smem_u32(sm + (h * 3 + 1) * TILE_ELEMS);
   const uint32_t sV = smem_u32(sm + (h * 3 + 2) * TILE_ELEMS);
 
-  // ---- S = Q K^T : 2 m-tiles x 8 n-tiles (keys) x 4 k-steps (head dim)
-  float s[MT][8][4];
+  // ---- S = Q K^T : MT m-tiles x NT key tiles x 4 k-steps (head dim)
+  float s[MT][NT][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
 #pragma unroll
@@ -82,7 +82,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       ldmatrix_x4(a[mt], sQ + (row * LDS + col) * 2);
     }
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {  // pairs of key tiles
+    for (int np = 0; np < NT / 2; ++np) {  // pairs of key tiles
       uint32_t b[4];
       const int krow = np * 16 + (lane & 7) + ((lane >> 4) << 3);
       const int col = kk * 16 + (((lane >> 3) & 1) << 3);
@@ -98,15 +98,19 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   // ---- softmax over keys (fp32); thread holds rows g and g+8 of each m-tile, cols nt*8 + 2*(lane&3) + {0,1}
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   float inv_sum[MT][2];
-  uint32_t pfrag[MT][8][2];  // P as bf16 pairs: [mt][nt][row half]
+  uint32_t pfrag[MT][NT][2];  // P as bf16 pairs: [mt][nt][row half]
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
+    const int q0 = r0 + mt * 16 + (lane >> 2);  // this thread's query rows: q0 and q0 + 8
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       const int c0 = nt * 8 + 2 * (lane & 3);
-      if (c0 >= T) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
-      if (c0 + 1 >= T) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+      // keys beyond the sequence and (text tower) keys after the query are masked out
+      if (c0 >= T || (CAUSAL && c0 > q0)) s[mt][nt][0] = -INFINITY;
+      if (c0 + 1 >= T || (CAUSAL && c0 + 1 > q0)) s[mt][nt][1] = -INFINITY;
+      if (c0 >= T || (CAUSAL && c0 > q0 + 8)) s[mt][nt][2] = -INFINITY;
+      if (c0 + 1 >= T || (CAUSAL && c0 + 1 > q0 + 8)) s[mt][nt][3] = -INFINITY;
       mx[0] = fmaxf(mx[0], fmaxf(s[mt][nt][0], s[mt][nt][1]));
       mx[1] = fmaxf(mx[1], fmaxf(s[mt][nt][2], s[mt][nt][3]));
     }
@@ -117,7 +121,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       const float p0 = exp2f((s[mt][nt][0] - mx[0]) * scale_log2);
       const float p1 = exp2f((s[mt][nt][1] - mx[0]) * scale_log2);
       const float p2 = exp2f((s[mt][nt][2] - mx[1]) * scale_log2);
@@ -135,7 +139,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
     }
   }
 
-  // ---- O = P V : 2 m-tiles x 8 d-tiles x 4 k-steps (keys)
+  // ---- O = P V : MT m-tiles x 8 d-tiles x KS k-steps (keys)
   float o[MT][8][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
@@ -144,7 +148,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[mt][dt][e] = 0.f;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < KS; ++ks) {
     uint32_t a[MT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -192,39 +196,44 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
   }
 }
 
-}  // namespace
-
-template <int HPC, int MT>
-cudaError_t launch_attention_hpc(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+template <int HPC, int MT, int TP, bool CAUSAL>
+cudaError_t launch_attention_cfg(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
                                  cudaStream_t stream) {
-  constexpr int SMEM = HPC * 3 * TILE_ELEMS * 2;  // 27648 B per head
+  constexpr int SMEM = HPC * 3 * TP * LDS * 2;
+  constexpr int THREADS = HPC * (TP / 16 / MT) * 32;
   static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HPC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  if (!attr_set && SMEM > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HPC, MT, TP, CAUSAL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const long long grid = n_views * (heads / HPC);
-  attention_kernel<HPC, MT><<<static_cast<unsigned>(grid), HPC * (4 / MT) * 32, SMEM, stream>>>(qkv, T, heads, out);
+  attention_kernel<HPC, MT, TP, CAUSAL><<<static_cast<unsigned>(grid), THREADS, SMEM, stream>>>(qkv, T, heads, out);
   return cudaGetLastError();
 }
 
+}  // namespace
+
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream) {
-  if (T < 1 || T > TP || heads % 4 != 0) return cudaErrorInvalidValue;
+                             cudaStream_t stream, int causal) {
+  if (T < 1 || T > 80 || heads < 1) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
+  if (causal) return launch_attention_cfg<1, 1, 80, true>(qkv, n_views, T, heads, out, stream);  // text tower
+  if (T > 64) return launch_attention_cfg<1, 1, 80, false>(qkv, n_views, T, heads, out, stream);
   static int cfg = 0;  // heads per CTA * 10 + query tiles per warp
   if (cfg == 0) {
     const char* env = getenv("JCB_ATT_CFG");
-    cfg = env ? atoi(env) : 11;  // measured on B200 (tools/bench_kernel.py attention): 11 -> 4.4 TB/s, 42 -> 2.5 TB/s
+    cfg = env ? atoi(env) : 11;
   }
-  switch (cfg) {
-    case 12: return launch_attention_hpc<1, 2>(qkv, n_views, T, heads, out, stream);
-    case 22: return launch_attention_hpc<2, 2>(qkv, n_views, T, heads, out, stream);
-    case 41: return launch_attention_hpc<4, 1>(qkv, n_views, T, heads, out, stream);
-    case 42: return launch_attention_hpc<4, 2>(qkv, n_views, T, heads, out, stream);
-    case 21: return launch_attention_hpc<2, 1>(qkv, n_views, T, heads, out, stream);
-    default: return launch_attention_hpc<1, 1>(qkv, n_views, T, heads, out, stream);
+  const int use = (heads % 4 != 0 && cfg > 20) ? 11 : cfg;
+  switch (use) {
+    case 12: return launch_attention_cfg<1, 2, 64, false>(qkv, n_views, T, heads, out, stream);
+    case 21: return launch_attention_cfg<2, 1, 64, false>(qkv, n_views, T, heads, out, stream);
+    case 22: return launch_attention_cfg<2, 2, 64, false>(qkv, n_views, T, heads, out, stream);
+    case 41: return launch_attention_cfg<4, 1, 64, false>(qkv, n_views, T, heads, out, stream);
+    case 42: return launch_attention_cfg<4, 2, 64, false>(qkv, n_views, T, heads, out, stream);
+    default: return launch_attention_cfg<1, 1, 64, false>(qkv, n_views, T, heads, out, stream);
   }
 }
 

@@ -51,12 +51,20 @@ cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const 
 // y_bf16[r,:] = LayerNorm(x_f32[r,:]) * g + b   (eps 1e-5, biased variance), W == 768 or any W % 128 == 0 <= 1024
 cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
                              __nv_bfloat16* y, cudaStream_t stream);
-// out[v,:] = (ln_post(tokens[v*T + 0, :]) @ proj[W,E]) ; optionally / ||.||_2
+// out[v,:] = (ln_post(tokens[v*T + row_idx[v], :]) @ proj[W,E]) ; optionally / ||.||_2.  row_idx == nullptr: row 0
+// (the class token); the text tower passes the EOT position of each sequence.
 cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, const float* g, const float* b,
-                        const float* proj, int E, int normalize, float* out, cudaStream_t stream);
+                        const float* proj, int E, int normalize, float* out, cudaStream_t stream,
+                        const int* row_idx = nullptr);
+// text tower front end (jclip/model.py:203-205): x[s*T + t, :] = tok_emb[ids[s, t], :] + pos[t, :] (fp32 residual
+// stream), y = ln_1(x) as bf16, and eot[s] = argmax_t ids[s, t] (first maximum; model.py:213-214)
+cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
+                                 const float* pos, const float* g1, const float* b1, float* tokens, __nv_bfloat16* y,
+                                 int* eot, cudaStream_t stream);
 // qkv [B*T, 3W] bf16 (q | k | v, heads = 64-wide column blocks) -> out [B*T, W] bf16
+// causal != 0: key j is visible to query i only if j <= i (text tower); T <= 80
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int causal = 0);
 // fp32 -> bf16 cast (weight packing)
 cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
 // W'[rows, cols] (bf16) = W (fp32) + scaling * B[rows, r] @ A[r, cols]   for a row range of a packed weight

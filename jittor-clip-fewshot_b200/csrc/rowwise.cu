@@ -173,6 +173,51 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
   store_row_bf16<NV>(v, y + row * W, lane);
 }
 
+// ------------------------------------------------------------------------------------------ text front end
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, int vocab,
+                     const float* __restrict__ tok_emb, const float* __restrict__ pos, const float* __restrict__ g1,
+                     const float* __restrict__ b1, float* __restrict__ tokens, __nv_bfloat16* __restrict__ y,
+                     int* __restrict__ eot) {
+  constexpr int W = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = static_cast<int>(row % T);
+  long long id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);   // out-of-range ids are clamped, never read out of bounds
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 e = __ldg(reinterpret_cast<const float4*>(tok_emb + id * W) + lane + 32 * i);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * W) + lane + 32 * i);
+    v[i] = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  }
+  float4* xr = reinterpret_cast<float4*>(tokens + row * W);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) xr[lane + 32 * i] = v[i];
+  float mean, rstd;
+  row_stats<NV>(v, W, mean, rstd);
+  normalize_row<NV>(v, mean, rstd, g1, b1, lane);
+  store_row_bf16<NV>(v, y + row * W, lane);
+  if (t == 0) {  // the warp of a sequence's first token also finds its EOT position: first maximum of the ids
+    long long best = -1;
+    int best_t = 0;
+    for (int j = lane; j < T; j += 32) {
+      const long long c = ids[row + j];
+      if (c > best) { best = c; best_t = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+      if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; }
+    }
+    if (lane == 0) eot[row / T] = best_t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ tail
 constexpr int TAIL_VIEWS = 8;
 constexpr int TAIL_THREADS = 256;
@@ -180,7 +225,8 @@ constexpr int TAIL_THREADS = 256;
 template <int NV, int E>
 __global__ void __launch_bounds__(TAIL_THREADS)
 tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const float* __restrict__ g,
-            const float* __restrict__ b, const float* __restrict__ proj, int normalize, float* __restrict__ out) {
+            const float* __restrict__ b, const float* __restrict__ proj, int normalize, float* __restrict__ out,
+            const int* __restrict__ row_idx) {
   constexpr int W = NV * 128;
   constexpr int EPT = E / TAIL_THREADS;  // outputs per thread
   __shared__ __align__(16) float s_x[TAIL_VIEWS][W];
@@ -191,7 +237,8 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
     const long long view = v0 + warp;
     float4 v[NV];
     if (view < n_views) {
-      const float4* xr = reinterpret_cast<const float4*>(tokens + view * T * W);
+      const long long trow = view * T + (row_idx ? row_idx[view] : 0);
+      const float4* xr = reinterpret_cast<const float4*>(tokens + trow * W);
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
       float mean, rstd;
@@ -315,12 +362,24 @@ cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const 
 }
 
 cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, const float* g, const float* b,
-                        const float* proj, int E, int normalize, float* out, cudaStream_t stream) {
+                        const float* proj, int E, int normalize, float* out, cudaStream_t stream, const int* row_idx) {
   if (W % 128 != 0 || E != 512) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((n_views + TAIL_VIEWS - 1) / TAIL_VIEWS);
   JCB_DISPATCH_NV(W, (tail_kernel<NV, 512><<<grid, TAIL_THREADS, 0, stream>>>(tokens, n_views, T, g, b, proj,
-                                                                             normalize, out)));
+                                                                             normalize, out, row_idx)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
+                                 const float* pos, const float* g1, const float* b1, float* tokens, __nv_bfloat16* y,
+                                 int* eot, cudaStream_t stream) {
+  if (W % 128 != 0 || T < 1 || vocab < 1) return cudaErrorInvalidValue;
+  const long long rows = n_seq * T;
+  if (rows == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
+  JCB_DISPATCH_NV(W, (text_embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(ids, rows, T, vocab, tok_emb, pos,
+                                                                                g1, b1, tokens, y, eot)));
   return cudaGetLastError();
 }
 

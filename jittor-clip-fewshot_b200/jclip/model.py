@@ -6,9 +6,9 @@ jclip/model.py:129-285) so that `apply_lora`, `load_lora` and the `ood.py` / `te
 unchanged -- but the objects are thin parameter containers: `encode_image` hands the whole forward
 to the sm_100a library through the C-ABI (include/jclip_b200.h), with no per-op Python.
 
-`encode_text` is outside the hot path (it runs once per run to produce the cached
-text embeddings); it is kept callable as a plain torch fp32 routine so `clip_classifier`
-(reference test.py:920-940) works.
+`encode_text` (it runs once per run to produce the cached text embeddings,
+`clip_classifier`, reference test.py:920-940) runs on the same library with a causal attention mask;
+`encode_text_torch` is a plain-torch cross-check for tests.
 """
 import math
 import pickle
@@ -326,9 +326,9 @@ class VisionTransformer(Module):
 
 
 class Embedding(Module):
-    def __init__(self, weight):
+    def __init__(self, weight, owner=None):
         super().__init__()
-        self.weight = Param(weight)
+        self.weight = Param(weight, owner)
 
 
 class CLIP(Module):
@@ -342,14 +342,68 @@ class CLIP(Module):
         vision_heads = vision_width // 64                         # jclip/model.py:152
         self.visual = VisionTransformer(sd, image_resolution, vision_patch_size, vision_width, vision_layers,
                                         vision_heads, embed_dim, design_details)
+        # the text tower's parameters are owned by this object: assigning to any of them (e.g. LoRA weights on
+        # the text blocks) marks the packed device copy of the text tower stale
         self.transformer = Transformer(sd, "transformer.", transformer_width, transformer_layers, transformer_heads,
-                                       None, attn_mask=self.build_attention_mask())
+                                       self, attn_mask=self.build_attention_mask())
         self.vocab_size = vocab_size
-        self.token_embedding = Embedding(sd["token_embedding.weight"])
-        self.positional_embedding = Param(sd["positional_embedding"])
-        self.ln_final = LayerNorm(sd["ln_final.weight"], sd["ln_final.bias"])
-        self.text_projection = Param(sd["text_projection"])
+        self.token_embedding = Embedding(sd["token_embedding.weight"], self)
+        self.positional_embedding = Param(sd["positional_embedding"], self)
+        self.ln_final = LayerNorm(sd["ln_final.weight"], sd["ln_final.bias"], self)
+        self.text_projection = Param(sd["text_projection"], self)
         self.logit_scale = Param(sd.get("logit_scale", np.log(1 / 0.07)))
+        self._text_dirty, self._text, self._text_ctx = True, None, None
+
+    def mark_dirty(self):
+        self._text_dirty = True
+
+    def _text_engine(self, device=None):
+        """Create / refresh the device-side packed text tower (jcb_text_*; LoRA merged in fp32, then bf16)."""
+        ctx = get_context(device)
+        if self._text is not None and self._text_ctx is not ctx:
+            self.release_text()
+        lib = ctx.lib
+        if self._text is None:
+            W = self.transformer.width
+            cfg = _capi.TextConfig(self.transformer.layers, W, self.context_length, self.vocab_size,
+                                   self.text_projection.shape[1])
+            h = c_void_p()
+            check(lib.jcb_text_create(ctx.handle, byref(cfg), byref(h)), ctx.handle)
+            self._text, self._text_ctx, self._text_dirty = h, ctx, True
+        if self._text_dirty:
+            named = [("token_embedding.weight", self.token_embedding.weight), ("positional_embedding", self.positional_embedding),
+                     ("ln_final.weight", self.ln_final.weight), ("ln_final.bias", self.ln_final.bias),
+                     ("text_projection", self.text_projection)]
+            named += [(n, p) for n, p in self.transformer.named_parameters("transformer.") if "lora_" not in n]
+            for name, p in named:
+                a = np.ascontiguousarray(p.data, dtype=np.float32)
+                check(lib.jcb_text_set_param(self._text, name.encode(), a.ctypes.data_as(c_void_p), a.size), ctx.handle)
+            check(lib.jcb_text_clear_lora(self._text), ctx.handle)
+            for i, block in enumerate(self.transformer.resblocks):
+                attn = block.attn
+                if not getattr(attn, "is_lora", False):
+                    continue
+                for attr, code in _LORA_PROJ:
+                    lin = getattr(attn, attr)
+                    if getattr(lin, "lora_enabled", False):
+                        A = np.ascontiguousarray(lin.w_lora_A.data, dtype=np.float32)
+                        B = np.ascontiguousarray(lin.w_lora_B.data, dtype=np.float32)
+                        check(lib.jcb_text_set_lora(self._text, i, code, A.ctypes.data_as(c_void_p),
+                                                    B.ctypes.data_as(c_void_p), lin.r, float(lin.scaling)), ctx.handle)
+            check(lib.jcb_text_finalize(self._text), ctx.handle)
+            self._text_dirty = False
+        return ctx, self._text
+
+    def release_text(self):
+        if self._text is not None and self._text_ctx is not None and self._text_ctx.handle:
+            self._text_ctx.lib.jcb_text_destroy(self._text)
+        self._text, self._text_ctx = None, None
+
+    def __del__(self):
+        try:
+            self.release_text()
+        except Exception:
+            pass
 
     def build_attention_mask(self):
         mask = torch.full((self.context_length, self.context_length), float("-inf"))
@@ -363,9 +417,28 @@ class CLIP(Module):
         # jclip/model.py:199-200
         return self.visual(image)
 
-    # ---- text tower: torch fp32, not a kernel target --------------------------------
+    def encode_text(self, text, normalize=False):
+        """jclip/model.py:202-215 on the sm_100a library (jcb_encode_text): [n, context_length] token ids ->
+        [n, embed_dim] float32 on the GPU."""
+        tok = as_torch(text)
+        if tok.dim() != 2 or tok.shape[1] != self.context_length:
+            raise ValueError(f"expected tokens of shape [n, {self.context_length}], got {tuple(tok.shape)}")
+        if not tok.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("encode_text runs on a B200 GPU only; there is no CPU fallback "
+                                   "(encode_text_torch is the plain-torch cross-check)")
+            tok = tok.cuda()
+        tok = tok.to(torch.int64).contiguous()
+        with torch.cuda.device(tok.device):
+            ctx, handle = self._text_engine(tok.device)
+            ctx.bind_current_stream()
+            out = torch.empty((tok.shape[0], self.text_projection.shape[1]), dtype=torch.float32, device=tok.device)
+            check(ctx.lib.jcb_encode_text(handle, ptr(tok), tok.shape[0], int(normalize), ptr(out)), ctx.handle)
+        return out
+
+    # ---- plain torch fp32 text tower: a cross-check for tests, never called by the product path ---------
     @torch.no_grad()
-    def encode_text(self, text):
+    def encode_text_torch(self, text):
         # jclip/model.py:202-215
         text = as_torch(text).long()
         dev = text.device
@@ -383,7 +456,7 @@ class CLIP(Module):
     def execute(self, image, text):
         # jclip/model.py:217-232
         fi = as_torch(self.encode_image(image))
-        ft = self.encode_text(text).to(fi.device)
+        ft = as_torch(self.encode_text(text)).to(fi.device)
         fi = fi / fi.norm(dim=1, keepdim=True)
         ft = ft / ft.norm(dim=1, keepdim=True)
         scale = float(np.exp(self.logit_scale.data))

@@ -193,3 +193,16 @@ def make_views_torch(seed, n_images, n_views, device, resolution=224, noise=0.5,
         img = up(base).unsqueeze(1) + up(pert.view(n * n_views, 3, 28, 28)).view(n, n_views, 3, resolution, resolution)
         out[i0:i0 + n] = torch.sigmoid(1.5 * img).to(out.dtype)
     return out
+
+
+def make_tokens(seed, n, vocab=64, context=77, min_len=3, max_len=20):
+    """Synthetic token ids [n, context] int64 in the layout `clip.tokenize` produces: <sot> words... <eot> then zero
+    padding, with <sot> = vocab - 2 and <eot> = vocab - 1 (the highest id, which `encode_text` locates by argmax)."""
+    rng = np.random.default_rng(seed)
+    t = np.zeros((n, context), np.int64)
+    for i in range(n):
+        L = int(rng.integers(min_len, max_len + 1))
+        t[i, 0] = vocab - 2
+        t[i, 1:1 + L] = rng.integers(1, vocab - 2, L)
+        t[i, 1 + L] = vocab - 1
+    return t

@@ -31,5 +31,6 @@ the reported CPU baseline.  Nothing under ``jittor-clip-fewshot_b200/`` imports 
 path fails loudly when the CUDA library is missing.
 """
 from .vit import vit_encode_image, merge_lora_into_state_dict, layer_norm  # noqa: F401
+from .text import text_encode                                               # noqa: F401
 from .mta import solve_mta, solve_mta_logits, cdist, gaussian_kernel        # noqa: F401
 from .head import channel_lp, logit_normalize, fuse_scores, topk_lowest_index_first, pipeline_image  # noqa: F401

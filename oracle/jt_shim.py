@@ -35,6 +35,25 @@ class Var(torch.Tensor):
     def view(self, *shape):                            # jt.Var.view is reshape (no contiguity demand)
         return self.reshape(*shape)
 
+    # Jittor Vars are immutable values: `a += b` rebinds `a` to a new (broadcast) Var
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
+    def __imul__(self, other):
+        return self * other
+
+    def __itruediv__(self, other):
+        return self / other
+
+    def argmax(self, dim=None, keepdims=False):        # ASSUMED Jittor semantics: (indices, values)
+        t = self.as_subclass(torch.Tensor)
+        idx = torch.argmax(t, dim=dim, keepdim=keepdims)
+        val = torch.amax(t, dim=dim, keepdim=keepdims)
+        return _v(idx), _v(val)
+
     def numpy(self):
         return torch.Tensor.numpy(self.detach().as_subclass(torch.Tensor))
 

@@ -150,6 +150,26 @@ def main():
         with torch.no_grad():
             out["tower_vlp"] = model_vlp.encode_image(jt.array(imgs)).numpy()
 
+        # ---------------- text tower: CLIP.encode_text (jclip/model.py:202-215), 2 blocks, with and without LoRA
+        sd_txt = synth.make_vit_state_dict(seed=27, layers=1, text_layers=2)
+        out["text_sd_checksum"] = checksum(np.concatenate([sd_txt[k].ravel() for k in sorted(sd_txt)]))
+        tokens = synth.make_tokens(28, 5, vocab=64)
+        out["text_tokens"] = tokens
+        model_t = refpkg.model.build_model({k: jt.array(v) for k, v in sd_txt.items()})
+        with torch.no_grad():
+            out["text_zero_shot"] = model_t.encode_text(jt.array(tokens)).numpy()
+        args_t = types.SimpleNamespace(encoder="text", position="all", params=["q", "k", "v"], r=4, alpha=1,
+                                       dropout_rate=0.25, backbone="ViT-B/32")
+        layers_t = ns["apply_lora"](args_t, model_t)
+        lora_t = synth.make_lora(seed=29, layers=2, width=512, b_std=0.3)
+        for i in range(2):
+            for name, (A, B) in lora_t[i].items():
+                getattr(layers_t[i], name).w_lora_A.data = jt.array(A)
+                getattr(layers_t[i], name).w_lora_B.data = jt.array(B)
+        model_t.eval()
+        with torch.no_grad():
+            out["text_lora_qkv"] = model_t.encode_text(jt.array(tokens)).numpy()
+
         # ---------------- solve_mta (test.py) and its ood.py twin
         T = synth.make_text_features(seed=31)
         out["mta_text_checksum"] = checksum(T)

@@ -138,11 +138,17 @@ def test_encode_text_runs_with_lora(jb):
     m = jb.jclip.build_model(sd)
     tok = torch.randint(1, 60, (3, 77), generator=torch.Generator().manual_seed(0))
     tok[:, 9] = 63
-    a = m.encode_text(tok)
+    from oracle import text_encode
+    a = m.encode_text_torch(tok)
+    assert (a - text_encode(sd, tok)).abs().max() < 1e-4
     layers = jb.apply_lora(_args(encoder="text"), m)
-    assert torch.allclose(a, m.encode_text(tok))                    # B = 0: adapters are a no-op
+    assert m._text_dirty
+    assert torch.allclose(a, m.encode_text_torch(tok))              # B = 0: adapters are a no-op
     layers[0].q_proj.w_lora_B.data = np.ones((512, 4), np.float32) * 0.05
-    assert not torch.allclose(a, m.encode_text(tok), atol=1e-4)
+    assert not torch.allclose(a, m.encode_text_torch(tok), atol=1e-4)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m.encode_text(tok)
 
 
 def test_tokenizer_with_a_tiny_vocab(jb, tmp_path, monkeypatch):

@@ -101,3 +101,16 @@ def test_head(jb, g):
     assert np.abs(z.numpy() - g["head_channel_lp"]).max() <= 1e-5
     assert np.abs(logit_normalize(z[:1]).numpy() - g["head_logit_normalize_n1"]).max() <= 1e-5
     assert np.abs(logit_normalize(z).numpy() - g["head_logit_normalize_n4"]).max() <= 1e-5
+
+
+def test_text_tower(jb, g):
+    """CLIP.encode_text of the reference (jclip/model.py:202-215) incl. LoRA on the text blocks."""
+    from oracle import text_encode
+    sd = jb.synth.make_vit_state_dict(seed=27, layers=1, text_layers=2)
+    assert np.allclose(_checksum(np.concatenate([sd[k].ravel() for k in sorted(sd)])), g["text_sd_checksum"], rtol=1e-6)
+    tok = jb.synth.make_tokens(28, 5, vocab=64)
+    assert np.array_equal(tok, g["text_tokens"])
+    assert np.abs(text_encode(sd, tok).numpy() - g["text_zero_shot"]).max() <= 2e-5
+    lora = jb.synth.make_lora(seed=29, layers=2, width=512, b_std=0.3)
+    assert np.abs(text_encode(sd, tok, lora=lora).numpy() - g["text_lora_qkv"]).max() <= 2e-5
+    assert np.abs(g["text_lora_qkv"] - g["text_zero_shot"]).max() > 0.05
