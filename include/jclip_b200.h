@@ -175,6 +175,10 @@ int jcb_text_finalize(jcb_text* text);
 /* tokens_dev [n_seq, context_length] int64 (what `clip.tokenize` returns); out_dev [n_seq, embed_dim] float32;
  * normalize != 0 fuses `/ norm(dim=-1)` (test.py:929) */
 int jcb_encode_text(jcb_text* text, const int64_t* tokens_dev, int64_t n_seq, int normalize, float* out_dev);
+/* The averaging step of `clip_classifier` (test.py:931-934): out[c] = normalise(mean of emb rows offsets[c] ..
+ * offsets[c+1]) for unit-norm template embeddings emb_dev [n, dim]; offsets_dev [n_classes + 1] int32. */
+int jcb_class_mean(jcb_ctx* ctx, const float* emb_dev, const int32_t* offsets_dev, int32_t n_classes, int32_t dim,
+                   float* out_dev);
 
 /* ---------------------------------------------------------------- TTA views ------------------ */
 /* The step upstream of encode_image: the reference builds, per test image, 1 centre view + N random crops on

@@ -13,7 +13,7 @@ from . import _capi, dist, jclip, lora, methods, pipeline, runtime, synth, tta  
 from ._capi import JcbError, load_library  # noqa: F401
 from .jclip import clip  # noqa: F401
 from .lora import apply_lora, load_lora, load_lora_swa, save_lora  # noqa: F401
-from .methods import Channel_LP, cls_acc, cosine_topk, logit_normalize, solve_mta, solve_mta_batched, solve_mta_logits  # noqa: F401
+from .methods import Channel_LP, clip_classifier, cls_acc, cosine_topk, logit_normalize, solve_mta, solve_mta_batched, solve_mta_logits  # noqa: F401
 from .pipeline import HotPath, TextBank, evaluate_new_batch, split_ood_batch  # noqa: F401
 from .runtime import get_context  # noqa: F401
 from .tta import TTAViews  # noqa: F401

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "jcb_text_clear_lora": (c_int, [c_void_p]),
     "jcb_text_finalize": (c_int, [c_void_p]),
     "jcb_encode_text": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "jcb_class_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "jcb_tta_views": (c_int, [c_void_p, c_void_p, POINTER(SrcImage), c_int32, POINTER(ViewJob), c_int64, c_int32,
                               c_void_p]),
     "jcb_mta_default_params": (None, [POINTER(MtaParams)]),

@@ -996,6 +996,15 @@ int jcb_channel_lp(jcb_ctx* ctx, const float* feats, int64_t n, int32_t n_classe
   return JCB_OK;
 }
 
+int jcb_class_mean(jcb_ctx* ctx, const float* emb_dev, const int32_t* offsets_dev, int32_t n_classes, int32_t dim,
+                   float* out_dev) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!emb_dev || !offsets_dev || !out_dev || n_classes < 0 || dim < 1) return fail(ctx, JCB_E_INVALID, "jcb_class_mean: bad arguments");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_class_mean(emb_dev, offsets_dev, n_classes, dim, out_dev, ctx->stream));
+  return JCB_OK;
+}
+
 int jcb_logit_normalize(jcb_ctx* ctx, const float* in, int64_t n, int32_t n_classes, float* out) {
   if (!ctx) return JCB_E_INVALID;
   if (!in || !out || n < 0) return fail(ctx, JCB_E_INVALID, "jcb_logit_normalize: bad arguments");

@@ -217,7 +217,33 @@ logit_normalize_kernel(const float* __restrict__ in, long long n, int C, float* 
   }
 }
 
+// clip_classifier (test.py:920-940): per class, mean of the (already unit-norm) template embeddings, re-normalised.
+// emb [n, D], offsets [C + 1] (templates of class c are rows offsets[c] .. offsets[c+1]), out [C, D].
+__global__ void __launch_bounds__(HEAD_THREADS)
+class_mean_kernel(const float* __restrict__ emb, const int* __restrict__ offsets, int D, float* __restrict__ out) {
+  __shared__ float s_red[32];
+  const int c = blockIdx.x;
+  const int lo = offsets[c], hi = offsets[c + 1];
+  const float inv_n = 1.0f / static_cast<float>(hi - lo);
+  float q = 0.f;
+  for (int d = threadIdx.x; d < D; d += HEAD_THREADS) {
+    float s = 0.f;
+    for (int r = lo; r < hi; ++r) s += emb[static_cast<long long>(r) * D + d];
+    s *= inv_n;
+    out[static_cast<long long>(c) * D + d] = s;
+    q = fmaf(s, s, q);
+  }
+  const float inv = 1.0f / sqrtf(hblock_sum(q, s_red));
+  for (int d = threadIdx.x; d < D; d += HEAD_THREADS) out[static_cast<long long>(c) * D + d] *= inv;
+}
+
 }  // namespace
+
+cudaError_t launch_class_mean(const float* emb, const int* offsets, int C, int D, float* out, cudaStream_t stream) {
+  if (C == 0) return cudaSuccess;
+  class_mean_kernel<<<static_cast<unsigned>(C), HEAD_THREADS, 0, stream>>>(emb, offsets, D, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream) {
   if (a.k < 1 || a.k > 8 || a.k > a.C || a.rank_by < 0 || a.rank_by >= SCORE_COUNT || a.C < 2 || a.D < 1)

@@ -108,6 +108,7 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream);
 // Stand-alone pieces of the head (drop-in functions of the reference's Python API)
 cudaError_t launch_channel_lp(const float* feats, int64_t n, int C, int D, const float* scale1, const float* bias1,
                               const float* fc_w, const float* fc_b, float* out, cudaStream_t stream);
+cudaError_t launch_class_mean(const float* emb, const int* offsets, int C, int D, float* out, cudaStream_t stream);
 cudaError_t launch_logit_normalize(const float* in, int64_t n, int C, float* out, cudaStream_t stream);
 cudaError_t launch_cosine_topk(const float* feats, const float* text, int64_t n, int C, int D, float scale, int k,
                                int32_t* out_topk, float* out_scores, cudaStream_t stream);

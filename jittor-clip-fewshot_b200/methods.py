@@ -147,6 +147,30 @@ def cosine_topk(features, text_features, k=5, scale=100.0, return_scores=False):
     return (idx, sc) if return_scores else idx
 
 
+def clip_classifier(templates_dict, clip_model, tokenize=None):
+    """reference test.py:920-940: per class, tokenize every template, encode_text, L2-normalise, average,
+    re-normalise; returns [1, C, D] (callers `.squeeze(0)`).  One batched `encode_text` call for all templates
+    instead of one call per template; `tokenize` defaults to `jclip.clip.tokenize`; `templates_dict` values may
+    also be pre-tokenised int64 arrays [T_c, context]."""
+    if tokenize is None:
+        from .jclip.clip import tokenize
+    toks, offsets = [], [0]
+    for _, templates in templates_dict.items():
+        t = templates if isinstance(templates, (np.ndarray, torch.Tensor)) else tokenize(list(templates))
+        t = as_torch(t).to(torch.int64).reshape(-1, as_torch(t).shape[-1])
+        toks.append(t.cpu())
+        offsets.append(offsets[-1] + t.shape[0])
+    emb = clip_model.encode_text(torch.cat(toks, dim=0), normalize=True)      # test.py:927-929
+    C, D = len(offsets) - 1, emb.shape[1]
+    with torch.cuda.device(emb.device):
+        ctx = get_context(emb.device)
+        ctx.bind_current_stream()
+        off = torch.tensor(offsets, dtype=torch.int32, device=emb.device)
+        out = torch.empty((C, D), dtype=torch.float32, device=emb.device)
+        check(ctx.lib.jcb_class_mean(ctx.handle, ptr(emb), ptr(off), C, D, ptr(out)), ctx.handle)
+    return out.unsqueeze(0)
+
+
 def cls_acc(output, target, topk=1):
     """reference test.py:821-826 (bookkeeping on the host; not a kernel)."""
     out = as_torch(output).detach().float().cpu()

@@ -67,3 +67,18 @@ def test_causal_attention_kernel(jb, cuda_dev):
     tok2[:, 40:60] = 5                                        # garbage after the EOT (ids below the EOT id)
     b = model.encode_text(torch.from_numpy(tok2).to(cuda_dev)).cpu()
     assert torch.equal(a, b)
+
+
+def test_clip_classifier(jb, cuda_dev):
+    """reference test.py:920-940 on pre-tokenised templates: per class mean of unit embeddings, re-normalised."""
+    from oracle import text_encode
+    sd = jb.synth.make_vit_state_dict(seed=8, layers=1, text_layers=2)
+    model = jb.jclip.build_model(sd)
+    templates = {c: jb.synth.make_tokens(100 + c, 2 + c % 3, vocab=64) for c in range(7)}
+    W = jb.clip_classifier(templates, model)
+    assert W.shape == (1, 7, 512) and W.is_cuda
+    for c, tok in templates.items():
+        e = text_encode(sd, tok, normalize=True).mean(dim=0)
+        e = e / e.norm()
+        assert _cos(W[0, c].cpu(), e) >= 0.9995
+    assert (W[0].norm(dim=-1).cpu() - 1).abs().max() < 1e-5
