@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--img-dtype", default="u8", choices=["u8", "f32"],
                     help="pixel format of the views: u8 (0..255, what an image decoder / the reference's PIL pipeline "
                          "produces before ToTensor; scaled by 1/255 on the device, bit-identical to ToTensor) or f32 in [0,1]")
+    ap.add_argument("--host-chunk-views", type=int, default=0, help="views per pass when the input is in host memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -198,6 +199,8 @@ def main():
     ctx = jb.get_context(dev)
     if args.chunk_views:
         ctx.set_chunk_views(args.chunk_views)
+    if args.host_chunk_views:
+        ctx.set_host_chunk_views(args.host_chunk_views)
 
     # this rank's shard of the step's images: I images x V views, generated on the device
     images = jb.synth.make_views_torch(1000 + rank, I, V, dev)

@@ -75,6 +75,7 @@ int jcb_ctx_set_stream(jcb_ctx* ctx, void* cuda_stream);
  * (measured on B200: larger passes are faster, intermediates never fit L2 anyway) and min(2048, bound)
  * for host input, so that the copy of pass i+1 overlaps the compute of pass i. */
 int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
+int jcb_ctx_set_host_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
 /* Wait for the context's stream and report any device-side kernel status. */
 int jcb_sync(jcb_ctx* ctx);
 const char* jcb_last_error(const jcb_ctx* ctx);

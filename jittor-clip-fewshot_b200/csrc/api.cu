@@ -463,6 +463,12 @@ int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views) {
   return JCB_OK;
 }
 
+int jcb_ctx_set_host_chunk_views(jcb_ctx* ctx, int64_t chunk_views) {
+  if (!ctx || chunk_views < 1 || chunk_views > 40000) return ctx ? fail(ctx, JCB_E_INVALID, "chunk_views out of range") : JCB_E_INVALID;
+  ctx->host_chunk_views = chunk_views;
+  return JCB_OK;
+}
+
 int jcb_sync(jcb_ctx* ctx) {
   if (!ctx) return JCB_E_INVALID;
   DeviceGuard g(ctx->device);

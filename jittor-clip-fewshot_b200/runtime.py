@@ -38,6 +38,9 @@ class Context:
     def set_chunk_views(self, n):
         check(self.lib.jcb_ctx_set_chunk_views(self.handle, int(n)), self.handle)
 
+    def set_host_chunk_views(self, n):
+        check(self.lib.jcb_ctx_set_host_chunk_views(self.handle, int(n)), self.handle)
+
     def sync(self):
         check(self.lib.jcb_sync(self.handle), self.handle)
 
