@@ -264,17 +264,22 @@ def main():
         src = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I)]
         gen = jb.TTAViews(n_crops=args.crops, scale=(0.5, 1.0), seed=rank)
 
-        def step_images():
+        def run_images(steps):
+            # software pipeline: while the GPU works on batch k, the host draws the boxes of batch k+1, packs its
+            # images into the other pinned buffer and enqueues upload + view generation behind the running step
             views = gen(src)
-            return hp.evaluate_base(views, topk_to_host=True)
+            for k in range(steps):
+                topk_dev = hp.evaluate_base(views, topk_to_host=False)
+                if k + 1 < steps:
+                    views = gen(src)
+                topk = topk_dev.cpu()          # the step's result on the host (synchronises with step k)
+            return topk
 
-        for _ in range(2):
-            step_images()
+        run_images(2)
         jb.dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(K):
-            step_images()
+        run_images(K)
         torch.cuda.synchronize()
         dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
         e2e_img = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,

@@ -352,9 +352,13 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
   TowerWs w = tower_ws_carve(v, chunk, b);
   const size_t view_bytes = static_cast<size_t>(3) * v->cfg.resolution * v->cfg.resolution * img_elem_bytes(dt);
   if (on_host && (rc = stage_reserve(ctx, chunk * view_bytes))) return rc;
+  // Host input: the upload of pass i+1 overlaps the compute of pass i, but nothing hides the FIRST upload, so
+  // the first pass is a quarter of the others (its copy is 4x shorter; it is too short to matter for the GEMMs).
+  const int64_t lead = (on_host && n > chunk) ? std::max<int64_t>(chunk / 4, 1) : 0;
+  const int64_t body = lead ? balanced_chunk(n - lead, chunk) : chunk;
   int64_t ci = 0;
-  for (int64_t off = 0; off < n; off += chunk, ++ci) {
-    const int64_t m = std::min(chunk, n - off);
+  for (int64_t off = 0; off < n; ++ci) {
+    const int64_t m = std::min(ci == 0 && lead ? lead : body, n - off);
     const void* src = static_cast<const uint8_t*>(images) + off * view_bytes;
     if (on_host) {
       const int buf = static_cast<int>(ci & 1);
@@ -369,6 +373,7 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
              static_cast<double>(m) * (v->cfg.width + v->cfg.embed_dim) * 4, launch_tail(w.tokens, m, v->tokens, v->cfg.width, v->ln_post_g, v->ln_post_b, v->proj,
                             v->cfg.embed_dim, normalize, out_dev + off * v->cfg.embed_dim, ctx->stream));
     if (on_host) CUDA_TRY(ctx, cudaEventRecord(ctx->compute_done[ci & 1], ctx->stream));
+    off += m;
   }
   return JCB_OK;
 }

@@ -104,7 +104,9 @@ class TTAViews:
         self.size, self.resize, self.flip_p = size, resize, flip_p
         self.rng = np.random.default_rng(seed)
         self.device = device
-        self._pinned = None     # grow-only pinned staging buffer for the packed source images
+        self._pinned = [None, None]     # two grow-only pinned staging buffers for the packed source images ...
+        self._copied = [None, None]     # ... and the event that marks the end of the upload out of each
+        self._turn = 0
 
     def draw_jobs(self, shapes):
         """One centre job + n_crops crop jobs per (H, W): a (ViewJob * n) ctypes array."""
@@ -175,17 +177,23 @@ class TTAViews:
         for i, im in enumerate(imgs):
             descs[i].offset, descs[i].height, descs[i].width = off, im.shape[0], im.shape[1]
             off += (im.size + 15) // 16 * 16
-        if self._pinned is None or self._pinned.numel() < off:
-            self._pinned = torch.empty(max(off, 16), dtype=torch.uint8, pin_memory=True)
-        else:
-            torch.cuda.current_stream(dev).synchronize()   # the previous upload from this buffer has finished
-        host = self._pinned[:max(off, 16)]
+        # double-buffered: packing batch i+1 on the host overlaps the GPU work of batch i; a buffer is reused only
+        # after the upload that last read it has completed (its event), never after a full stream sync
+        t = self._turn
+        self._turn ^= 1
+        if self._pinned[t] is None or self._pinned[t].numel() < off:
+            self._pinned[t] = torch.empty(max(off, 16), dtype=torch.uint8, pin_memory=True)
+        elif self._copied[t] is not None:
+            self._copied[t].synchronize()
+        host = self._pinned[t][:max(off, 16)]
         hv = host.numpy()
         for d, im in zip(descs, imgs):
             hv[d.offset:d.offset + im.size] = im.reshape(-1)
         with torch.cuda.device(dev):
             ctx.bind_current_stream()
             src = host.to(dev, non_blocking=True)
+            self._copied[t] = torch.cuda.Event()
+            self._copied[t].record()
             out = torch.empty((n_jobs, 3, self.size, self.size), dtype=torch.uint8, device=dev)
             check(ctx.lib.jcb_tta_views(ctx.handle, ptr(src), descs, len(imgs), jobs_ptr, n_jobs, self.size, ptr(out)),
                   ctx.handle)
