@@ -1,0 +1,88 @@
+"""GPU: BASELINE.json's full sizes through size-independent properties (the oracle cannot run these in
+seconds): config 2 = batch 1024 views through the LoRA tower; config 5 = thousands of images x N in {1, 16, 64}
+crops through the whole pipeline.  Properties: a sub-sample matches the fp32 oracle, results do not depend on
+how the batch is split into passes (bit-exact), views / images are processed independently (permutation
+equivariance, bit-exact), and a batched call equals per-image calls."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double(), b.double()
+    return (a * b).sum(-1) / (a.norm(dim=-1) * b.norm(dim=-1))
+
+
+@pytest.fixture(scope="module")
+def lora_model(jb):
+    sd = jb.synth.make_vit_state_dict(seed=0)
+    model = jb.jclip.build_model(sd)
+    args = types.SimpleNamespace(encoder="vision", position="all", params=["q", "k", "v"], r=4, alpha=1,
+                                 dropout_rate=0.25, backbone="ViT-B/32")
+    layers = jb.apply_lora(args, model)
+    lora = jb.synth.make_lora(seed=7, b_std=0.05)
+    for i, layer in enumerate(layers):
+        for name, (A, B) in lora[i].items():
+            getattr(layer, name).w_lora_A.data = A
+            getattr(layer, name).w_lora_B.data = B
+    return sd, lora, model
+
+
+def test_batch_1024_encode_image(jb, cuda_dev, lora_model):
+    """BASELINE config 2: ViT-B/32 + LoRA encode_image, batch 1024."""
+    from oracle import vit_encode_image
+    sd, lora, model = lora_model
+    x = jb.synth.make_views_torch(5, 16, 64, cuda_dev).reshape(1024, 3, 224, 224)
+    ctx = jb.get_context(cuda_dev)
+    f = model.visual(x, apply_clip_norm=True, normalize=True)
+    assert f.shape == (1024, 512) and torch.isfinite(f).all()
+    assert (f.norm(dim=-1) - 1).abs().max() < 1e-5
+    # a sub-sample against the fp32 oracle
+    idx = torch.tensor([0, 1, 63, 64, 500, 777, 1022, 1023])
+    ref = vit_encode_image(sd, x[idx.to(cuda_dev)].cpu().numpy(), lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    assert _cos(f[idx.to(cuda_dev)].cpu(), ref).min() >= 0.9995
+    # pass-size invariance: 1 pass of 1024 == 4 passes of 256 == 7 ragged passes, bit for bit
+    try:
+        for bound in (256, 150):
+            ctx.set_chunk_views(bound)
+            assert torch.equal(model.visual(x, apply_clip_norm=True, normalize=True), f), bound
+    finally:
+        ctx.set_chunk_views(16384)
+    # views are independent: permuting the batch permutes the embeddings, bit for bit
+    perm = torch.randperm(1024, generator=torch.Generator().manual_seed(0)).to(cuda_dev)
+    assert torch.equal(model.visual(x[perm].contiguous(), apply_clip_norm=True, normalize=True), f[perm])
+    # determinism
+    assert torch.equal(model.visual(x, apply_clip_norm=True, normalize=True), f)
+
+
+@pytest.mark.parametrize("n_crops,n_images", [(1, 2048), (16, 512), (64, 192)])
+def test_pipeline_sweep_sizes(jb, cuda_dev, lora_model, n_crops, n_images):
+    """BASELINE config 5 (scaled to one GPU's minute budget): images x N in {1, 16, 64} crops."""
+    from oracle import pipeline_image
+    sd, lora, model = lora_model
+    V = n_crops + 1
+    imgs = (jb.synth.make_views_torch(11, n_images, V, cuda_dev) * 255).round_().to(torch.uint8)
+    Ts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
+    lp_np = jb.synth.make_head(2, Ts[2].numpy())
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = lp_np
+    hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by="cs5")
+    topk, feats, scores = hp.evaluate_base(imgs, return_feats=True, return_scores=True)
+    assert topk.shape == (n_images, 5) and int(topk.min()) >= 0 and int(topk.max()) < 403
+    assert all(len(set(r)) == 5 for r in topk.cpu().tolist())
+    # images are independent: a permutation of the images permutes the predictions, bit for bit
+    perm = torch.randperm(n_images, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    assert torch.equal(hp.evaluate_base(imgs[perm].contiguous()), topk[perm])
+    # batched == one image at a time (a handful), and the oracle agrees on those given the same embeddings
+    lp_t = tuple(torch.from_numpy(a) for a in lp_np)
+    for i in (0, n_images // 2, n_images - 1):
+        single = hp.evaluate_base(imgs[i:i + 1].contiguous())
+        assert torch.equal(single[0], topk[i])
+        fi = feats[i].cpu()
+        t5, sc, _ = pipeline_image(fi, fi, Ts[0], Ts[1], Ts[2], lp_t, score="cs5")
+        assert (scores[i].cpu() - sc["cs5"][0]).abs().max() <= 1e-2
+        assert set(t5.tolist()) == set(topk[i].cpu().tolist())
