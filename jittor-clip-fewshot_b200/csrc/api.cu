@@ -3,6 +3,7 @@
 // gemm.cu, attention.cu, rowwise.cu, mta.cu and head.cu.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -30,6 +31,8 @@ struct jcb_ctx {
   void* stage[2] = {nullptr, nullptr};  // device staging for host images
   size_t stage_bytes = 0;
   int64_t launches = 0;
+  int ln_fold = 1;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
+                                     // 0 none, 1 ln_1 only (c_proj -> QKV), 2 ln_1 and ln_2
   char err[512] = {0};
   // per-kernel-class CUDA-event profile (jcb_ctx_profile): event pairs recorded on the launch stream
   bool prof_on = false;
@@ -160,6 +163,9 @@ struct LayerDev {
   __nv_bfloat16 *in_w = nullptr, *out_w = nullptr, *fc_w = nullptr, *proj_w = nullptr;
   float *in_b = nullptr, *out_b = nullptr, *fc_b = nullptr, *proj_b = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  // LayerNorm folded into the consuming GEMM: gamma-scaled weights, their column sums S and the constants c
+  __nv_bfloat16 *in_wf = nullptr, *fc_wf = nullptr;
+  float *in_S = nullptr, *in_c = nullptr, *fc_S = nullptr, *fc_c = nullptr;
 };
 
 // What the image tower and the text tower share: a stack of pre-LN transformer blocks with packed-QKV
@@ -240,11 +246,12 @@ struct TowerWs {
   __nv_bfloat16* ln_out;  // [n*T, W]
   __nv_bfloat16* qkv;     // [n*T, 3W]
   __nv_bfloat16* attn;    // [n*T, W]
+  float* stats;           // [n*T, W/256, 2] partial (sum, sum of squares) of the residual rows (LayerNorm fold)
 };
 size_t tower_ws_bytes_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n) {
   const size_t big = std::max(n * GG * KP, n * T * 4 * W) * 2;
   return align_up(big) + align_up(n * T * W * 4) + align_up(n * T * W * 2) + align_up(n * T * 3 * W * 2) +
-         align_up(n * T * W * 2);
+         align_up(n * T * W * 2) + align_up(n * T * ((W + 255) / 256) * 8);
 }
 size_t tower_ws_bytes(const jcb_vit* v, int64_t n) {
   return tower_ws_bytes_dims(v->W, v->tokens, static_cast<size_t>(v->grid) * v->grid, v->kpatch, n);
@@ -256,6 +263,7 @@ TowerWs tower_ws_carve_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n,
   w.ln_out = b.take<__nv_bfloat16>(n * T * W);
   w.qkv = b.take<__nv_bfloat16>(n * T * 3 * W);
   w.attn = b.take<__nv_bfloat16>(n * T * W);
+  w.stats = b.take<float>(n * T * ((W + 255) / 256) * 2);
   return w;
 }
 TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
@@ -264,12 +272,16 @@ TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
 
 int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
              const float* bias, int epi, void* out, int64_t ldo, const float* pos = nullptr, int tin = 49,
-             int tout = 50) {
+             int tout = 50, float* stats = nullptr, int stats_slots = 0, const float* colsum = nullptr,
+             void* out2 = nullptr) {
   GemmArgs g;
+  g.stats = stats; g.stats_slots = stats_slots; g.colsum = colsum; g.out2 = out2; g.ldo2 = N;
   g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo; g.pos = pos; g.tokens_in = tin; g.tokens_out = tout;
   // algorithmic bytes: A + B read once, C written once (read-modify-write for the residual epilogue)
-  const double out_b = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 ? 2.0 : (epi == EPI_BIAS_RESID_F32 ? 8.0 : 4.0);
+  const bool lnprep = epi == EPI_RESID_LNPREP_SHORT || epi == EPI_RESID_LNPREP_LONG;
+  const double out_b = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16)
+                           ? 2.0 : (epi == EPI_BIAS_RESID_F32 ? 8.0 : (lnprep ? 10.0 : 4.0));
   const double bytes = 2.0 * M * K + 2.0 * N * K + out_b * M * N;
   LAUNCH_P(ctx, cls, 2.0 * M * N * K, bytes, launch_gemm(g, ctx->dev_status, ctx->num_sms, ctx->stream));
   return JCB_OK;
@@ -284,6 +296,41 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
   const int M = static_cast<int>(n * T);
   const double MW = static_cast<double>(M) * W;
   int rc;
+  if (ctx->ln_fold && t->layers[0].in_wf != nullptr) {
+    // LayerNorm folded into the GEMMs: for a folded LayerNorm, w.ln_out holds the RAW bf16 copy of the residual
+    // stream and w.stats its per-row partial sums (written by the embed kernel for block 0, then by the residual
+    // epilogue of the producing GEMM), and no stand-alone pass reads the fp32 residual stream.
+    //   ln_fold >= 1: ln_1 (c_proj of block l-1 -> QKV of block l).  c_proj's 48 k-blocks per tile hide the heavier
+    //                 epilogue; measured net gain.
+    //   ln_fold == 2: ln_2 as well (out_proj -> c_fc).  out_proj is HBM-bound and pays 12 instead of 10 bytes per
+    //                 element, c_fc's GELU epilogue gets heavier: measured net LOSS against the 3.6 ms ln_2 pass.
+    const bool fold2 = ctx->ln_fold >= 2;
+    const int slots = (W + 255) / 256;
+    for (int l = 0; l < t->L; ++l) {
+      const LayerDev& L = t->layers[l];
+      if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, nullptr,
+                         49, 50, w.stats, slots, L.in_S))) return rc;
+      LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
+               launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal));
+      if (fold2) {
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens, W, nullptr,
+                           49, 50, w.stats, slots, nullptr, w.ln_out))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_wf, M, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W,
+                           nullptr, 49, 50, w.stats, slots, L.fc_S))) return rc;
+      } else {
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+        LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
+      }
+      if (l + 1 < t->L) {
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_RESID_LNPREP_LONG, w.tokens, W,
+                           nullptr, 49, 50, w.stats, slots, nullptr, w.ln_out))) return rc;
+      } else if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) {
+        return rc;
+      }
+    }
+    return JCB_OK;
+  }
   for (int l = 0; l < t->L; ++l) {
     const LayerDev& L = t->layers[l];
     if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
@@ -318,7 +365,7 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   if (rc) return rc;
   // class token + ln_pre (residual stream) + layer 0's ln_1
   LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->vpt, v->cfg.vpt_tokens, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
-                              v->layers[0].ln1_b, w.ln_out, s));
+                              v->layers[0].ln1_b, w.ln_out, s, (ctx->ln_fold && v->layers[0].in_wf) ? w.stats : nullptr, (W + 255) / 256));
   return tower_blocks(v, n, w, 0);
 }
 
@@ -409,6 +456,10 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
   jcb_ctx* ctx = new jcb_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  {
+    const char* env = getenv("JCB_LN_FOLD");
+    ctx->ln_fold = env ? atoi(env) : 1;   // default: fold ln_1 (measured -1.5 ms / step); see tower_blocks
+  }
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   DeviceGuard g(device);
@@ -656,6 +707,29 @@ struct Packer {
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return JCB_OK;
   }
+  // LayerNorm fold of one weight: merged fp32 W (LoRA adapters applied in place) -> gamma-scaled bf16 Wf, S, c
+  int up_folded(const std::string& key, size_t rows, size_t cols,
+                const std::vector<std::pair<size_t, const LoraAdapter*>>& adapters, const float* gamma_dev,
+                const float* beta_dev, const float* bias_dev, __nv_bfloat16** wf, float** S, float** c) {
+    cudaStream_t s = ctx->stream;
+    const std::vector<float>& h = t->host[key];
+    *wf = b.take<__nv_bfloat16>(h.size());
+    *S = b.take<float>(rows);
+    *c = b.take<float>(rows);
+    CUDA_TRY(ctx, cudaMemcpyAsync(tmp_w, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
+    for (auto& ad : adapters) {
+      const LoraAdapter* a = ad.second;
+      CUDA_TRY(ctx, cudaMemcpyAsync(tmp_A, a->A.data(), a->A.size() * 4, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(ctx, cudaMemcpyAsync(tmp_B, a->B.data(), a->B.size() * 4, cudaMemcpyHostToDevice, s));
+      LAUNCH(ctx, launch_merge_lora_f32(tmp_w + ad.first * cols, tmp_A, tmp_B, t->W, static_cast<int>(cols), a->r,
+                                        a->scaling, s));
+      CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    }
+    LAUNCH(ctx, launch_fold_ln(tmp_w, gamma_dev, beta_dev, bias_dev, static_cast<int>(rows), static_cast<int>(cols), *wf,
+                               *S, *c, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return JCB_OK;
+  }
   int pack_blocks() {
     const size_t W = t->W;
     t->layers.assign(t->L, LayerDev());
@@ -681,6 +755,12 @@ struct Packer {
       if ((rc = up_f32(blk(t, li, "ln_1.bias"), &Ld.ln1_b))) return rc;
       if ((rc = up_f32(blk(t, li, "ln_2.weight"), &Ld.ln2_g))) return rc;
       if ((rc = up_f32(blk(t, li, "ln_2.bias"), &Ld.ln2_b))) return rc;
+      if (ctx->ln_fold) {
+        if ((rc = up_folded(blk(t, li, "attn.in_proj_weight"), 3 * W, W, in_ad, Ld.ln1_g, Ld.ln1_b, Ld.in_b, &Ld.in_wf,
+                            &Ld.in_S, &Ld.in_c))) return rc;
+        if ((rc = up_folded(blk(t, li, "mlp.c_fc.weight"), 4 * W, W, {}, Ld.ln2_g, Ld.ln2_b, Ld.fc_b, &Ld.fc_wf, &Ld.fc_S,
+                            &Ld.fc_c))) return rc;
+      }
     }
     return JCB_OK;
   }
@@ -693,7 +773,9 @@ struct Packer {
 };
 
 size_t blocks_arena_bytes(size_t W, size_t L) {
-  return L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2) + 8 * align_up(4 * W * 4));
+  // packed weights + biases / LayerNorm vectors, plus the LayerNorm-folded copies of in_proj / c_fc (Wf, S, c)
+  return L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2) + 8 * align_up(4 * W * 4) +
+              align_up(3 * W * W * 2) + align_up(4 * W * W * 2) + 4 * align_up(4 * W * 4));
 }
 
 int tower_set_param(TowerBase* t, const char* name, const float* data, int64_t numel) {
@@ -853,7 +935,7 @@ int jcb_encode_text(jcb_text* t, const int64_t* tokens_dev, int64_t n_seq, int n
     LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2),
              launch_text_embed_ln(reinterpret_cast<const long long*>(tokens_dev) + off * T, m, T, W, t->cfg.vocab_size,
                                   t->tok_emb, t->pos, t->layers[0].ln1_g, t->layers[0].ln1_b, w.tokens, w.ln_out, eot,
-                                  ctx->stream));
+                                  ctx->stream, (ctx->ln_fold && t->layers[0].in_wf) ? w.stats : nullptr, (W + 255) / 256));
     if ((rc = tower_blocks(t, m, w, 1))) return rc;
     LAUNCH_P(ctx, JCB_KC_TAIL, 2.0 * m * W * E, static_cast<double>(m) * (W + E) * 4,
              launch_tail(w.tokens, m, T, W, t->ln_final_g, t->ln_final_b, t->text_projection, E, normalize,

@@ -35,28 +35,49 @@ namespace {
 constexpr int BLOCK_M = 128;  // rows of A (and of the accumulator) per CTA
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARPS = 4;
-constexpr int SMEM_TOTAL = 200 * 1024;  // operand ring + epilogue staging (bias tile, barriers, align slack on top)
+// epilogue warps: 4 (one per TMEM lane quarter, all BN columns each) or 8 (two per quarter, half the columns each)
+// for the MUFU-heavy GELU epilogues, which are bound by the epilogue warps' issue slots rather than by the tensor pipe
+__host__ __device__ constexpr int epi_warps_of(int epi) {
+  // measured on B200 (tools/bench_kernel.py gemm): 8 warps do NOT help c_fc (1284 vs 1337 TFLOP/s) -- under the
+  // power cap the extra warps cost more than the issue slots they add -- so every epilogue uses 4
+  return (epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_GELU_BF16) ? 4 : 4;
+}
 
 // chunks converted per generic->async proxy fence / per batch of TMA stores.  The MUFU-heavy GELU epilogue
 // (fc1) is the one that is epilogue-bound: it gets the whole tile per fence and pays with one ring stage
 // (4 instead of 5); the mainloop-bound shapes keep 5 stages and fence every 2 chunks.  Measured on B200:
 // fc1 1260 -> 1346 TFLOP/s with GROUP 4; fc2 / qkv lose ~5 % with only 4 stages.
-constexpr int group_of(int epi) { return epi == EPI_BIAS_GELU_BF16 ? 4 : 2; }
+__host__ __device__ constexpr int group_of(int epi) { return (epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_GELU_BF16) ? 4 : 2; }
+__host__ __device__ constexpr bool is_lnprep(int epi) { return epi == EPI_RESID_LNPREP_SHORT || epi == EPI_RESID_LNPREP_LONG; }
+__host__ __device__ constexpr bool is_lnfold(int epi) { return epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16; }
+__host__ __device__ constexpr bool out_is_bf16(int epi) { return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || is_lnfold(epi); }
+// LNPREP (residual epilogue that also reads the old residual through TMA loads): NB fp32 chunk buffers per warp,
+// loads issued D chunks ahead, NH bf16 chunk buffers.  SHORT (out_proj, HBM-bound, 12 k-blocks per tile): deep
+// prefetch, 3 ring stages.  LONG (c_proj, 48 k-blocks per tile, tensor-bound): shallow prefetch, 5 ring stages.
+__host__ __device__ constexpr int lnprep_nb(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? 5 : 2; }
+__host__ __device__ constexpr int lnprep_d(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? 3 : 1; }
+__host__ __device__ constexpr int lnprep_nh(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? 2 : 1; }
 
 template <int BN, int CTAS, int EPI>
 struct TileCfg {
-  static constexpr int GROUP = group_of(EPI);
-  static constexpr int WARP_STAGING = GROUP * 4096;  // per epilogue warp: GROUP 32-row x 128-B swizzled chunks
+  static constexpr int EPI_WARPS = epi_warps_of(EPI);
+  static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int HALVES = EPI_WARPS / 4;     // column slices of the tile, one per warp of a lane quarter
+  static constexpr int CW = BN / HALVES;           // columns handled by one epilogue warp
+  static constexpr int GROUP = group_of(EPI) / HALVES;
+  // per epilogue warp: 32-row x 128-B swizzled chunks (GROUP of them, or NB + NH for the LNPREP epilogues)
+  static constexpr int WARP_STAGING = (is_lnprep(EPI) ? lnprep_nb(EPI) + lnprep_nh(EPI) : GROUP) * 4096;
   static constexpr int STAGING_BYTES = EPI_WARPS * WARP_STAGING;
+  static constexpr int SMEM_TOTAL = is_lnprep(EPI) ? 220 * 1024 : 200 * 1024;  // operand ring + epilogue staging
+  static constexpr int VEC_FLOATS = (is_lnfold(EPI) ? 2 : 1) * CW;             // per-warp bias (+ column-sum) slice
+  static constexpr int BAR_BYTES = 512;
   static constexpr int B_ROWS = BN / CTAS;  // rows of the B tile this CTA stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_TOTAL - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; power of two for BN in {128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 4 * BN * 4 + 256 + 1024;  // + per-warp bias + barriers + align slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + EPI_WARPS * VEC_FLOATS * 4 + BAR_BYTES + 1024;  // + per-warp vectors + barriers + align slack
 };
 
 struct GemmDev {
@@ -67,6 +88,9 @@ struct GemmDev {
   const float* pos;
   int tokens_in, tokens_out;
   int* status;
+  float* stats;          // LNFOLD: in / LNPREP: out, [M, stats_slots, 2]
+  int stats_slots;
+  const float* colsum;   // LNFOLD
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
@@ -78,12 +102,14 @@ __device__ __forceinline__ float quick_gelu(float x) {
 
 template <int BN, int EPI, int CTAS>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                                          const GemmDev& p) {
+                                          const CUtensorMap& tmOut2, const GemmDev& p) {
   using Cfg = TileCfg<BN, CTAS, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GROUP = Cfg::GROUP;
   constexpr int WARP_STAGING = Cfg::WARP_STAGING;
   constexpr int STAGING_BYTES = Cfg::STAGING_BYTES;
+  constexpr int EPI_WARPS = Cfg::EPI_WARPS;
+  constexpr int CW = Cfg::CW;
   constexpr bool PAIR = CTAS == 2;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment in the shared address space.
@@ -92,12 +118,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   uint8_t* ring = smem;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;   // 1024-B aligned (STAGE_BYTES is a multiple of 1024)
   float* s_bias_all = reinterpret_cast<float*>(staging + STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + 4 * BN * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + EPI_WARPS * Cfg::VEC_FLOATS * 4);
   uint64_t* full_bar = bars;                         // [STAGES]  TMA -> MMA       (the leader CTA's copy is used)
   uint64_t* empty_bar = bars + STAGES;               // [STAGES]  MMA -> TMA       (each CTA its own)
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]  MMA -> epilogue       (each CTA its own)
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]  epilogue -> MMA       (the leader CTA's copy is used)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* load_bar = bars + 2 * STAGES + 5;        // [EPI_WARPS][8]  LNPREP: old-residual chunk landed in staging
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -117,6 +144,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_PATCH_F32) tma_prefetch_desc(&tmOut);
+    if (is_lnprep(EPI)) {
+      tma_prefetch_desc(&tmOut2);
+      for (int i = 0; i < EPI_WARPS * 8; ++i) mbar_init(&load_bar[i], 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -212,10 +243,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     }
   } else {
     // ===================================================================== epilogue (warps 2..5, every CTA)
-    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int q = warp_idx & 3;              // TMEM lane quarter this warp may access
+    const int ew = warp_idx - 2;             // epilogue warp index
+    const int col0 = (ew >> 2) * CW;         // first column of the tile this warp handles
     // Each epilogue warp keeps a private copy of the tile's bias slice: no cross-warp barrier in
     // the epilogue, so a warp that abandons its loop on a pipeline error cannot strand the others.
-    float* s_bias = s_bias_all + q * BN;
+    float* s_bias = s_bias_all + ew * Cfg::VEC_FLOATS;  // bias (LNFOLD: c[n]) of this warp's columns ...
+    float* s_csum = s_bias + CW;                          // ... and, LNFOLD only, the column sums S[n]
+    uint64_t* my_lbar = load_bar + ew * 8;
+    uint32_t lphase = 0;                                  // LNPREP: parity bit per staging buffer
     const uint32_t empty_addr0 = smem_u32(&tmem_empty_bar[0]) & (PAIR ? PEER_BIT_MASK : 0xFFFFFFFFu);
     int it = 0;
     bool ok = true;
@@ -224,8 +260,25 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       __syncwarp();
-      for (int i = lane; i < BN; i += 32) s_bias[i] = p.bias ? __ldg(p.bias + n_blk * BN + i) : 0.0f;
+      for (int i = lane; i < CW; i += 32) {
+        s_bias[i] = p.bias ? __ldg(p.bias + n_blk * BN + col0 + i) : 0.0f;
+        if (is_lnfold(EPI)) s_csum[i] = __ldg(p.colsum + n_blk * BN + col0 + i);
+      }
       __syncwarp();
+      const int row0e = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;   // this warp's 32 rows
+      if (is_lnprep(EPI)) {
+        // the old residual of the first D chunks is requested BEFORE waiting for the accumulator: its latency hides
+        // behind the main loop.  Every earlier store of this warp must have released the staging buffers.
+        if (lane == 0) {
+          bulk_wait_read<0>();
+#pragma unroll
+          for (int d = 0; d < lnprep_d(EPI); ++d) {
+            mbar_arrive_expect_tx(&my_lbar[d], 4096);
+            tma_load_2d(staging + ew * WARP_STAGING + d * 4096, &tmOut, &my_lbar[d], n_blk * BN + d * 32, row0e);
+          }
+        }
+        __syncwarp();
+      }
 
       ok = mbar_wait(&tmem_full_bar[as], aphase, p.status, JCB_DEV_TIMEOUT_EPILOGUE);
       ok = __all_sync(0xffffffffu, ok);
@@ -233,7 +286,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       tc_fence_after();
 
       const int row0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;  // this warp's 32 rows
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + col0);
       if (EPI == EPI_PATCH_F32) {
         // conv1 output rows scatter to token rows 1..T-1 of each view (+ positional embedding): direct stores
         const int row = row0 + lane;
@@ -262,14 +315,114 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             }
           }
         }
+      } else if (is_lnprep(EPI)) {
+        // Residual epilogue that prepares the next LayerNorm: new = old + acc + bias.  The old residual chunk
+        // arrives by TMA load in the swizzled staging buffer (requested D chunks ahead), is updated in place and
+        // leaves by TMA store; the same pass emits the bf16 copy the next GEMM consumes as its A operand and this
+        // thread's (= this row's) partial sum / sum of squares over the tile's BN columns.
+        constexpr int NB = lnprep_nb(EPI), D = lnprep_d(EPI), NH = lnprep_nh(EPI);
+        constexpr int NCH = BN / 32;
+        uint8_t* my_stage = staging + ew * WARP_STAGING;
+        uint8_t* my_half = my_stage + NB * 4096;   // bf16 chunk buffers (64 columns each)
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(taddr, v[0]);
+        float rs = 0.f, rq = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t(&cur)[32] = v[c & 1];
+          constexpr int WAITN = NB - D - 1;
+          if (c >= 1) {
+            // stores issued up to chunk c - 1 - WAITN have released their buffers: frees the fp32 buffer the next
+            // prefetch lands in and the bf16 buffer this chunk (pair) writes
+            if (lane == 0) bulk_wait_read<WAITN>();
+            __syncwarp();
+          }
+          if (c + D < NCH && lane == 0) {
+            const int nb = (c + D) % NB;
+            mbar_arrive_expect_tx(&my_lbar[nb], 4096);
+            tma_load_2d(my_stage + nb * 4096, &tmOut, &my_lbar[nb], n_blk * BN + (c + D) * 32, row0);
+          }
+          float bb[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * j);
+            bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+          }
+          tmem_ld_wait();
+          if (c + 1 < NCH) {
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>((c + 1) * 32), v[(c + 1) & 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8));
+              else mbar_arrive(&tmem_empty_bar[as]);
+            }
+          }
+          const int b = c % NB;
+          ok = mbar_wait(&my_lbar[b], (lphase >> b) & 1u, p.status, JCB_DEV_TIMEOUT_EPILOGUE);   // old chunk landed
+          lphase ^= 1u << b;
+          uint8_t* rowp = my_stage + b * 4096 + lane * 128;
+          uint8_t* halfp = my_half + ((c >> 1) % NH) * 4096 + lane * 128;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {   // 8 columns = two 16-byte fp32 pieces -> one 16-byte bf16 piece
+            float f[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = 2 * jj + h;
+              float4* piece = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
+              float4 o = *piece;
+              o.x += __uint_as_float(cur[4 * j + 0]) + bb[4 * j + 0];
+              o.y += __uint_as_float(cur[4 * j + 1]) + bb[4 * j + 1];
+              o.z += __uint_as_float(cur[4 * j + 2]) + bb[4 * j + 2];
+              o.w += __uint_as_float(cur[4 * j + 3]) + bb[4 * j + 3];
+              *piece = o;
+              f[4 * h + 0] = o.x; f[4 * h + 1] = o.y; f[4 * h + 2] = o.z; f[4 * h + 3] = o.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { rs += f[e]; rq = fmaf(f[e], f[e], rq); }
+            uint4 hb;
+            hb.x = pack_bf16x2(f[0], f[1]); hb.y = pack_bf16x2(f[2], f[3]);
+            hb.z = pack_bf16x2(f[4], f[5]); hb.w = pack_bf16x2(f[6], f[7]);
+            const int hp = (c & 1) * 4 + jj;   // piece of the 128-byte bf16 row (64 columns = two fp32 chunks)
+            *reinterpret_cast<uint4*>(halfp + ((hp ^ (lane & 7)) << 4)) = hb;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, my_stage + b * 4096, n_blk * BN + c * 32, row0);
+            if (c & 1) tma_store_2d(&tmOut2, my_half + ((c >> 1) % NH) * 4096, n_blk * BN + (c - 1) * 32, row0);
+            bulk_commit();
+          }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (row0 + lane < p.M)
+          *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(row0 + lane) * p.stats_slots + n_blk) * 2) =
+              make_float2(rs, rq);
       } else {
         // TMEM -> registers -> (+bias, activation, rounding) -> 128B-swizzled smem chunk of 32 rows x 128 B ->
         // one TMA store (or fp32 reduce-add for the residual epilogues) per chunk: fully coalesced, asynchronous,
         // and the residual stream is never read into the SM.  Rows >= M are clipped by the tensor map.
-        constexpr bool OUT_BF16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16;
+        constexpr bool OUT_BF16 = out_is_bf16(EPI);
+        constexpr bool FOLD = is_lnfold(EPI);
+        constexpr bool GELU = EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LNFOLD_GELU_BF16;
         constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;
-        constexpr int NCH = BN / CHUNK_COLS;
-        uint8_t* my_stage = staging + q * WARP_STAGING;
+        constexpr int NCH = CW / CHUNK_COLS;
+        uint8_t* my_stage = staging + ew * WARP_STAGING;
+        // LayerNorm folded into this GEMM: this thread's row statistics from the producer's partial sums
+        float ln_r = 1.f, ln_nmr = 0.f;
+        if (FOLD) {
+          float su = 0.f, sq = 0.f;
+          if (row0 + lane < p.M) {
+            const float2* st = reinterpret_cast<const float2*>(p.stats) + static_cast<long long>(row0 + lane) * p.stats_slots;
+            for (int i = 0; i < p.stats_slots; ++i) { const float2 t2 = __ldg(st + i); su += t2.x; sq += t2.y; }
+          }
+          const float inv_k = 1.0f / static_cast<float>(p.K);
+          const float mean = su * inv_k;
+          const float var = fmaxf(fmaf(sq, inv_k, -mean * mean), 0.f);   // E[x^2] - E[x]^2 (as Jittor computes it), clamped
+          ln_r = 1.0f / sqrtf(var + 1e-5f);
+          ln_nmr = -mean * ln_r;
+        }
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted; the smem
         // staging holds GROUP chunks so the generic->async proxy fence (MEMBAR + ERRBAR, ~17 % of all
         // stall samples when issued per chunk) and the TMA issue happen once per GROUP chunks
@@ -290,6 +443,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           for (int j = 0; j < CHUNK_COLS / 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * CHUNK_COLS + 4 * j);
             bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+            if (FOLD) {   // c[n] - r mu S[n]: the per-row, per-column additive term of the folded LayerNorm
+              const float4 s4 = *reinterpret_cast<const float4*>(s_csum + c * CHUNK_COLS + 4 * j);
+              bb[4 * j] = fmaf(ln_nmr, s4.x, bb[4 * j]); bb[4 * j + 1] = fmaf(ln_nmr, s4.y, bb[4 * j + 1]);
+              bb[4 * j + 2] = fmaf(ln_nmr, s4.z, bb[4 * j + 2]); bb[4 * j + 3] = fmaf(ln_nmr, s4.w, bb[4 * j + 3]);
+            }
           }
           if (c % GROUP == 0) {
             // the TMA stores of the previous group must have finished READING the staging buffers
@@ -317,8 +475,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                f[e] = __uint_as_float(cur[8 * j + e]) + bb[8 * j + e];
-                if (EPI == EPI_BIAS_GELU_BF16) f[e] = quick_gelu(f[e]);
+                f[e] = FOLD ? fmaf(__uint_as_float(cur[8 * j + e]), ln_r, bb[8 * j + e])
+                            : __uint_as_float(cur[8 * j + e]) + bb[8 * j + e];
+                if (GELU) f[e] = quick_gelu(f[e]);
               }
               o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
               o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
@@ -338,8 +497,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
               for (int g = c - (c % GROUP); g <= c; ++g) {
                 const uint8_t* src = my_stage + (g % GROUP) * 4096;
-                if (EPI == EPI_BIAS_RESID_F32) tma_reduce_add_2d(&tmOut, src, n_blk * BN + g * CHUNK_COLS, row0);
-                else tma_store_2d(&tmOut, src, n_blk * BN + g * CHUNK_COLS, row0);
+                if (EPI == EPI_BIAS_RESID_F32) tma_reduce_add_2d(&tmOut, src, n_blk * BN + col0 + g * CHUNK_COLS, row0);
+                else tma_store_2d(&tmOut, src, n_blk * BN + col0 + g * CHUNK_COLS, row0);
               }
               (void)G0;
               bulk_commit();
@@ -369,17 +528,19 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * epi_warps_of(EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmOut, const GemmDev p) {
-  gemm_body<BN, EPI, 1>(tmA, tmB, tmOut, p);
+                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                         const GemmDev p) {
+  gemm_body<BN, EPI, 1>(tmA, tmB, tmOut, tmOut2, p);
 }
 
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * epi_warps_of(EPI), 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                              const __grid_constant__ CUtensorMap tmOut, const GemmDev p) {
-  gemm_body<BN, EPI, 2>(tmA, tmB, tmOut, p);
+                              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                              const GemmDev p) {
+  gemm_body<BN, EPI, 2>(tmA, tmB, tmOut, tmOut2, p);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
@@ -407,12 +568,19 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   CUtensorMap tmA, tmB, tmOut;
   if (!make_tmap_2d(&tmA, true, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&tmB, true, a.B, a.N, a.K, a.ldb, Cfg::B_ROWS, BLOCK_K)) return cudaErrorInvalidValue;
-  constexpr bool OUT_BF16 = EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16;
+  constexpr bool OUT_BF16 = out_is_bf16(EPI);
+  CUtensorMap tmOut2;
   if (EPI == EPI_PATCH_F32) {
     tmOut = tmA;  // unused by the scatter epilogue
   } else if (!make_tmap_2d(&tmOut, OUT_BF16, a.out, a.M, a.N, a.ldo, 32, OUT_BF16 ? 64 : 32)) {
     return cudaErrorInvalidValue;
   }
+  tmOut2 = tmOut;
+  if (is_lnprep(EPI)) {
+    if (!a.out2 || !a.stats || a.stats_slots < a.N / BN) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmOut2, true, a.out2, a.M, a.N, a.ldo2, 32, 64)) return cudaErrorInvalidValue;
+  }
+  if (is_lnfold(EPI) && (!a.stats || !a.colsum || a.stats_slots < 1)) return cudaErrorInvalidValue;
   auto kern = CTAS == 2 ? gemm_bf16_tcgen05_2cta_kernel<BN, EPI> : gemm_bf16_tcgen05_kernel<BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -424,11 +592,12 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.pos = a.pos;
   p.tokens_in = a.tokens_in; p.tokens_out = a.tokens_out; p.status = dev_status;
+  p.stats = a.stats; p.stats_slots = a.stats_slots; p.colsum = a.colsum;
   const int tile_m = BLOCK_M * CTAS;
   const int tiles = ((a.M + tile_m - 1) / tile_m) * (a.N / BN);
   const int units = num_sms / CTAS;                       // CTAs or CTA pairs that fit the chip
   const int grid = (tiles < units ? tiles : units) * CTAS;
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, p);
+  kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, p);
   return cudaGetLastError();
 }
 
@@ -440,6 +609,10 @@ cudaError_t launch_bn(const GemmArgs& a, int* st, int sms, cudaStream_t s) {
     case EPI_BIAS_RESID_F32: return launch_cfg<BN, EPI_BIAS_RESID_F32, CTAS>(a, st, sms, s);
     case EPI_PATCH_F32: return launch_cfg<BN, EPI_PATCH_F32, CTAS>(a, st, sms, s);
     case EPI_F32: return launch_cfg<BN, EPI_F32, CTAS>(a, st, sms, s);
+    case EPI_LNFOLD_BF16: return launch_cfg<BN, EPI_LNFOLD_BF16, CTAS>(a, st, sms, s);
+    case EPI_LNFOLD_GELU_BF16: return launch_cfg<BN, EPI_LNFOLD_GELU_BF16, CTAS>(a, st, sms, s);
+    case EPI_RESID_LNPREP_SHORT: return launch_cfg<BN, EPI_RESID_LNPREP_SHORT, CTAS>(a, st, sms, s);
+    case EPI_RESID_LNPREP_LONG: return launch_cfg<BN, EPI_RESID_LNPREP_LONG, CTAS>(a, st, sms, s);
     default: return cudaErrorInvalidValue;
   }
 }

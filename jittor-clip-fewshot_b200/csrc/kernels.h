@@ -15,6 +15,15 @@ enum GemmEpilogue : int {
   EPI_BIAS_RESID_F32 = 2,  // out_f32[m,n]  += acc + bias[n]                       (out_proj / c_proj + residual)
   EPI_PATCH_F32 = 3,       // out_f32[row(m),n] = acc + pos[1 + m % T_in, n], row(m) = (m / T_in) * T_out + 1 + m % T_in
   EPI_F32 = 4,             // out_f32[m,n]   = acc (+ bias[n] if given)            (tests / generic)
+  // ---- LayerNorm folded into the GEMMs (no stand-alone LayerNorm pass over the residual stream) ----
+  // LN(x) W^T = r (x (g*W)^T) - r mu S + c  with  S[n] = sum_k g[k] W[n,k],  c[n] = sum_k b[k] W[n,k] + bias[n]:
+  // the consumer GEMM multiplies the RAW bf16 copy of the residual stream by the gamma-folded weight and applies
+  // the per-row (mu, r) in its epilogue; the producer GEMM (a residual epilogue) writes that bf16 copy and the
+  // per-row partial sums next to the fp32 residual.
+  EPI_LNFOLD_BF16 = 5,       // out_bf16[m,n] = r[m] * acc - r[m] * mu[m] * colsum[n] + bias[n]          (QKV)
+  EPI_LNFOLD_GELU_BF16 = 6,  // out_bf16[m,n] = quickgelu(that)                                        (MLP c_fc)
+  EPI_RESID_LNPREP_SHORT = 7,  // out_f32 += acc + bias; out2_bf16 = bf16(out_f32); stats[m, n_blk] = (sum, sumsq)
+  EPI_RESID_LNPREP_LONG = 8,   // same; staging / ring split tuned for long K (c_proj) instead of HBM-bound short K (out_proj)
 };
 
 struct GemmArgs {
@@ -28,6 +37,11 @@ struct GemmArgs {
   int64_t ldo = 0;
   const float* pos = nullptr;        // EPI_PATCH_F32: positional embedding [T_out, N]
   int tokens_in = 49, tokens_out = 50;
+  float* stats = nullptr;            // LNFOLD: in, LNPREP: out.  [M, stats_slots, 2] fp32 partial (sum, sum of squares)
+  int stats_slots = 0;               // partial slots per row (= N / 256 of the producer; the consumer adds them up)
+  const float* colsum = nullptr;     // LNFOLD: S[N]
+  void* out2 = nullptr;              // LNPREP: bf16 copy of the updated residual [M, N]
+  int64_t ldo2 = 0;
 };
 
 // Persistent TMA + tcgen05 GEMM.  Requires N % 128 == 0 and K % 64 == 0 (every GEMM of the ViT-B/32
@@ -47,7 +61,8 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
 // then x := ln_pre(x) written back in place (the residual stream), and y := ln_1(x) as bf16.
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
                             const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
-                            const float* b1, __nv_bfloat16* y, cudaStream_t stream);
+                            const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats = nullptr,
+                            int stats_slots = 0);   // stats != nullptr: y = bf16(x) raw + (sum, sumsq) for EPI_LNFOLD_*
 // y_bf16[r,:] = LayerNorm(x_f32[r,:]) * g + b   (eps 1e-5, biased variance), W == 768 or any W % 128 == 0 <= 1024
 cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
                              __nv_bfloat16* y, cudaStream_t stream);
@@ -60,7 +75,7 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
 // stream), y = ln_1(x) as bf16, and eot[s] = argmax_t ids[s, t] (first maximum; model.py:213-214)
 cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
                                  const float* pos, const float* g1, const float* b1, float* tokens, __nv_bfloat16* y,
-                                 int* eot, cudaStream_t stream);
+                                 int* eot, cudaStream_t stream, float* stats = nullptr, int stats_slots = 0);
 // qkv [B*T, 3W] bf16 (q | k | v, heads = 64-wide column blocks) -> out [B*T, W] bf16
 // causal != 0: key j is visible to query i only if j <= i (text tower); T <= 80
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
@@ -70,6 +85,12 @@ cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cu
 // W'[rows, cols] (bf16) = W (fp32) + scaling * B[rows, r] @ A[r, cols]   for a row range of a packed weight
 cudaError_t launch_merge_lora_cast(const float* W, const float* A, const float* B, int rows, int cols, int r,
                                    float scaling, __nv_bfloat16* dst, cudaStream_t stream);
+
+// in place W (fp32) += scaling * B A; and the LayerNorm fold of a weight (see EPI_LNFOLD_* above)
+cudaError_t launch_merge_lora_f32(float* W, const float* A, const float* B, int rows, int cols, int r, float scaling,
+                                  cudaStream_t stream);
+cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+                           __nv_bfloat16* Wf, float* S, float* c, cudaStream_t stream);
 
 // ---- MTA + head --------------------------------------------------------------------------------
 struct MtaParams {

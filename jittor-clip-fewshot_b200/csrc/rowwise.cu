@@ -115,6 +115,23 @@ __device__ __forceinline__ void store_row_bf16(const float4 (&v)[NV], __nv_bfloa
 
 constexpr int LN_WARPS = 8;
 
+// what a residual GEMM epilogue with EPI_RESID_LNPREP_* leaves behind, for the first block of a tower:
+// y = bf16(x) and stats[0] = (sum x, sum x^2), stats[1..slots) = 0
+template <int NV>
+__device__ __forceinline__ void emit_raw_and_stats(const float4 (&v)[NV], __nv_bfloat16* __restrict__ y,
+                                                   float* __restrict__ st, int slots, int lane) {
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  store_row_bf16<NV>(v, y, lane);
+  if (lane < 2 * slots) st[lane] = lane == 0 ? s : (lane == 1 ? q : 0.f);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const float* __restrict__ x, long long rows, const float* __restrict__ g,
@@ -138,7 +155,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* __restrict__ cls,
                 const float* __restrict__ pos, const float* __restrict__ vpt, int n_vpt,
                 const float* __restrict__ g_pre, const float* __restrict__ b_pre,
-                const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y) {
+                const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y,
+                float* __restrict__ stats, int stats_slots) {
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -168,6 +186,10 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
   normalize_row<NV>(v, mean, rstd, g_pre, b_pre, lane);  // ln_pre -> residual stream
 #pragma unroll
   for (int i = 0; i < NV; ++i) xr[lane + 32 * i] = v[i];
+  if (stats != nullptr) {   // LayerNorm folded into the consuming GEMM: raw bf16 copy + (sum, sum of squares)
+    emit_raw_and_stats<NV>(v, y + row * W, stats + row * stats_slots * 2, stats_slots, lane);
+    return;
+  }
   row_stats<NV>(v, W, mean, rstd);
   normalize_row<NV>(v, mean, rstd, g1, b1, lane);        // layer 0's ln_1
   store_row_bf16<NV>(v, y + row * W, lane);
@@ -179,7 +201,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, int vocab,
                      const float* __restrict__ tok_emb, const float* __restrict__ pos, const float* __restrict__ g1,
                      const float* __restrict__ b1, float* __restrict__ tokens, __nv_bfloat16* __restrict__ y,
-                     int* __restrict__ eot) {
+                     int* __restrict__ eot, float* __restrict__ stats, int stats_slots) {
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -197,10 +219,14 @@ text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, i
   float4* xr = reinterpret_cast<float4*>(tokens + row * W);
 #pragma unroll
   for (int i = 0; i < NV; ++i) xr[lane + 32 * i] = v[i];
-  float mean, rstd;
-  row_stats<NV>(v, W, mean, rstd);
-  normalize_row<NV>(v, mean, rstd, g1, b1, lane);
-  store_row_bf16<NV>(v, y + row * W, lane);
+  if (stats != nullptr) {
+    emit_raw_and_stats<NV>(v, y + row * W, stats + row * stats_slots * 2, stats_slots, lane);
+  } else {
+    float mean, rstd;
+    row_stats<NV>(v, W, mean, rstd);
+    normalize_row<NV>(v, mean, rstd, g1, b1, lane);
+    store_row_bf16<NV>(v, y + row * W, lane);
+  }
   if (t == 0) {  // the warp of a sequence's first token also finds its EOT position: first maximum of the ids
     long long best = -1;
     int best_t = 0;
@@ -313,7 +339,56 @@ __global__ void merge_lora_cast_kernel(const float* __restrict__ W, const float*
   dst[i] = __float2bfloat16_rn(W[i] + scaling * d);
 }
 
+// in place: W[rows, cols] (fp32) += scaling * B[rows, r] @ A[r, cols]
+__global__ void merge_lora_f32_kernel(float* __restrict__ W, const float* __restrict__ A, const float* __restrict__ B,
+                                      int rows, int cols, int r, float scaling) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int o = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  float d = 0.f;
+  for (int k = 0; k < r; ++k) d = fmaf(B[o * r + k], A[k * cols + c], d);
+  W[i] += scaling * d;
+}
+
+// LayerNorm folded into the consuming GEMM (kernels.h EPI_LNFOLD_*): one warp per output row n of W [N, K]
+//   Wf[n, k] = bf16(gamma[k] * W[n, k]);  S[n] = sum_k float(Wf[n, k]);  c[n] = sum_k beta[k] * W[n, k] + bias[n]
+// S is the sum of the ROUNDED folded weights, i.e. exactly what the tensor core will multiply the row mean by.
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, int N, int K, __nv_bfloat16* __restrict__ Wf, float* __restrict__ S,
+               float* __restrict__ c) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float s = 0.f, cc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<long long>(n) * K + k];
+    const __nv_bfloat16 wf = __float2bfloat16_rn(gamma[k] * w);
+    Wf[static_cast<long long>(n) * K + k] = wf;
+    s += __bfloat162float(wf);
+    cc = fmaf(beta[k], w, cc);
+  }
+  s = warp_sum(s);
+  cc = warp_sum(cc);
+  if (lane == 0) { S[n] = s; c[n] = cc + bias[n]; }
+}
+
 }  // namespace
+
+cudaError_t launch_merge_lora_f32(float* W, const float* A, const float* B, int rows, int cols, int r, float scaling,
+                                  cudaStream_t stream) {
+  const long long n = static_cast<long long>(rows) * cols;
+  if (n == 0) return cudaSuccess;
+  merge_lora_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(W, A, B, rows, cols, r, scaling);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+                           __nv_bfloat16* Wf, float* S, float* c, cudaStream_t stream) {
+  if (N == 0) return cudaSuccess;
+  fold_ln_kernel<<<static_cast<unsigned>((N + 7) / 8), 256, 0, stream>>>(W, gamma, beta, bias, N, K, Wf, S, c);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
                           int apply_norm, __nv_bfloat16* patches, cudaStream_t stream) {
@@ -351,13 +426,14 @@ cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g
 
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
                             const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
-                            const float* b1, __nv_bfloat16* y, cudaStream_t stream) {
+                            const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats, int stats_slots) {
   if (W % 128 != 0) return cudaErrorInvalidValue;
   const long long rows = n_views * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   JCB_DISPATCH_NV(W, (embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(tokens, rows, T, cls, pos, vpt,
-                                                                           n_vpt, g_pre, b_pre, g1, b1, y)));
+                                                                           n_vpt, g_pre, b_pre, g1, b1, y, stats,
+                                                                           stats_slots)));
   return cudaGetLastError();
 }
 
@@ -373,13 +449,13 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
 
 cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
                                  const float* pos, const float* g1, const float* b1, float* tokens, __nv_bfloat16* y,
-                                 int* eot, cudaStream_t stream) {
+                                 int* eot, cudaStream_t stream, float* stats, int stats_slots) {
   if (W % 128 != 0 || T < 1 || vocab < 1) return cudaErrorInvalidValue;
   const long long rows = n_seq * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   JCB_DISPATCH_NV(W, (text_embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(ids, rows, T, vocab, tok_emb, pos,
-                                                                                g1, b1, tokens, y, eot)));
+                                                                                g1, b1, tokens, y, eot, stats, stats_slots)));
   return cudaGetLastError();
 }
 
