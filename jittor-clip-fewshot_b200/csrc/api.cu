@@ -311,7 +311,7 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
       if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, nullptr,
                          49, 50, w.stats, slots, L.in_S))) return rc;
       LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
-               launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal));
+               launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms));
       if (fold2) {
         if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens, W, nullptr,
                            49, 50, w.stats, slots, nullptr, w.ln_out))) return rc;
@@ -335,7 +335,7 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
     const LayerDev& L = t->layers[l];
     if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
     LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
-             launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal));
+             launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms));
     if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
     LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
     if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
@@ -1187,7 +1187,7 @@ int jcb_attention_bf16(jcb_ctx* ctx, const void* qkv, int64_t n_views, int32_t t
   if (!qkv || !out) return fail(ctx, JCB_E_INVALID, "jcb_attention_bf16: null pointer");
   DeviceGuard g(ctx->device);
   LAUNCH(ctx, launch_attention(static_cast<const __nv_bfloat16*>(qkv), n_views, tokens, heads,
-                               static_cast<__nv_bfloat16*>(out), ctx->stream));
+                               static_cast<__nv_bfloat16*>(out), ctx->stream, 0, ctx->dev_status, ctx->num_sms));
   return JCB_OK;
 }
 

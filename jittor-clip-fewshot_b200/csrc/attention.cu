@@ -216,9 +216,16 @@ cudaError_t launch_attention_cfg(const __nv_bfloat16* qkv, int64_t n_views, int 
 }  // namespace
 
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream, int causal) {
+                             cudaStream_t stream, int causal, int* dev_status, int num_sms) {
   if (T < 1 || T > 80 || heads < 1) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
+  static int impl = -1;  // 1: tcgen05 kernel where the shape allows it (default), 0: mma.sync kernel everywhere
+  if (impl < 0) {
+    const char* env = getenv("JCB_ATT_IMPL");
+    impl = (env && env[0] == 'm') ? 0 : 1;
+  }
+  if (impl == 1 && dev_status != nullptr && num_sms > 0 && attention_tc_supported(T, heads, causal))
+    return launch_attention_tc(qkv, n_views, T, heads, out, stream, dev_status, num_sms);
   if (causal) return launch_attention_cfg<1, 1, 80, true>(qkv, n_views, T, heads, out, stream);  // text tower
   if (T > 64) return launch_attention_cfg<1, 1, 80, false>(qkv, n_views, T, heads, out, stream);
   static int cfg = 0;  // heads per CTA * 10 + query tiles per warp

@@ -619,6 +619,8 @@ cudaError_t launch_bn(const GemmArgs& a, int* st, int sms, cudaStream_t s) {
 
 }  // namespace
 
+void* gemm_encode_tiled_fn() { return reinterpret_cast<void*>(g_encode_tiled); }
+
 const char* gemm_init_driver_api() {
   if (g_encode_tiled) return nullptr;
   void* fn = nullptr;

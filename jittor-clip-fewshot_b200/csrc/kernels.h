@@ -78,8 +78,13 @@ cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int
                                  int* eot, cudaStream_t stream, float* stats = nullptr, int stats_slots = 0);
 // qkv [B*T, 3W] bf16 (q | k | v, heads = 64-wide column blocks) -> out [B*T, W] bf16
 // causal != 0: key j is visible to query i only if j <= i (text tower); T <= 80
+// dev_status + num_sms given: the tcgen05 / TMEM kernel (attention_tc.cu) runs when the shape allows it (no mask,
+// T <= 64, even head count; JCB_ATT_IMPL=mma forces the mma.sync kernel); otherwise the mma.sync kernel (attention.cu)
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream, int causal = 0);
+                             cudaStream_t stream, int causal = 0, int* dev_status = nullptr, int num_sms = 0);
+bool attention_tc_supported(int T, int heads, int causal);
+cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                                cudaStream_t stream, int* dev_status, int num_sms);
 // fp32 -> bf16 cast (weight packing)
 cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
 // W'[rows, cols] (bf16) = W (fp32) + scaling * B[rows, r] @ A[r, cols]   for a row range of a packed weight

@@ -6,7 +6,7 @@ Tolerances (written here, used below):
   GEMM, fp32 out :  |d| <= 2e-3 * sqrt(K/768) + 1e-3 * |ref|      (fp32 accumulate, different order)
   GEMM, bf16 out :  one bf16 ulp of the result (2^-8 relative) on top of the above
   LayerNorm bf16 :  2^-8 relative + 1e-3 absolute
-  attention bf16 :  P is rounded to bf16 before P V (as flash-style kernels do): 1e-2 absolute on O(1) values
+  attention bf16 :  P is rounded to bf16 before P V (as flash-style kernels do): 1e-2 absolute + 2^-8 relative
 """
 import math
 
@@ -135,11 +135,14 @@ def test_layernorm(jb, cuda_dev, rows):
     assert ((y.float().cpu() - ref).abs() <= 1e-3 + 2 ** -8 * ref.abs()).all()
 
 
-@pytest.mark.parametrize("n_views,T", [(1, 50), (3, 50), (64, 50), (5, 54), (2, 64), (2, 17)])
-def test_attention(jb, cuda_dev, n_views, T):
+@pytest.mark.parametrize("n_views,T,H", [(1, 50, 12), (3, 50, 12), (64, 50, 12), (5, 54, 12), (2, 64, 12), (2, 17, 12),
+                                         (1, 1, 2), (700, 50, 12), (333, 54, 8), (9, 50, 3)])
+def test_attention(jb, cuda_dev, n_views, T, H):
+    # T <= 64 with an even head count runs the tcgen05 / TMEM kernel (several work items per persistent CTA at
+    # 700 x 6 head pairs); H = 3 falls back to the mma.sync kernel
     from ctypes import c_void_p
     g = torch.Generator().manual_seed(n_views * 100 + T)
-    H, d = 12, 64
+    d = 64
     W = H * d
     qkv = (torch.randn(n_views * T, 3 * W, generator=g) * 1.2).to(torch.bfloat16).to(cuda_dev)
     out = torch.empty(n_views * T, W, dtype=torch.bfloat16, device=cuda_dev)
@@ -151,4 +154,5 @@ def test_attention(jb, cuda_dev, n_views, T):
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     att = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(d), dim=-1)       # jclip/mha.py:55-83
     ref = (att @ v).permute(0, 2, 1, 3).reshape(n_views * T, W)
-    assert (out.float() - ref).abs().max() <= 1e-2
+    # 1e-2 absolute (P rounded to bf16) + one bf16 ulp of the output itself (2^-8 relative)
+    assert ((out.float() - ref).abs() <= 1e-2 + 2.0 ** -8 * ref.abs()).all()
