@@ -10,8 +10,9 @@ One "step" = one pass of the whole hot path over `--images-per-gpu` images x 65 
 (weak scaling: per-GPU work is fixed).  Rank 0 prints ONE JSON line:
 
   value      images/s, whole job, inputs resident in HBM (device pointers into jcb_pipeline)
-  e2e        the same through HotPath.evaluate_base with PINNED HOST images: host->device copies of
-             the view chunks and the device->host read of the top-5 are inside the timed region
+  e2e        the same through HotPath.evaluate_stream with PINNED HOST images (two batches in flight): the
+             host->device copies of every step's view chunks and the device->host read of its top-5 are inside
+             the timed region; `blocking_call` is one HotPath.evaluate_base call per step
   roofline   the tcgen05 GEMM family (99 % of the FLOPs): algorithmic FLOPs / CUDA-event time of its
              launches, recorded on the launch stream inside the timed region, vs the measured bf16 peak
   cpu_baseline  the fp32 CPU oracle (a port: the reference needs Jittor, which is not installable) on a
@@ -245,6 +246,7 @@ def main():
         for _ in range(max(W, 1)):
             tk = hp.evaluate_base(host_images)
         assert not tk.is_cuda and torch.equal(tk, out[rank * I:(rank + 1) * I].cpu())
+        # (a) one blocking call per step: nothing hides the first upload of a step or the final read
         jb.dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -252,9 +254,26 @@ def main():
             tk = hp.evaluate_base(host_images)
             jb.dist.all_gather_topk(tk.to(dev), n_total)
         torch.cuda.synchronize()
+        dt_block = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
+        # (b) the streaming form of the same call (HotPath.evaluate_stream, the reference's `for images in loader`
+        #     loop): batch k+1 is submitted before batch k is collected, so its uploads overlap k's compute.  Every
+        #     step still copies its own views from pinned host memory and reads its own top-5 back to the host.
+        for tk2 in hp.evaluate_stream(host_images for _ in range(2)):
+            assert torch.equal(tk2, tk)
+        jb.dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for tk2 in hp.evaluate_stream(host_images for _ in range(K)):
+            # stream-ordered (a blocking .to() would make the host wait for the batch submitted after this one)
+            jb.dist.all_gather_topk(tk2.to(dev, non_blocking=True), n_total)
+        torch.cuda.synchronize()
         dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
+        assert torch.equal(tk2, tk)
         e2e = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
-               "h2d_bytes_per_step": int(images.numel() * images.element_size()), "d2h_bytes_per_step": int(I * 5 * 4)}
+               "h2d_bytes_per_step": int(images.numel() * images.element_size()), "d2h_bytes_per_step": int(I * 5 * 4),
+               "api": "HotPath.evaluate_stream(batches, depth=2): pinned host views in, host top-5 out, two batches in flight",
+               "blocking_call": {"value": n_total * K / dt_block, "ms_per_step": 1e3 * dt_block / K,
+                                 "api": "HotPath.evaluate_base(host_views), one blocking call per step"}}
         del host_images
     # ---- informational: the same step fed from DECODED IMAGES: crop boxes drawn on the host, one upload of the
     #      source image per image, views generated on the GPU (TTAViews, Pillow-exact), then the hot path

@@ -35,7 +35,7 @@ extern "C" {
 #define JCB_E_KERNEL (-5)      /* a kernel reported a device-side status (pipeline timeout) */
 #define JCB_E_NOMEM (-6)
 
-#define JCB_ABI_VERSION 1
+#define JCB_ABI_VERSION 2
 
 typedef struct jcb_ctx jcb_ctx;
 typedef struct jcb_vit jcb_vit;
@@ -285,6 +285,17 @@ typedef struct jcb_pipeline_args {
  * MTA solves.  `vit_zs` may be NULL (single tower) or a second tower for the zero-shot branch
  * (test.py:1711-1713). */
 int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* args);
+
+/* The same for a STREAM of batches (the reference's `for images in loader:` loop, test.py:1692): submit enqueues
+ * everything jcb_pipeline does -- the host->device copies of the view chunks, the tower, MTA, head and, with
+ * topk_on_host, the device->host copy of the top-k -- and returns without waiting; jcb_pipeline_wait blocks until
+ * the submission `ticket` has completed (its out_topk is valid) and reports device-side errors.  Submitting batch
+ * k+1 before waiting for batch k overlaps the uploads of k+1 with the compute of k.  `images` and `out_topk` of a
+ * submission must stay valid and untouched until its wait returns; tickets complete in submission order; at most
+ * JCB_MAX_INFLIGHT submissions may be un-waited (JCB_E_STATE otherwise). */
+#define JCB_MAX_INFLIGHT 4
+int jcb_pipeline_submit(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* args, int64_t* ticket);
+int jcb_pipeline_wait(jcb_ctx* ctx, int64_t ticket);
 
 /* ---------------------------------------------------------------- building blocks (tests) ---- */
 /* C[M,N] = A[M,K] (bf16) * B[N,K]^T (bf16) with the fused epilogues of the tower; see csrc/kernels.h. */

@@ -14,7 +14,8 @@ LIB_PATH = PKG_DIR / "libjclip_b200.so"
 
 JCB_OK = 0
 JCB_E_INVALID, JCB_E_CUDA, JCB_E_STATE, JCB_E_NO_DEVICE, JCB_E_KERNEL, JCB_E_NOMEM = -1, -2, -3, -4, -5, -6
-JCB_ABI_VERSION = 1
+JCB_ABI_VERSION = 2
+MAX_INFLIGHT = 4   # JCB_MAX_INFLIGHT
 IMG_F32, IMG_BF16, IMG_U8 = 0, 1, 2
 PROJ_Q, PROJ_K, PROJ_V, PROJ_O = 0, 1, 2, 3
 SCORE_NAMES = ("logits", "cs", "cs1", "cs2", "cs3", "cs4", "cs5")
@@ -114,6 +115,8 @@ PROTOTYPES = {
     "jcb_channel_lp": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, POINTER(HeadWeights), c_void_p]),
     "jcb_logit_normalize": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "jcb_pipeline": (c_int, [c_void_p, c_void_p, POINTER(PipelineArgs)]),
+    "jcb_pipeline_submit": (c_int, [c_void_p, c_void_p, POINTER(PipelineArgs), POINTER(c_int64)]),
+    "jcb_pipeline_wait": (c_int, [c_void_p, c_int64]),
     "jcb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32,
                               c_void_p, c_int64]),
     "jcb_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -30,6 +30,13 @@ struct jcb_ctx {
   size_t ws_bytes = 0;
   void* stage[2] = {nullptr, nullptr};  // device staging for host images
   size_t stage_bytes = 0;
+  int64_t stage_seq = 0;             // staging uses so far (buffer = seq & 1): persists ACROSS calls, so a call that
+  bool stage_recorded[2] = {false, false};  // starts while the previous one still computes cannot overwrite its input
+  // asynchronous submissions (jcb_pipeline_submit / jcb_pipeline_wait)
+  cudaEvent_t ticket_done[JCB_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
+  int* ticket_status = nullptr;      // pinned host, [JCB_MAX_INFLIGHT]: device status word copied behind each submission
+  int64_t next_ticket = 0, waited_ticket = 0;
+  bool overlapped = false;           // this submission was enqueued behind an un-waited one: its first upload is hidden
   int64_t launches = 0;
   int ln_fold = 1;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
                                      // 0 none, 1 ln_1 only (c_proj -> QKV), 2 ln_1 and ln_2
@@ -133,6 +140,7 @@ int stage_reserve(jcb_ctx* ctx, size_t bytes) {
     if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for image staging failed: %s", bytes, cudaGetErrorString(e));
   }
   ctx->stage_bytes = bytes;
+  ctx->stage_recorded[0] = ctx->stage_recorded[1] = false;
   return JCB_OK;
 }
 
@@ -369,6 +377,13 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   return tower_blocks(v, n, w, 0);
 }
 
+// Views per pass through the tower.  Host input of a blocking call is cut into small passes so that the upload of
+// pass i+1 hides behind the compute of pass i; a submission queued behind a running one (jcb_pipeline_submit) hides
+// its WHOLE upload behind that one's compute and keeps the large, more efficient passes of device-resident input.
+int64_t views_bound(const jcb_ctx* ctx, bool on_host) {
+  return (on_host && !ctx->overlapped) ? std::min(ctx->host_chunk_views, ctx->chunk_views) : ctx->chunk_views;
+}
+
 int64_t balanced_chunk(int64_t n, int64_t bound) {
   if (n <= bound) return n;
   const int64_t passes = (n + bound - 1) / bound;
@@ -392,7 +407,7 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
   if (!images || !out_dev) return fail(ctx, JCB_E_INVALID, "null image / output pointer");
   // balanced chunks: the fewest passes that respect the bound, all (nearly) the same size, so no pass
   // runs the 148 SMs on a sliver of work
-  const int64_t chunk = balanced_chunk(n, on_host ? std::min(ctx->host_chunk_views, ctx->chunk_views) : ctx->chunk_views);
+  const int64_t chunk = balanced_chunk(n, views_bound(ctx, on_host));
   int rc = ws_reserve(ctx, ws_extra + tower_ws_bytes(v, chunk));
   if (rc) return rc;
   Bump b(static_cast<uint8_t*>(ctx->ws) + ws_extra);
@@ -401,15 +416,18 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
   if (on_host && (rc = stage_reserve(ctx, chunk * view_bytes))) return rc;
   // Host input: the upload of pass i+1 overlaps the compute of pass i, but nothing hides the FIRST upload, so
   // the first pass is a quarter of the others (its copy is 4x shorter; it is too short to matter for the GEMMs).
-  const int64_t lead = (on_host && n > chunk) ? std::max<int64_t>(chunk / 4, 1) : 0;
+  // (not needed when the call is queued behind a running submission: that one's compute hides it)
+  const int64_t lead = (on_host && n > chunk && !ctx->overlapped) ? std::max<int64_t>(chunk / 4, 1) : 0;
   const int64_t body = lead ? balanced_chunk(n - lead, chunk) : chunk;
   int64_t ci = 0;
   for (int64_t off = 0; off < n; ++ci) {
     const int64_t m = std::min(ci == 0 && lead ? lead : body, n - off);
     const void* src = static_cast<const uint8_t*>(images) + off * view_bytes;
+    int buf = 0;
     if (on_host) {
-      const int buf = static_cast<int>(ci & 1);
-      if (ci >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[buf], 0));
+      buf = static_cast<int>(ctx->stage_seq++ & 1);
+      // the pass that last read this staging buffer (possibly of the previous, still running call) must be done
+      if (ctx->stage_recorded[buf]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[buf], 0));
       CUDA_TRY(ctx, cudaMemcpyAsync(ctx->stage[buf], src, m * view_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
       CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done[buf], ctx->copy_stream));
       CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[buf], 0));
@@ -419,7 +437,10 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
     LAUNCH_P(ctx, JCB_KC_TAIL, 2.0 * m * v->cfg.width * v->cfg.embed_dim,
              static_cast<double>(m) * (v->cfg.width + v->cfg.embed_dim) * 4, launch_tail(w.tokens, m, v->tokens, v->cfg.width, v->ln_post_g, v->ln_post_b, v->proj,
                             v->cfg.embed_dim, normalize, out_dev + off * v->cfg.embed_dim, ctx->stream));
-    if (on_host) CUDA_TRY(ctx, cudaEventRecord(ctx->compute_done[ci & 1], ctx->stream));
+    if (on_host) {
+      CUDA_TRY(ctx, cudaEventRecord(ctx->compute_done[buf], ctx->stream));
+      ctx->stage_recorded[buf] = true;
+    }
     off += m;
   }
   return JCB_OK;
@@ -470,6 +491,9 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming) == cudaSuccess;
   }
+  for (int i = 0; ok && i < JCB_MAX_INFLIGHT; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->ticket_done[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&ctx->ticket_status), JCB_MAX_INFLIGHT * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->dev_status, sizeof(int)) == cudaSuccess &&
        cudaMemset(ctx->dev_status, 0, sizeof(int)) == cudaSuccess;
   const char* derr = ok ? gemm_init_driver_api() : "context setup failed";
@@ -493,6 +517,9 @@ int jcb_ctx_destroy(jcb_ctx* ctx) {
     if (ctx->compute_done[i]) cudaEventDestroy(ctx->compute_done[i]);
   }
   if (ctx->dev_status) cudaFree(ctx->dev_status);
+  for (int i = 0; i < JCB_MAX_INFLIGHT; ++i)
+    if (ctx->ticket_done[i]) cudaEventDestroy(ctx->ticket_done[i]);
+  if (ctx->ticket_status) cudaFreeHost(ctx->ticket_status);
   for (auto e : ctx->prof_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1107,7 +1134,9 @@ int jcb_logit_normalize(jcb_ctx* ctx, const float* in, int64_t n, int32_t n_clas
 }
 
 // ------------------------------------------------------------------------------------------------
-int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
+namespace {
+// Everything jcb_pipeline does, enqueued on the context's streams without waiting for any of it.
+int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
   int rc = check_vit(vit);
   if (rc) return rc;
   jcb_ctx* ctx = vit->ctx;
@@ -1127,7 +1156,7 @@ int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
   const size_t scratch_b = align_up(mta_scratch_bytes(3 * I, V, C, E));
   const bool own_feats = a->out_feats_dev == nullptr;
   const size_t head_bytes = (own_feats ? feats_b : 0) + (vit_zs ? feats_b : 0) + 3 * modes_b + topk_b + scratch_b;
-  if ((rc = ws_reserve(ctx, head_bytes + tower_ws_bytes(vit, balanced_chunk(NV, a->images_on_host ? std::min(ctx->host_chunk_views, ctx->chunk_views) : ctx->chunk_views))))) return rc;
+  if ((rc = ws_reserve(ctx, head_bytes + tower_ws_bytes(vit, balanced_chunk(NV, views_bound(ctx, a->images_on_host != 0)))))) return rc;
   Bump b(ctx->ws);
   float* feats = own_feats ? b.take<float>(static_cast<size_t>(NV) * E) : a->out_feats_dev;
   float* feats_zs = vit_zs ? b.take<float>(static_cast<size_t>(NV) * E) : feats;
@@ -1155,9 +1184,53 @@ int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
   h.I = I; h.C = C; h.D = E; h.rank_by = a->rank_by; h.k = a->k;
   h.out_topk = topk_dev; h.out_scores = a->out_scores_dev; h.out_all = nullptr;
   LAUNCH_P(ctx, JCB_KC_HEAD, 0, static_cast<double>(I) * (3 * E + a->k) * 4, launch_head(h, ctx->stream));
-  if (a->topk_on_host) {
+  if (a->topk_on_host)
     CUDA_TRY(ctx, cudaMemcpyAsync(a->out_topk, topk_dev, static_cast<size_t>(I) * a->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    return sync_and_check(ctx);
+  return JCB_OK;
+}
+}  // namespace
+
+int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
+  int rc = pipeline_enqueue(vit, vit_zs, a);
+  if (rc) return rc;
+  if (a->n_images > 0 && a->topk_on_host) return sync_and_check(vit->ctx);
+  return JCB_OK;
+}
+
+int jcb_pipeline_submit(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a, int64_t* ticket) {
+  int rc = check_vit(vit);
+  if (rc) return rc;
+  jcb_ctx* ctx = vit->ctx;
+  if (!ticket) return fail(ctx, JCB_E_INVALID, "jcb_pipeline_submit: null ticket");
+  if (ctx->next_ticket - ctx->waited_ticket >= JCB_MAX_INFLIGHT)
+    return fail(ctx, JCB_E_STATE, "jcb_pipeline_submit: %d submissions already in flight; call jcb_pipeline_wait first",
+                JCB_MAX_INFLIGHT);
+  ctx->overlapped = ctx->next_ticket > ctx->waited_ticket;
+  rc = pipeline_enqueue(vit, vit_zs, a);
+  ctx->overlapped = false;
+  if (rc) return rc;
+  DeviceGuard g(ctx->device);
+  const int slot = static_cast<int>(ctx->next_ticket % JCB_MAX_INFLIGHT);
+  // the device status word as of the end of this submission travels to the host behind it: waiting needs no
+  // stream-wide synchronisation (which would also wait for the submissions queued after this one)
+  CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->ticket_status[slot], ctx->dev_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ticket_done[slot], ctx->stream));
+  *ticket = ctx->next_ticket++;
+  return JCB_OK;
+}
+
+int jcb_pipeline_wait(jcb_ctx* ctx, int64_t ticket) {
+  if (!ctx) return JCB_E_INVALID;
+  if (ticket < 0 || ticket >= ctx->next_ticket) return fail(ctx, JCB_E_INVALID, "jcb_pipeline_wait: unknown ticket %lld", static_cast<long long>(ticket));
+  if (ticket < ctx->waited_ticket) return JCB_OK;   // tickets complete in order; this one was covered by a later wait
+  DeviceGuard g(ctx->device);
+  const int slot = static_cast<int>(ticket % JCB_MAX_INFLIGHT);
+  CUDA_TRY(ctx, cudaEventSynchronize(ctx->ticket_done[slot]));
+  ctx->waited_ticket = ticket + 1;
+  const int st = ctx->ticket_status[slot];
+  if (st != 0) {
+    cudaMemsetAsync(ctx->dev_status, 0, sizeof(int), ctx->stream);
+    return fail(ctx, JCB_E_KERNEL, "device-side kernel status %d (101 producer / 102 mma / 103 epilogue pipeline timeout, 104 smem alignment)", st);
   }
   return JCB_OK;
 }

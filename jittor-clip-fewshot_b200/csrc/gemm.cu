@@ -91,6 +91,7 @@ struct GemmDev {
   float* stats;          // LNFOLD: in / LNPREP: out, [M, stats_slots, 2]
   int stats_slots;
   const float* colsum;   // LNFOLD
+  int arrive_release;    // A/B: 1 = the old `.release.cluster` accumulator hand-back
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
@@ -355,7 +356,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (PAIR) mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8));
+              if (PAIR) { if (p.arrive_release) mbar_arrive_cluster_release(empty_addr0 + static_cast<uint32_t>(as * 8)); else mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8)); }
               else mbar_arrive(&tmem_empty_bar[as]);
             }
           }
@@ -463,7 +464,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (PAIR) mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8));
+              if (PAIR) { if (p.arrive_release) mbar_arrive_cluster_release(empty_addr0 + static_cast<uint32_t>(as * 8)); else mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8)); }
               else mbar_arrive(&tmem_empty_bar[as]);
             }
           }
@@ -510,7 +511,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8));
+          if (PAIR) { if (p.arrive_release) mbar_arrive_cluster_release(empty_addr0 + static_cast<uint32_t>(as * 8)); else mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8)); }
           else mbar_arrive(&tmem_empty_bar[as]);
         }
       }
@@ -593,6 +594,12 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.pos = a.pos;
   p.tokens_in = a.tokens_in; p.tokens_out = a.tokens_out; p.status = dev_status;
   p.stats = a.stats; p.stats_slots = a.stats_slots; p.colsum = a.colsum;
+  static int arrive_release = -1;
+  if (arrive_release < 0) {
+    const char* env = getenv("JCB_GEMM_ARRIVE_RELEASE");
+    arrive_release = (env && env[0] == '1') ? 1 : 0;
+  }
+  p.arrive_release = arrive_release;
   const int tile_m = BLOCK_M * CTAS;
   const int tiles = ((a.M + tile_m - 1) / tile_m) * (a.N / BN);
   const int units = num_sms / CTAS;                       // CTAs or CTA pairs that fit the chip

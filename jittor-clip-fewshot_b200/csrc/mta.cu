@@ -13,6 +13,8 @@
 //
 // X [V, D] unit rows (row 0 = un-augmented view), T given as [D, C] (the orientation the reference
 // passes: `text_features.t()`), so class-parallel threads read it coalesced.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -33,6 +35,7 @@ struct MtaDev {
   float* scratch;       // per image: region R (max(V*C, V*D)) + A (V*ldA), only used when !in_smem
   long long scratch_stride;
   int in_smem;
+  int ldx, ldp;         // fast kernel: padded row strides of X and P in shared memory
 };
 
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
@@ -418,6 +421,277 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
 
 constexpr size_t MTA_SMEM_LIMIT = 220 * 1024;
 
+// ---------------------------------------------------------------------------------------------------
+// Fast solver for problems that fit in shared memory (V <~ 95 at D = 512, C = 403): 512 threads, the two V x V
+// Gram matrices (P P^T and X X^T) as register-tiled fp32 products instead of one warp-shuffle dot per pair, the
+// mode vector in registers during the density passes, two block barriers per inlierness iteration.
+// Measured on B200 at V = 65 (ncu, profiles/r01l_*): the first kernel spent 65 % of its 1.0 M cycles per problem
+// in the per-pair dots of the set-up and ran 8 warps per SM.
+constexpr int MF_THREADS = 512;
+constexpr int MF_WARPS = MF_THREADS / 32;
+
+// row stride (floats) >= n: a multiple of 4 (16-byte rows) whose quarter is odd, so 8 consecutive rows read as
+// float4 at the same column hit 8 different 4-bank groups
+__host__ __device__ inline int mf_pad(int n) {
+  int ld = (n + 3) & ~3;
+  if (((ld >> 2) & 1) == 0) ld += 4;
+  return ld;
+}
+
+__device__ __forceinline__ float mf_block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();  // protect s_red from the previous use
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < MF_WARPS; ++w) t += s_red[w];
+  return t;
+}
+
+// G[i * ldg + j] = sum_k M[i * ld + k] M[j * ld + k] for i, j < V, k < 4 * K4 (columns past the logical width are
+// zero).  One thread = one 4 x 4 tile of the upper triangle; tile t of a dimension owns rows t, t + nt, t + 2 nt,
+// t + 3 nt so that neighbouring threads (neighbouring column tiles) read neighbouring rows: conflict-free LDS.128,
+// and the row tile they share is a broadcast.
+__device__ void mf_gram(const float* __restrict__ M, int ld, int K4, int V, float* __restrict__ G, int ldg) {
+  const int nt = (V + 3) >> 2;
+  const int npairs = nt * (nt + 1) / 2;
+  for (int p = threadIdx.x; p < npairs; p += MF_THREADS) {
+    int ta = 0, rem = p;
+    while (rem >= nt - ta) { rem -= nt - ta; ++ta; }
+    const int tb = ta + rem;
+    const float4* pa[4];
+    const float4* pb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ia = ta + nt * r, ib = tb + nt * r;
+      pa[r] = reinterpret_cast<const float4*>(M + static_cast<long long>(ia < V ? ia : V - 1) * ld);
+      pb[r] = reinterpret_cast<const float4*>(M + static_cast<long long>(ib < V ? ib : V - 1) * ld);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < K4; ++k) {
+      float4 xa[4], xb[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { xa[r] = pa[r][k]; xb[r] = pb[r][k]; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[r][c] = fmaf(xa[r].x, xb[c].x, acc[r][c]);
+          acc[r][c] = fmaf(xa[r].y, xb[c].y, acc[r][c]);
+          acc[r][c] = fmaf(xa[r].z, xb[c].z, acc[r][c]);
+          acc[r][c] = fmaf(xa[r].w, xb[c].w, acc[r][c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = ta + nt * r, j = tb + nt * c;
+        if (i < V && j < V) {
+          G[i * ldg + j] = acc[r][c];
+          G[j * ldg + i] = acc[r][c];
+        }
+      }
+  }
+}
+
+// gaussian_kernel(mode, bandwidth, X)  (test.py:1310-1313): one warp per view, the mode in registers
+__device__ __forceinline__ void mf_density(const float* __restrict__ X, int ldx, const float* s_mode,
+                                           const float* s_bw, float* s_dens, int V, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nq = D >> 7;  // float4 per lane, D % 128 == 0, D <= 1024
+  float4 m[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < nq) m[q] = *reinterpret_cast<const float4*>(s_mode + 128 * q + 4 * lane);
+  for (int i = warp; i < V; i += MF_WARPS) {
+    const float* xr = X + i * ldx + 4 * lane;
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < nq) {
+        const float4 x = *reinterpret_cast<const float4*>(xr + 128 * q);
+        float t = x.x - m[q].x; acc = fmaf(t, t, acc);
+        t = x.y - m[q].y; acc = fmaf(t, t, acc);
+        t = x.z - m[q].z; acc = fmaf(t, t, acc);
+        t = x.w - m[q].w; acc = fmaf(t, t, acc);
+      }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float dist = sqrtf(acc);  // jt.norm(...), then dist**2 as the reference does
+      const float bw = s_bw[i];
+      s_dens[i] = expf(-(dist * dist) / (2.0f * bw * bw));
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MF_THREADS, 1) mta_fast_kernel(const MtaDev a) {
+  extern __shared__ __align__(16) float mta_smem[];
+  const int V = a.V, C = a.C, D = a.D, ldA = a.ldA, ldx = a.ldx, ldp = a.ldp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long img = blockIdx.x;
+  const MtaSet& set = a.sets[blockIdx.y];
+  const float* __restrict__ Xg = set.feats + img * V * D;
+  const float* __restrict__ Tt = set.text;
+
+  float* s_mode = mta_smem;           // [D]
+  float* s_new = s_mode + D;          // [D]
+  float* s_bw = s_new + D;            // [V]
+  float* s_y = s_bw + V;              // [V]
+  float* s_dens = s_y + V;            // [V]
+  float* s_z = s_dens + V;            // [V]
+  float* s_sq = s_z + V;              // [V]
+  float* s_red = s_sq + V;            // [32]
+  float* big = s_red + 32;
+  big = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(big) + 15) & ~static_cast<uintptr_t>(15));
+  float* R = big;                                        // P [V, ldp], later X [V, ldx]
+  const int r_elems = V * (ldp > ldx ? ldp : ldx);
+  float* A = R + r_elems;                                // affinity [V, ldA]
+  float* Dm = A + ((V * ldA + 3) & ~3);                  // Gram of X, then the pairwise distances [V, ldA]
+
+  // ---- 1+2. this problem's V x C block of softmax(100 X T) (mta_probs_kernel), zero padded to ldp columns
+  {
+    const float* Pg = a.P + (static_cast<long long>(blockIdx.y) * a.I + img) * V * C;
+    for (int i = tid; i < V * ldp; i += MF_THREADS) {
+      const int v = i / ldp, c = i - v * ldp;
+      R[i] = c < C ? __ldg(Pg + v * C + c) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- 3. affinity A = P P^T                                    (test.py:1411)
+  mf_gram(R, ldp, ldp >> 2, V, A, ldA);
+  __syncthreads();
+  // ---- 4. the view embeddings replace P on chip
+  for (int i = tid; i < V * (D >> 2); i += MF_THREADS) {
+    const int v = i / (D >> 2), c4 = i - v * (D >> 2);
+    *reinterpret_cast<float4*>(R + v * ldx + 4 * c4) = __ldg(reinterpret_cast<const float4*>(Xg + v * D) + c4);
+  }
+  __syncthreads();
+  const float* X = R;
+  // ---- 5. pairwise distances and per-view bandwidth             (test.py:1314-1318, :1403-1408)
+  mf_gram(X, ldx, D >> 2, V, Dm, ldA);
+  __syncthreads();
+  for (int i = tid; i < V; i += MF_THREADS) s_sq[i] = Dm[i * ldA + i];   // ||x_i||^2, same summation as the dots
+  __syncthreads();
+  for (int idx = tid; idx < V * V; idx += MF_THREADS) {
+    const int i = idx / V, j = idx - i * V;
+    const float d2 = s_sq[i] - 2.0f * Dm[i * ldA + j] + s_sq[j];
+    Dm[i * ldA + j] = sqrtf(fmaxf(d2, 0.0f));
+  }
+  __syncthreads();
+  for (int i = warp; i < V; i += MF_WARPS) {
+    // mean of the squared k smallest distances, skipping rank 0 (the point itself)
+    const float* my_row = Dm + i * ldA;
+    float acc = 0.f;
+    for (int j = lane; j < V; j += 32) {
+      const float dj = my_row[j];
+      int rank = 0;
+      for (int l = 0; l < V; ++l) {
+        const float dl = my_row[l];
+        rank += (dl < dj || (dl == dj && l < j)) ? 1 : 0;
+      }
+      if (rank >= 1 && rank <= a.k) acc += dj * dj;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_bw[i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
+  }
+  // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
+  for (int i = tid; i < V; i += MF_THREADS) s_y[i] = 1.0f / static_cast<float>(V);
+  for (int d = tid; d < D; d += MF_THREADS) s_mode[d] = X[d];
+  __syncthreads();
+
+  const float inv_lambda_y = 1.0f / a.p.lambda_y;
+  for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
+    mf_density(X, ldx, s_mode, s_bw, s_dens, V, D);                // :1426
+    for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
+      for (int i = warp; i < V; i += MF_WARPS) {                   // z = (rho + lambda_q A y) / lambda_y
+        float s = 0.f;
+        for (int j = lane; j < V; j += 32) s = fmaf(A[i * ldA + j], s_y[j], s);
+        s = warp_sum(s);
+        if (lane == 0) s_z[i] = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
+      }
+      __syncthreads();
+      if (warp == 0) {                                             // y <- softmax(z), ||y_old - y||
+        float mx = -INFINITY;
+        for (int i = lane; i < V; i += 32) mx = fmaxf(mx, s_z[i]);
+        mx = warp_max(mx);
+        float zs = 0.f;
+        for (int i = lane; i < V; i += 32) {
+          const float e = expf(s_z[i] - mx);
+          s_z[i] = e;
+          zs += e;
+        }
+        zs = warp_sum(zs);
+        const float inv = 1.0f / zs;
+        float diff = 0.f;
+        for (int i = lane; i < V; i += 32) {
+          const float yn = s_z[i] * inv;
+          const float t = s_y[i] - yn;
+          diff = fmaf(t, t, diff);
+          s_y[i] = yn;
+        }
+        diff = warp_sum(diff);
+        if (lane == 0) s_red[31] = diff;
+      }
+      __syncthreads();
+      if (sqrtf(s_red[31]) < a.p.th || it >= a.p.max_iter) break;  // :1436
+    }
+    for (int it = 1;; ++it) {                                      // mode loop :1443-1453
+      mf_density(X, ldx, s_mode, s_bw, s_dens, V, D);              // :1446
+      float nrm = 0.f;
+      for (int d = tid; d < D; d += MF_THREADS) {
+        float s = 0.f, wsum = 0.f;
+        for (int i = 0; i < V; ++i) {
+          const float w = s_dens[i] * s_y[i];                      // :1447
+          wsum += w;
+          s = fmaf(w, X[i * ldx + d], s);
+        }
+        s = s / wsum;                                              // :1448
+        s_new[d] = s;
+        nrm = fmaf(s, s, nrm);
+      }
+      nrm = mf_block_sum(nrm, s_red);
+      const float inv = 1.0f / sqrtf(nrm);                         // :1449
+      float diff = 0.f;
+      for (int d = tid; d < D; d += MF_THREADS) {
+        const float m = s_new[d] * inv;
+        const float t = s_mode[d] - m;
+        diff = fmaf(t, t, diff);
+        s_new[d] = m;
+      }
+      diff = mf_block_sum(diff, s_red);
+      for (int d = tid; d < D; d += MF_THREADS) s_mode[d] = s_new[d];
+      __syncthreads();
+      if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
+    }
+  }
+
+  // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
+  for (int d = tid; d < D; d += MF_THREADS) set.out_mode[img * D + d] = s_mode[d];
+  if (set.out_logits) {
+    for (int c = tid; c < C; c += MF_THREADS) {
+      float s = 0.f;
+      for (int d = 0; d < D; ++d) s = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s);
+      set.out_logits[img * C + c] = s * 100.0f;
+    }
+  }
+}
+
+size_t mf_smem_bytes(int V, int C, int D) {
+  const int ldx = mf_pad(D), ldp = mf_pad(C), ldA = V | 1;
+  const size_t small = sizeof(float) * (2 * D + 5 * V + 32) + 16;
+  const size_t bigf = static_cast<size_t>(V) * (ldp > ldx ? ldp : ldx) + 2 * static_cast<size_t>((V * ldA + 3) & ~3);
+  return small + bigf * sizeof(float);
+}
+
+
 size_t small_state_bytes(int V, int D) { return sizeof(float) * (2 * D + (5 + MTA_WARPS) * V + 32) + 16; }
 long long big_elems(int V, int C, int D, int ldA) {
   const long long r = static_cast<long long>(V) * (C > D ? C : D);
@@ -431,6 +705,14 @@ static bool mta_fits_smem(int V, int C, int D) {
 }
 
 static bool mta_use_probs_kernel(int C, int D) { return C <= PB_CPAD && D % PB_KC == 0; }
+static bool mta_fast_enabled() {   // JCB_MTA_FAST=0 keeps the first (256-thread, per-pair dot) kernel for A/B runs
+  static int v = -1;
+  if (v < 0) {
+    const char* env = getenv("JCB_MTA_FAST");
+    v = (env && env[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D) {
   size_t b = 0;
@@ -478,6 +760,23 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     if (e != cudaSuccess) return e;
     a.P = scratch;
     scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + p_bytes);
+  }
+  if (a.P != nullptr && D % 128 == 0 && mf_smem_bytes(V, C, D) <= MTA_SMEM_LIMIT && mta_fast_enabled()) {
+    a.ldx = mf_pad(D);
+    a.ldp = mf_pad(C);
+    a.in_smem = 1;
+    a.scratch = nullptr;
+    a.scratch_stride = 0;
+    static bool fattr = false;
+    if (!fattr) {
+      cudaError_t e = cudaFuncSetAttribute(mta_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(MTA_SMEM_LIMIT));
+      if (e != cudaSuccess) return e;
+      fattr = true;
+    }
+    dim3 fgrid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
+    mta_fast_kernel<<<fgrid, MF_THREADS, mf_smem_bytes(V, C, D), stream>>>(a);
+    return cudaGetLastError();
   }
   if (!a.in_smem && scratch == nullptr) return cudaErrorInvalidValue;
   a.scratch = scratch;

@@ -282,8 +282,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// Arrive on an mbarrier that may live in the peer CTA (address in the shared::cluster window).
+// Arrive on an mbarrier that may live in the peer CTA (address in the shared::cluster window).  Default semantics
+// (release at CTA scope = one SYNCS.ARRIVE): the `.release.cluster` form compiles to MEMBAR.ALL.GPU + ERRBAR +
+// CGAERRBAR in front of the arrive, which cost an epilogue warp ~20 % of its time (profiles/r01e: 14 % of all stall
+// samples of the c_fc GEMM).  The TMEM reads this arrive publishes are ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync, not by the memory model.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {   // A/B only (JCB_GEMM_ARRIVE_RELEASE=1)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-D tiled load issued by either CTA of a pair into ITS OWN shared memory; the bytes are reported

@@ -32,6 +32,13 @@ class TextBank:
         self.num_classes, self.dim = self.pt.shape
 
 
+class _Ticket:
+    """One un-collected submission: keeps the input / output buffers and the argument struct alive."""
+
+    def __init__(self, ctx, ticket_id, topk, keep):
+        self.ctx, self.id, self.topk, self.keep = ctx, ticket_id, topk, keep
+
+
 class HotPath:
     """encode_image -> L2 normalise -> solve_mta x3 -> Channel_LP / logit_normalize / fusion -> top-k."""
 
@@ -90,6 +97,47 @@ class HotPath:
         if return_scores:
             out.append(scores)
         return out[0] if len(out) == 1 else tuple(out)
+
+    # ---- streams of batches: the reference's `for images in loader:` loop with the next batch's uploads
+    #      overlapping this batch's compute (jcb_pipeline_submit / jcb_pipeline_wait)
+    def submit(self, images):
+        """Enqueue evaluate_base(images) without waiting and return a ticket for `collect`.  `images` as in
+        evaluate_base; host images must be page-locked (pin_memory) for the copies to overlap compute and
+        must not be modified until `collect` returns."""
+        t = as_torch(images)
+        if t.dim() != 5:
+            raise ValueError(f"expected images [I, V, 3, R, R], got {tuple(t.shape)}")
+        t = t.contiguous()
+        I, V = t.shape[0], t.shape[1]
+        device = self.text.device
+        with torch.cuda.device(device):
+            ctx, vit = self.model.visual._engine(device)
+            vit_zs = self.model_zs.visual._engine(device)[1] if self.model_zs is not None else None
+            ctx.bind_current_stream()
+            topk = torch.empty((I, self.k), dtype=torch.int32, device="cpu", pin_memory=True)
+            a = self._args(t, I, V, not t.is_cuda, topk, None, None, device)
+            ticket = _capi.c_int64()
+            check(ctx.lib.jcb_pipeline_submit(vit, vit_zs, _capi.byref(a), _capi.byref(ticket)), ctx.handle)
+        return _Ticket(ctx, ticket.value, topk, (t, a))
+
+    def collect(self, ticket):
+        """Block until the submission has completed; returns its int32 top-k [I, k] on the host."""
+        check(ticket.ctx.lib.jcb_pipeline_wait(ticket.ctx.handle, ticket.id), ticket.ctx.handle)
+        ticket.keep = None
+        return ticket.topk
+
+    def evaluate_stream(self, batches, depth=2):
+        """Generator over an iterable of image batches: yields the host top-k of each batch in order while up to
+        `depth` batches are in flight (depth 2 = the uploads of batch k+1 overlap the compute of batch k)."""
+        if not 1 <= depth <= _capi.MAX_INFLIGHT:
+            raise ValueError(f"depth must be in 1..{_capi.MAX_INFLIGHT}")
+        pending = []
+        for images in batches:
+            pending.append(self.submit(images))
+            if len(pending) >= depth:
+                yield self.collect(pending.pop(0))
+        while pending:
+            yield self.collect(pending.pop(0))
 
     def evaluate_new(self, images, text_zs=None):
         """evaluate_new (test.py:1759-1779): zero-shot tower -> solve_mta -> 100 f T^T -> top-5."""

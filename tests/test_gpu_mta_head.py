@@ -165,6 +165,41 @@ def test_pipeline_matches_oracle_given_same_embeddings(jb, cuda_dev):
         assert agree / (5 * I) >= TOP5_AGREE
 
 
+def test_evaluate_stream_matches_blocking_calls(jb, cuda_dev):
+    """HotPath.evaluate_stream (jcb_pipeline_submit / jcb_pipeline_wait): batches of different sizes in flight
+    together, host and device inputs, several host chunks per batch; every batch's top-5 equals the blocking
+    evaluate_base call on the same images; too many un-collected submissions are refused, not queued."""
+    sd = jb.synth.make_vit_state_dict(seed=4, layers=2)
+    model = jb.jclip.build_model(sd)
+    Ts = _texts(jb, 3)
+    lp_np = jb.synth.make_head(2, Ts[2].numpy())
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = lp_np
+    hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp)
+    ctx = jb.get_context(cuda_dev)
+    ctx.set_host_chunk_views(16)          # 45 views per batch -> 3-4 staged passes per batch
+    try:
+        batches = [torch.from_numpy(jb.synth.make_views(20 + b, I, 9)) for b, I in enumerate((5, 3, 5, 1, 4, 5))]
+        want = [hp.evaluate_base(b.to(cuda_dev)).cpu() for b in batches]
+        pinned = [b.pin_memory() for b in batches]
+        for depth in (1, 2, 4):
+            got = list(hp.evaluate_stream(iter(pinned), depth=depth))
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert not g.is_cuda and torch.equal(g, w)
+        mixed = [b.to(cuda_dev) if i % 2 else pinned[i] for i, b in enumerate(batches)]
+        for g, w in zip(hp.evaluate_stream(iter(mixed), depth=3), want):
+            assert torch.equal(g, w)
+        tickets = [hp.submit(pinned[0]) for _ in range(4)]
+        with pytest.raises(jb._capi.JcbError):
+            hp.submit(pinned[0])
+        for t in reversed(tickets):       # collecting out of order is allowed: tickets complete in order
+            assert torch.equal(hp.collect(t), want[0])
+        assert torch.equal(hp.evaluate_base(pinned[1]), want[1])
+    finally:
+        ctx.set_host_chunk_views(2048)
+
+
 def test_evaluate_new_and_ood_split(jb, cuda_dev):
     from oracle import solve_mta as o_mta
     sd = jb.synth.make_vit_state_dict(seed=4, layers=2)
