@@ -303,6 +303,10 @@ int jcb_gemm_bf16(jcb_ctx* ctx, const void* A_dev, const void* B_dev, int32_t M,
                   const float* bias_dev, int32_t epilogue, void* out_dev, int64_t ldo);
 int jcb_layernorm_bf16(jcb_ctx* ctx, const float* x_dev, int64_t rows, int32_t width, const float* gamma_dev,
                        const float* beta_dev, void* out_bf16_dev);
+/* `tfm_clip` + the patch extraction of conv1 (test.py:1301, jclip/model.py:105-108): images_dev [n_views, 3, R, R]
+ * (JCB_IMG_*) -> patches_bf16_dev [n_views * (R/P)^2, 3 * P * P], row = (view, py, px), column = (c, i, j). */
+int jcb_im2col_bf16(jcb_ctx* ctx, const void* images_dev, int32_t img_dtype, int64_t n_views, int32_t resolution,
+                    int32_t patch, int32_t apply_clip_norm, void* patches_bf16_dev);
 int jcb_attention_bf16(jcb_ctx* ctx, const void* qkv_bf16_dev, int64_t n_views, int32_t tokens, int32_t heads,
                        void* out_bf16_dev);
 

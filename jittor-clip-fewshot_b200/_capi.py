@@ -5,6 +5,7 @@ library is missing the import of any product module fails with instructions to b
 context cannot be created without an sm_100 GPU.
 """
 import ctypes
+import os
 from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_void_p)
 from pathlib import Path
@@ -121,6 +122,7 @@ PROTOTYPES = {
                               c_void_p, c_int64]),
     "jcb_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "jcb_attention_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "jcb_im2col_bf16": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "jcb_encode_image_dlpack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
 }
 
@@ -139,7 +141,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("JCB_LIB_PATH") or LIB_PATH)   # JCB_LIB_PATH: A/B builds only
     if not p.exists():
         raise RuntimeError(
             f"{p} is missing: the hot path is CUDA-only and has no CPU fallback.  Build it with "

@@ -41,6 +41,31 @@ def _stale(target, deps):
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def build_variant(out_path, defines):
+    """A/B experiments: the same library with extra -D macros, built out of tree objects into `out_path`
+    (load it with JCB_LIB_PATH=...).  Not used by the product build."""
+    nvcc = find_nvcc()
+    vdir = OBJ_DIR / ("variant_" + Path(out_path).stem)
+    vdir.mkdir(parents=True, exist_ok=True)
+    flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
+
+    def one(src):
+        o = vdir / (Path(src).stem + ".o")
+        r = subprocess.run([nvcc] + flags + ["-c", str(CSRC / src), "-o", str(o)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return o
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, SOURCES))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out_path)] + \
+          [str(o) for o in objs] + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return Path(out_path)
+
+
 def build(force=False, verbose=False):
     """Compile every .cu for sm_100a and link the shared library.  Returns the library path."""
     nvcc = find_nvcc()
@@ -78,5 +103,9 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(p)
+    if "--variant" in sys.argv:      # python build.py --variant out.so -DNAME=VALUE ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+        print(p)

@@ -23,6 +23,7 @@
 // positional-embedding add (jclip/model.py:114) are fused into the epilogues.
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <cudaTypedefs.h>
 
 #include "kernels.h"
@@ -35,19 +36,28 @@ namespace {
 constexpr int BLOCK_M = 128;  // rows of A (and of the accumulator) per CTA
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-// epilogue warps: 4 (one per TMEM lane quarter, all BN columns each) or 8 (two per quarter, half the columns each)
-// for the MUFU-heavy GELU epilogues, which are bound by the epilogue warps' issue slots rather than by the tensor pipe
-__host__ __device__ constexpr int epi_warps_of(int epi) {
-  // measured on B200 (tools/bench_kernel.py gemm): 8 warps do NOT help c_fc (1284 vs 1337 TFLOP/s) -- under the
-  // power cap the extra warps cost more than the issue slots they add -- so every epilogue uses 4
-  return (epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_GELU_BF16) ? 4 : 4;
-}
+// epilogue warps: 4 (one per TMEM lane quarter, all BN columns each); 8 (two per quarter, half the columns each) is
+// supported by the tile configuration but never pays: the epilogues are idle more than half of every tile
+// (JCB_GEMM_TRACE) -- measured c_fc 1284 (8 warps) vs 1337 (4 warps) TFLOP/s.
+__host__ __device__ constexpr int epi_warps_of(int) { return 4; }
 
-// chunks converted per generic->async proxy fence / per batch of TMA stores.  The MUFU-heavy GELU epilogue
-// (fc1) is the one that is epilogue-bound: it gets the whole tile per fence and pays with one ring stage
-// (4 instead of 5); the mainloop-bound shapes keep 5 stages and fence every 2 chunks.  Measured on B200:
-// fc1 1260 -> 1346 TFLOP/s with GROUP 4; fc2 / qkv lose ~5 % with only 4 stages.
-__host__ __device__ constexpr int group_of(int epi) { return (epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_GELU_BF16) ? 4 : 2; }
+// chunks converted per generic->async proxy fence / per batch of TMA stores = staging buffers per epilogue warp.
+// Every epilogue fences every 2 chunks and leaves the ring 5 stages (160 KB in flight per SM).  The role timeline
+// (JCB_GEMM_TRACE) shows why staging must not eat a ring stage: with 4 stages the c_fc GEMM's MMA issuer waits for
+// operands (157 cycles per UMMA instead of the pipe's 135-138) while its GELU epilogue idles 4.4 k of every 7.8 k
+// cycles -- the loads are latency-bound (~1.7 us under load), so bytes in flight set the rate.  Measured on B200
+// (tools/gpu_ab.sh): c_fc 1309 -> 1432 TFLOP/s with 5 stages; 6 stages with per-chunk fences gain 3 % on QKV but
+// cost the HBM-bound out_proj 10 %.  (JCB_* macros: A/B builds via build.py --variant.)
+#ifndef JCB_GELU_GROUP
+#define JCB_GELU_GROUP 2
+#endif
+#ifndef JCB_GROUP
+#define JCB_GROUP 2
+#endif
+#ifndef JCB_SMEM_KB
+#define JCB_SMEM_KB 200
+#endif
+__host__ __device__ constexpr int group_of(int epi) { return (epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_GELU_BF16) ? JCB_GELU_GROUP : JCB_GROUP; }
 __host__ __device__ constexpr bool is_lnprep(int epi) { return epi == EPI_RESID_LNPREP_SHORT || epi == EPI_RESID_LNPREP_LONG; }
 __host__ __device__ constexpr bool is_lnfold(int epi) { return epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16; }
 __host__ __device__ constexpr bool out_is_bf16(int epi) { return epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || is_lnfold(epi); }
@@ -68,7 +78,7 @@ struct TileCfg {
   // per epilogue warp: 32-row x 128-B swizzled chunks (GROUP of them, or NB + NH for the LNPREP epilogues)
   static constexpr int WARP_STAGING = (is_lnprep(EPI) ? lnprep_nb(EPI) + lnprep_nh(EPI) : GROUP) * 4096;
   static constexpr int STAGING_BYTES = EPI_WARPS * WARP_STAGING;
-  static constexpr int SMEM_TOTAL = is_lnprep(EPI) ? 220 * 1024 : 200 * 1024;  // operand ring + epilogue staging
+  static constexpr int SMEM_TOTAL = is_lnprep(EPI) ? 220 * 1024 : JCB_SMEM_KB * 1024;  // operand ring + epilogue staging
   static constexpr int VEC_FLOATS = (is_lnfold(EPI) ? 2 : 1) * CW;             // per-warp bias (+ column-sum) slice
   static constexpr int BAR_BYTES = 512;
   static constexpr int B_ROWS = BN / CTAS;  // rows of the B tile this CTA stages
@@ -92,14 +102,13 @@ struct GemmDev {
   int stats_slots;
   const float* colsum;   // LNFOLD
   int arrive_release;    // A/B: 1 = the old `.release.cluster` accumulator hand-back
+  long long* trace;      // debug (JCB_GEMM_TRACE=file): clock64 stamps of CTA 0's roles, [TRACE_TILES][8]
 };
-
-__device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)  (reference jclip/model.py:27) = 0.5 x (1 + tanh(0.851 x)): one MUFU op per element
-  // (tanh.approx, rel. error 2^-11, below the bf16 rounding of the output) instead of ex2 + rcp
-  const float h = 0.5f * x;
-  return fmaf(h, tanh_approx(0.851f * x), h);
-}
+constexpr int TRACE_TILES = 96;
+#define JCB_TRACE(slot)                                                                  \
+  do {                                                                                   \
+    if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_TILES) p.trace[it * 8 + (slot)] = clock64(); \
+  } while (0)
 
 template <int BN, int EPI, int CTAS>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
@@ -180,12 +189,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = unit; tile < num_tiles && ok; tile += num_units) {
+      int it = 0;
+      for (int tile = unit; tile < num_tiles && ok; tile += num_units, ++it) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int m0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!mbar_wait(&empty_bar[stage], phase ^ 1u, p.status, JCB_DEV_TIMEOUT_PRODUCER)) { ok = false; break; }
+          if (kb == 0) JCB_TRACE(5);
+          if (kb == num_kb - 1) JCB_TRACE(6);
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (PAIR) {
@@ -216,6 +228,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         const uint32_t aphase = (it >> 1) & 1;
         if (!mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, p.status, JCB_DEV_TIMEOUT_MMA)) { ok = false; break; }
         tc_fence_after();
+        JCB_TRACE(0);
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!mbar_wait(&full_bar[stage], phase, p.status, JCB_DEV_TIMEOUT_MMA)) { ok = false; break; }
@@ -240,6 +253,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         if (ok) {  // accumulator complete -> epilogue warps of both CTAs
           if (PAIR) umma_commit_pair(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
         }
+        JCB_TRACE(1);
       }
     }
   } else {
@@ -285,6 +299,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       tc_fence_after();
+      if (ew == 0 && lane == 0) JCB_TRACE(2);
 
       const int row0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;  // this warp's 32 rows
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + col0);
@@ -424,6 +439,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           ln_r = 1.0f / sqrtf(var + 1e-5f);
           ln_nmr = -mean * ln_r;
         }
+        const uint64_t r2 = f2_pack(ln_r, ln_r), nmr2 = f2_pack(ln_nmr, ln_nmr);
+        const uint64_t k05 = f2_pack(0.5f, 0.5f), k851 = f2_pack(0.851f, 0.851f);
+        (void)r2; (void)nmr2; (void)k05; (void)k851;
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted; the smem
         // staging holds GROUP chunks so the generic->async proxy fence (MEMBAR + ERRBAR, ~17 % of all
         // stall samples when issued per chunk) and the TMA issue happen once per GROUP chunks
@@ -439,15 +457,17 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         for (int c = 0; c < NCH; ++c) {
           uint32_t(&cur)[CHUNK_COLS] = v[c & 1];
           // bias of this chunk into registers while the TMEM load is still in flight
-          float bb[CHUNK_COLS];
+          // additive term of every column as packed fp32 pairs: bias, or for the folded LayerNorm c[n] - r mu S[n]
+          uint64_t bb2[CHUNK_COLS / 2];
 #pragma unroll
           for (int j = 0; j < CHUNK_COLS / 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * CHUNK_COLS + 4 * j);
-            bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
-            if (FOLD) {   // c[n] - r mu S[n]: the per-row, per-column additive term of the folded LayerNorm
+            bb2[2 * j] = f2_pack(b4.x, b4.y);
+            bb2[2 * j + 1] = f2_pack(b4.z, b4.w);
+            if (FOLD) {
               const float4 s4 = *reinterpret_cast<const float4*>(s_csum + c * CHUNK_COLS + 4 * j);
-              bb[4 * j] = fmaf(ln_nmr, s4.x, bb[4 * j]); bb[4 * j + 1] = fmaf(ln_nmr, s4.y, bb[4 * j + 1]);
-              bb[4 * j + 2] = fmaf(ln_nmr, s4.z, bb[4 * j + 2]); bb[4 * j + 3] = fmaf(ln_nmr, s4.w, bb[4 * j + 3]);
+              bb2[2 * j] = f2_fma(nmr2, f2_pack(s4.x, s4.y), bb2[2 * j]);
+              bb2[2 * j + 1] = f2_fma(nmr2, f2_pack(s4.z, s4.w), bb2[2 * j + 1]);
             }
           }
           if (c % GROUP == 0) {
@@ -463,6 +483,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             // (leader CTA) before the last chunk is even converted
             tc_fence_before();
             __syncwarp();
+            if (ew == 0 && lane == 0) JCB_TRACE(3);
             if (lane == 0) {
               if (PAIR) { if (p.arrive_release) mbar_arrive_cluster_release(empty_addr0 + static_cast<uint32_t>(as * 8)); else mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8)); }
               else mbar_arrive(&tmem_empty_bar[as]);
@@ -475,18 +496,26 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             if (OUT_BF16) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = FOLD ? fmaf(__uint_as_float(cur[8 * j + e]), ln_r, bb[8 * j + e])
-                            : __uint_as_float(cur[8 * j + e]) + bb[8 * j + e];
-                if (GELU) f[e] = quick_gelu(f[e]);
+              for (int e = 0; e < 4; ++e) {   // two columns per instruction
+                const uint64_t a2 = f2_pack(__uint_as_float(cur[8 * j + 2 * e]), __uint_as_float(cur[8 * j + 2 * e + 1]));
+                uint64_t x2 = FOLD ? f2_fma(a2, r2, bb2[4 * j + e]) : f2_add(a2, bb2[4 * j + e]);
+                if (GELU) {
+                  // x * sigmoid(1.702 x)  (reference jclip/model.py:27) = h + h tanh(0.851 x), h = 0.5 x: one MUFU op
+                  // per element (tanh.approx, rel. error 2^-11, below the bf16 rounding of the output)
+                  const uint64_t h2 = f2_mul(x2, k05);
+                  float t0, t1;
+                  f2_unpack(f2_mul(x2, k851), t0, t1);
+                  x2 = f2_fma(h2, f2_pack(tanh_approx(t0), tanh_approx(t1)), h2);
+                }
+                f2_unpack(x2, f[2 * e], f[2 * e + 1]);
               }
               o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
               o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
             } else {
-              o.x = __float_as_uint(__uint_as_float(cur[4 * j + 0]) + bb[4 * j + 0]);
-              o.y = __float_as_uint(__uint_as_float(cur[4 * j + 1]) + bb[4 * j + 1]);
-              o.z = __float_as_uint(__uint_as_float(cur[4 * j + 2]) + bb[4 * j + 2]);
-              o.w = __float_as_uint(__uint_as_float(cur[4 * j + 3]) + bb[4 * j + 3]);
+              float f0, f1, f2, f3;
+              f2_unpack(f2_add(f2_pack(__uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1])), bb2[2 * j]), f0, f1);
+              f2_unpack(f2_add(f2_pack(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), bb2[2 * j + 1]), f2, f3);
+              o.x = __float_as_uint(f0); o.y = __float_as_uint(f1); o.z = __float_as_uint(f2); o.w = __float_as_uint(f3);
             }
             *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = o;
           }
@@ -507,6 +536,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           }
         }
       }
+      if (ew == 0 && lane == 0) JCB_TRACE(4);
       if (EPI == EPI_PATCH_F32) {
         tc_fence_before();
         __syncwarp();
@@ -600,11 +630,36 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
     arrive_release = (env && env[0] == '1') ? 1 : 0;
   }
   p.arrive_release = arrive_release;
+  static const char* trace_path = getenv("JCB_GEMM_TRACE");
+  static long long* trace_dev = nullptr;
+  p.trace = nullptr;
+  if (trace_path) {
+    if (!trace_dev) cudaMalloc(&trace_dev, TRACE_TILES * 8 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, TRACE_TILES * 8 * sizeof(long long), stream);
+    p.trace = trace_dev;
+  }
   const int tile_m = BLOCK_M * CTAS;
   const int tiles = ((a.M + tile_m - 1) / tile_m) * (a.N / BN);
   const int units = num_sms / CTAS;                       // CTAs or CTA pairs that fit the chip
   const int grid = (tiles < units ? tiles : units) * CTAS;
   kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, p);
+  if (trace_path) {   // debug only: synchronous dump of CTA 0's role timeline (cycles relative to its first stamp)
+    std::vector<long long> h(TRACE_TILES * 8);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "# gemm M=%d N=%d K=%d epi=%d: it mma_start mma_commit epi_full epi_release epi_done prod_first prod_last\n", a.M, a.N, a.K, EPI);
+      long long t0 = 0;
+      for (size_t i = 0; i < h.size(); ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+      for (int i = 0; i < TRACE_TILES; ++i) {
+        if (!h[i * 8]) break;
+        fprintf(f, "%d", i);
+        for (int s = 0; s < 7; ++s) fprintf(f, " %lld", h[i * 8 + s] ? h[i * 8 + s] - t0 : -1);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   return cudaGetLastError();
 }
 

@@ -62,7 +62,9 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
                             const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
                             const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats = nullptr,
-                            int stats_slots = 0);   // stats != nullptr: y = bf16(x) raw + (sum, sumsq) for EPI_LNFOLD_*
+                            int stats_slots = 0,    // stats != nullptr: y = bf16(x) raw + (sum, sumsq) for EPI_LNFOLD_*
+                            const float* patch_out = nullptr);   // dense conv1 output [n_views * (T-1-n_vpt), W] (no pos) instead
+                                                                 // of patch rows already scattered into `tokens`
 // y_bf16[r,:] = LayerNorm(x_f32[r,:]) * g + b   (eps 1e-5, biased variance), W == 768 or any W % 128 == 0 <= 1024
 cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
                              __nv_bfloat16* y, cudaStream_t stream);

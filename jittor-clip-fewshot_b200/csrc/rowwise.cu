@@ -5,6 +5,8 @@
 // Reference: jclip/model.py:17-21 (LayerNorm), :105-115 (conv1 as patches, cls, pos, ln_pre),
 // :121-124 (ln_post, proj), test.py:1301 (tfm_clip), test.py:1706 (L2 normalisation),
 // test.py:310-313 (merge_BA).
+#include <algorithm>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -18,56 +20,79 @@ __constant__ float c_clip_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
 // ------------------------------------------------------------------------------------------ im2col
-// One thread converts EPT consecutive pixels of one image row segment (a patch row is P = 32 pixels, so a
-// segment never crosses a patch): 16 B loaded per thread whatever the pixel type (4 fp32, 8 bf16, 16 u8).
+// One block = the K / EPT 16-byte chunks of a patch row (192 threads for u8, 384 for bf16 / fp32 pixels); a thread
+// keeps its (channel, row, column) offset for the whole kernel and walks over patches, UNROLL of them in flight.
+// ToTensor's 1/255 and tfm_clip's (x - mean_c) / std_c are one FMA per pixel, x * a_c + b_c with a_c = 1 / (255 std_c),
+// b_c = -mean_c / std_c: for all 3 x 256 possible uint8 inputs the bf16-rounded result equals the reference's
+// ((u / 255) - mean) / std evaluated in fp32 (tests/test_host_logic.py::test_u8_normalise_fma_is_exact_in_bf16).
+// The first version spent ~600 instructions per thread on 64-bit index divisions and fp32 divisions and ran at
+// 1.7 TB/s; this one is a plain streaming kernel.
+constexpr int IM2COL_UNROLL = 4;
+
 template <int DT>
-__global__ void __launch_bounds__(256)
-im2col_kernel(const void* __restrict__ images, long long n_views, int R, int P, int apply_norm,
+__global__ void __launch_bounds__(384)
+im2col_kernel(const void* __restrict__ images, unsigned n_patches, int R, int P, int G, int apply_norm,
               __nv_bfloat16* __restrict__ patches) {
-  constexpr int EPT = DT == IMG_F32 ? 8 : (DT == IMG_BF16 ? 8 : 16);
-  const int G = R / P;
+  constexpr int EPT = DT == IMG_U8 ? 16 : 8;
   const int K = 3 * P * P;
-  const int chunks_per_row = K / EPT;
-  const long long total = n_views * G * G * chunks_per_row;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const long long row = idx / chunks_per_row;                    // (view, py, px)
-  const int col = static_cast<int>(idx % chunks_per_row) * EPT;  // (c, i, j) with j % EPT == 0
+  const int col = static_cast<int>(threadIdx.x) * EPT;  // (c, i, j) with j % EPT == 0
   const int c = col / (P * P);
   const int i = (col % (P * P)) / P;
   const int j = col % P;
-  const long long b = row / (G * G);
-  const int pidx = static_cast<int>(row % (G * G));
-  const int py = pidx / G, px = pidx % G;
-  const long long src = ((b * 3 + c) * R + (py * P + i)) * R + px * P + j;
-  float f[EPT];
-  if (DT == IMG_F32) {
-    const float4* s = reinterpret_cast<const float4*>(static_cast<const float*>(images) + src);
-    const float4 a = __ldg(s), d = __ldg(s + 1);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = d.x; f[5] = d.y; f[6] = d.z; f[7] = d.w;
-  } else if (DT == IMG_BF16) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(images) + src));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
-  } else {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(images) + src));
-    const uint8_t* u = reinterpret_cast<const uint8_t*>(&a);
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) f[e] = static_cast<float>(u[e]) * (1.0f / 255.0f);
-  }
+  const long long thread_off = (static_cast<long long>(c) * R + i) * R + j;   // offset inside a view, patch (0, 0)
+  const long long view_elems = 3LL * R * R;
+  const int GG = G * G;
+  float a = DT == IMG_U8 ? 1.0f / 255.0f : 1.0f, b = 0.0f;
   if (apply_norm) {
-    const float m = c_clip_mean[c], s = c_clip_std[c];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) f[e] = (f[e] - m) / s;
+    a = 1.0f / ((DT == IMG_U8 ? 255.0f : 1.0f) * c_clip_std[c]);
+    b = -c_clip_mean[c] / c_clip_std[c];
   }
-  uint4* dst = reinterpret_cast<uint4*>(patches + row * K + col);
+  for (unsigned p0 = blockIdx.x * IM2COL_UNROLL; p0 < n_patches; p0 += gridDim.x * IM2COL_UNROLL) {
+    uint4 raw[IM2COL_UNROLL][DT == IMG_F32 ? 2 : 1];
 #pragma unroll
-  for (int h = 0; h < EPT / 8; ++h) {
-    uint4 o;
-    o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]); o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
-    o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]); o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
-    dst[h] = o;
+    for (int u = 0; u < IM2COL_UNROLL; ++u) {
+      const unsigned p = p0 + u < n_patches ? p0 + u : n_patches - 1;
+      const unsigned view = p / GG, pidx = p - view * GG;
+      const unsigned py = pidx / G, px = pidx - py * G;
+      const long long src = view * view_elems + thread_off + (static_cast<long long>(py) * R + px) * P;
+      if (DT == IMG_F32) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(static_cast<const float*>(images) + src);
+        raw[u][0] = __ldg(s4);
+        raw[u][DT == IMG_F32 ? 1 : 0] = __ldg(s4 + 1);
+      } else if (DT == IMG_BF16) {
+        raw[u][0] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(images) + src));
+      } else {
+        raw[u][0] = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(images) + src));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < IM2COL_UNROLL; ++u) {
+      if (p0 + u >= n_patches) break;
+      float f[EPT];
+      if (DT == IMG_F32) {
+        const float* v = reinterpret_cast<const float*>(&raw[u][0]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = v[e];
+      } else if (DT == IMG_BF16) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][0]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+      } else {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[u][0]);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) f[e] = static_cast<float>((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
+      }
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) f[e] = fmaf(f[e], a, b);
+      uint4* dst = reinterpret_cast<uint4*>(patches + static_cast<long long>(p0 + u) * K + col);
+#pragma unroll
+      for (int h = 0; h < EPT / 8; ++h) {
+        uint4 o;
+        o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]); o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
+        o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]); o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
+        dst[h] = o;
+      }
+    }
   }
 }
 
@@ -156,7 +181,7 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
                 const float* __restrict__ pos, const float* __restrict__ vpt, int n_vpt,
                 const float* __restrict__ g_pre, const float* __restrict__ b_pre,
                 const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y,
-                float* __restrict__ stats, int stats_slots) {
+                float* __restrict__ stats, int stats_slots, const float* __restrict__ patch_out) {
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -177,9 +202,20 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       v[i] = __ldg(reinterpret_cast<const float4*>(vpt + static_cast<long long>(t - (T - n_vpt)) * W) + lane + 32 * i);
+  } else if (patch_out != nullptr) {
+    // patch embedding from the conv1 GEMM's dense output [view * (T - 1 - n_vpt) + t - 1, W] + positional embedding
+    const long long prow = (row / T) * (T - 1 - n_vpt) + (t - 1);
+    const float4* pr = reinterpret_cast<const float4*>(patch_out + prow * W);
+    const float4* pe = reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * W);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = pr[lane + 32 * i];
+      const float4 p = __ldg(pe + lane + 32 * i);
+      v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
   } else {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];  // patch embedding + pos (GEMM epilogue)
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];  // patch embedding + pos already in place (scatter epilogue)
   }
   float mean, rstd;
   row_stats<NV>(v, W, mean, rstd);
@@ -395,13 +431,24 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
   if (resolution % patch != 0 || patch % 16 != 0) return cudaErrorInvalidValue;
   const int G = resolution / patch;
   const int ept = img_dtype == IMG_U8 ? 16 : 8;
-  const long long total = n_views * G * G * (3 * patch * patch / ept);
-  if (total == 0) return cudaSuccess;
-  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  const int threads = 3 * patch * patch / ept;           // one thread per 16-byte chunk of a patch row
+  if (threads > 384 || threads % 32 != 0) return cudaErrorInvalidValue;   // patch 32: 192 (u8) / 384
+  const int64_t n_patches = n_views * G * G;
+  if (n_patches == 0) return cudaSuccess;
+  if (n_patches > 0x7fffffffLL) return cudaErrorInvalidValue;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int64_t want = (n_patches + IM2COL_UNROLL - 1) / IM2COL_UNROLL;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * (1536 / threads) * 2));
+  const unsigned np = static_cast<unsigned>(n_patches);
   switch (img_dtype) {
-    case IMG_F32: im2col_kernel<IMG_F32><<<grid, 256, 0, stream>>>(images, n_views, resolution, patch, apply_norm, patches); break;
-    case IMG_BF16: im2col_kernel<IMG_BF16><<<grid, 256, 0, stream>>>(images, n_views, resolution, patch, apply_norm, patches); break;
-    case IMG_U8: im2col_kernel<IMG_U8><<<grid, 256, 0, stream>>>(images, n_views, resolution, patch, apply_norm, patches); break;
+    case IMG_F32: im2col_kernel<IMG_F32><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); break;
+    case IMG_BF16: im2col_kernel<IMG_BF16><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); break;
+    case IMG_U8: im2col_kernel<IMG_U8><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -426,14 +473,15 @@ cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g
 
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
                             const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
-                            const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats, int stats_slots) {
+                            const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats, int stats_slots,
+                            const float* patch_out) {
   if (W % 128 != 0) return cudaErrorInvalidValue;
   const long long rows = n_views * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
   JCB_DISPATCH_NV(W, (embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(tokens, rows, T, cls, pos, vpt,
                                                                            n_vpt, g_pre, b_pre, g1, b1, y, stats,
-                                                                           stats_slots)));
+                                                                           stats_slots, patch_out)));
   return cudaGetLastError();
 }
 

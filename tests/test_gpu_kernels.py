@@ -156,3 +156,37 @@ def test_attention(jb, cuda_dev, n_views, T, H):
     ref = (att @ v).permute(0, 2, 1, 3).reshape(n_views * T, W)
     # 1e-2 absolute (P rounded to bf16) + one bf16 ulp of the output itself (2^-8 relative)
     assert ((out.float() - ref).abs() <= 1e-2 + 2.0 ** -8 * ref.abs()).all()
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32", "bf16"])
+@pytest.mark.parametrize("norm", [0, 1])
+def test_im2col(jb, cuda_dev, dtype, norm):
+    """tfm_clip + patch extraction (test.py:1301, jclip/model.py:105-108).  uint8 pixels: the bf16 patches equal the
+    reference's fp32 arithmetic ((u / 255) - mean) / std rounded to bf16, bit for bit; float pixels: one bf16 ulp."""
+    from ctypes import c_void_p
+    g = torch.Generator().manual_seed(5)
+    n, R, P = 5, 224, 32
+    G = R // P
+    if dtype == "u8":
+        img = torch.randint(0, 256, (n, 3, R, R), generator=g, dtype=torch.uint8)
+        x = img.float() / 255.0                                       # T.ToTensor
+    else:
+        img = torch.rand(n, 3, R, R, generator=g)
+        if dtype == "bf16":
+            img = img.to(torch.bfloat16)
+        x = img.float()
+    if norm:
+        mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+        std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+        x = (x - mean) / std                                          # T.ImageNormalize
+    ref = x.view(n, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(n * G * G, 3 * P * P).to(torch.bfloat16)
+    out = torch.empty(n * G * G, 3 * P * P, dtype=torch.bfloat16, device=cuda_dev)
+    ctx = _ctx(jb, cuda_dev)
+    d = img.to(cuda_dev)
+    jb._capi.check(ctx.lib.jcb_im2col_bf16(ctx.handle, c_void_p(d.data_ptr()), {"f32": 0, "bf16": 1, "u8": 2}[dtype], n, R, P,
+                                           norm, c_void_p(out.data_ptr())), ctx.handle)
+    ctx.sync()
+    if dtype == "u8":
+        assert torch.equal(out.cpu(), ref)
+    else:
+        assert ((out.cpu().float() - ref.float()).abs() <= 2.0 ** -7 * ref.float().abs() + 1e-6).all()   # one bf16 ulp

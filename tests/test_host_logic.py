@@ -199,3 +199,23 @@ def test_cls_acc(jb):
     out = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5]])
     assert jb.cls_acc(out, torch.tensor([1, 0, 0]), topk=1) == pytest.approx(200 / 3)
     assert jb.cls_acc(out, torch.tensor([1, 0, 1]), topk=2) == pytest.approx(100.0)
+
+
+def test_u8_normalise_fma_is_exact_in_bf16():
+    """im2col fuses ToTensor (u / 255) and tfm_clip ((x - mean) / std, test.py:1301) into one FMA per pixel,
+    u * a_c + b_c.  For every one of the 3 x 256 possible inputs the bf16 operand the patch GEMM sees is the one
+    the reference's fp32 arithmetic rounds to; likewise u * (1 / 255) without normalisation."""
+    mean = np.array([0.48145466, 0.4578275, 0.40821073], np.float32)
+    std = np.array([0.26862954, 0.26130258, 0.27577711], np.float32)
+    u = np.arange(256, dtype=np.float32)
+
+    def bf16(x):
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16)
+
+    assert torch.equal(bf16(u * np.float32(1.0 / 255.0)), bf16(u / np.float32(255.0)))
+    for c in range(3):
+        exact = ((u / np.float32(255.0)) - mean[c]) / std[c]
+        a = np.float32(1.0) / (np.float32(255.0) * std[c])
+        b = -mean[c] / std[c]
+        fma = (u.astype(np.float64) * np.float64(a) + np.float64(b)).astype(np.float32)   # one rounding, as fmaf
+        assert torch.equal(bf16(fma), bf16(exact)), c
