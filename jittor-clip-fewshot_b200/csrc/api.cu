@@ -38,7 +38,7 @@ struct jcb_ctx {
   int64_t next_ticket = 0, waited_ticket = 0;
   bool overlapped = false;           // this submission was enqueued behind an un-waited one: its first upload is hidden
   int64_t launches = 0;
-  int ln_fold = 1;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
+  int ln_fold = 2;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
                                      // 0 none, 1 ln_1 only (c_proj -> QKV), 2 ln_1 and ln_2
   char err[512] = {0};
   // per-kernel-class CUDA-event profile (jcb_ctx_profile): event pairs recorded on the launch stream
@@ -279,13 +279,12 @@ TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
 }
 
 int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
-             const float* bias, int epi, void* out, int64_t ldo, const float* pos = nullptr, int tin = 49,
-             int tout = 50, float* stats = nullptr, int stats_slots = 0, const float* colsum = nullptr,
-             void* out2 = nullptr) {
+             const float* bias, int epi, void* out, int64_t ldo, float* stats = nullptr, int stats_slots = 0,
+             const float* colsum = nullptr, void* out2 = nullptr) {
   GemmArgs g;
   g.stats = stats; g.stats_slots = stats_slots; g.colsum = colsum; g.out2 = out2; g.ldo2 = N;
   g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K;
-  g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo; g.pos = pos; g.tokens_in = tin; g.tokens_out = tout;
+  g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo;
   // algorithmic bytes: A + B read once, C written once (read-modify-write for the residual epilogue)
   const bool lnprep = epi == EPI_RESID_LNPREP_SHORT || epi == EPI_RESID_LNPREP_LONG;
   const double out_b = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16)
@@ -309,30 +308,28 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
     // stream and w.stats its per-row partial sums (written by the embed kernel for block 0, then by the residual
     // epilogue of the producing GEMM), and no stand-alone pass reads the fp32 residual stream.
     //   ln_fold >= 1: ln_1 (c_proj of block l-1 -> QKV of block l).  c_proj's 48 k-blocks per tile hide the heavier
-    //                 epilogue; measured net gain.
-    //   ln_fold == 2: ln_2 as well (out_proj -> c_fc).  out_proj is HBM-bound and pays 12 instead of 10 bytes per
-    //                 element, c_fc's GELU epilogue gets heavier: measured net LOSS against the 3.6 ms ln_2 pass.
+    //                 epilogue; measured net gain (-1.5 ms / step).
+    //   ln_fold == 2: ln_2 as well (out_proj -> c_fc); the default.  out_proj is HBM-bound and pays 12 instead of 10
+    //                 bytes per element (6.9 -> 9.3 ms), c_fc's epilogue gets one FMA heavier (+0.3 ms); the 4.0 ms ln_2
+    //                 pass disappears.  A net loss while c_fc ran a 4-stage operand ring (its heavier epilogue then
+    //                 stalled an already starved main loop); with 5 stages a net gain of 1.5-3 ms / step.
     const bool fold2 = ctx->ln_fold >= 2;
     const int slots = (W + 255) / 256;
     for (int l = 0; l < t->L; ++l) {
       const LayerDev& L = t->layers[l];
-      if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, nullptr,
-                         49, 50, w.stats, slots, L.in_S))) return rc;
+      if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, w.stats, slots, L.in_S))) return rc;
       LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
                launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms));
       if (fold2) {
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens, W, nullptr,
-                           49, 50, w.stats, slots, nullptr, w.ln_out))) return rc;
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_wf, M, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W,
-                           nullptr, 49, 50, w.stats, slots, L.fc_S))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens, W, w.stats, slots, nullptr, w.ln_out))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_wf, M, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W, w.stats, slots, L.fc_S))) return rc;
       } else {
         if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
         LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
         if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
       }
       if (l + 1 < t->L) {
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_RESID_LNPREP_LONG, w.tokens, W,
-                           nullptr, 49, 50, w.stats, slots, nullptr, w.ln_out))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_RESID_LNPREP_LONG, w.tokens, W, w.stats, slots, nullptr, w.ln_out))) return rc;
       } else if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) {
         return rc;
       }
@@ -483,7 +480,8 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   {
     const char* env = getenv("JCB_LN_FOLD");
-    ctx->ln_fold = env ? atoi(env) : 1;   // default: fold ln_1 (measured -1.5 ms / step); see tower_blocks
+    ctx->ln_fold = env ? atoi(env) : 2;   // default: both LayerNorms folded (measured, same box: 75.7-76.0 vs
+                                          // 77.2-78.7 ms / step for ln_1 only); see tower_blocks
   }
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
@@ -1244,7 +1242,7 @@ int jcb_gemm_bf16(jcb_ctx* ctx, const void* A, const void* B, int32_t M, int32_t
                   int32_t epilogue, void* out, int64_t ldo) {
   if (!ctx) return JCB_E_INVALID;
   if (!A || !B || !out) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: null pointer");
-  if (epilogue == EPI_PATCH_F32) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: the patch epilogue is internal");
+  if (epilogue == 3) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: epilogue 3 (conv1 scatter) no longer exists");
   DeviceGuard g(ctx->device);
   return run_gemm(ctx, JCB_KC_OTHER, static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(B), M, N, K, bias,
                   epilogue, out, ldo);

@@ -39,7 +39,12 @@ constexpr int UMMA_K = 16;
 // epilogue warps: 4 (one per TMEM lane quarter, all BN columns each); 8 (two per quarter, half the columns each) is
 // supported by the tile configuration but never pays: the epilogues are idle more than half of every tile
 // (JCB_GEMM_TRACE) -- measured c_fc 1284 (8 warps) vs 1337 (4 warps) TFLOP/s.
-__host__ __device__ constexpr int epi_warps_of(int) { return 4; }
+#ifndef JCB_GELU_WARPS
+#define JCB_GELU_WARPS 4
+#endif
+__host__ __device__ constexpr int epi_warps_of(int epi) {
+  return (epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_GELU_BF16) ? JCB_GELU_WARPS : 4;
+}
 
 // chunks converted per generic->async proxy fence / per batch of TMA stores = staging buffers per epilogue warp.
 // Every epilogue fences every 2 chunks and leaves the ring 5 stages (160 KB in flight per SM).  The role timeline
@@ -95,8 +100,6 @@ struct GemmDev {
   const float* bias;
   void* out;
   long long ldo;
-  const float* pos;
-  int tokens_in, tokens_out;
   int* status;
   float* stats;          // LNFOLD: in / LNPREP: out, [M, stats_slots, 2]
   int stats_slots;
@@ -153,7 +156,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (EPI != EPI_PATCH_F32) tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmOut);
     if (is_lnprep(EPI)) {
       tma_prefetch_desc(&tmOut2);
       for (int i = 0; i < EPI_WARPS * 8; ++i) mbar_init(&load_bar[i], 1);
@@ -303,35 +306,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 
       const int row0 = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;  // this warp's 32 rows
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + col0);
-      if (EPI == EPI_PATCH_F32) {
-        // conv1 output rows scatter to token rows 1..T-1 of each view (+ positional embedding): direct stores
-        const int row = row0 + lane;
-        const bool valid = row < p.M;
-        const int tok = row % p.tokens_in + 1;
-        const long long orow = static_cast<long long>(row / p.tokens_in) * p.tokens_out + tok;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
-          const int n0 = n_blk * BN + c * 32;
-          tmem_ld_wait();
-          if (valid) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldo + n0);
-            const float4* pe = reinterpret_cast<const float4*>(p.pos + static_cast<long long>(tok) * p.N + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * j);
-              const float4 e = __ldg(pe + j);
-              float4 o;
-              o.x = __uint_as_float(v[4 * j + 0]) + b.x + e.x;
-              o.y = __uint_as_float(v[4 * j + 1]) + b.y + e.y;
-              o.z = __uint_as_float(v[4 * j + 2]) + b.z + e.z;
-              o.w = __uint_as_float(v[4 * j + 3]) + b.w + e.w;
-              dst[j] = o;
-            }
-          }
-        }
-      } else if (is_lnprep(EPI)) {
+      if (is_lnprep(EPI)) {
         // Residual epilogue that prepares the next LayerNorm: new = old + acc + bias.  The old residual chunk
         // arrives by TMA load in the swizzled staging buffer (requested D chunks ahead), is updated in place and
         // leaves by TMA store; the same pass emits the bf16 copy the next GEMM consumes as its A operand and this
@@ -370,6 +345,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           } else {
             tc_fence_before();
             __syncwarp();
+            if (ew == 0 && lane == 0) JCB_TRACE(3);
             if (lane == 0) {
               if (PAIR) { if (p.arrive_release) mbar_arrive_cluster_release(empty_addr0 + static_cast<uint32_t>(as * 8)); else mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8)); }
               else mbar_arrive(&tmem_empty_bar[as]);
@@ -537,14 +513,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
       }
       if (ew == 0 && lane == 0) JCB_TRACE(4);
-      if (EPI == EPI_PATCH_F32) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) { if (p.arrive_release) mbar_arrive_cluster_release(empty_addr0 + static_cast<uint32_t>(as * 8)); else mbar_arrive_cluster(empty_addr0 + static_cast<uint32_t>(as * 8)); }
-          else mbar_arrive(&tmem_empty_bar[as]);
-        }
-      }
     }
     if (lane == 0) bulk_wait<0>();  // every TMA store / reduce of this warp has been performed
   }
@@ -601,11 +569,7 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   if (!make_tmap_2d(&tmB, true, a.B, a.N, a.K, a.ldb, Cfg::B_ROWS, BLOCK_K)) return cudaErrorInvalidValue;
   constexpr bool OUT_BF16 = out_is_bf16(EPI);
   CUtensorMap tmOut2;
-  if (EPI == EPI_PATCH_F32) {
-    tmOut = tmA;  // unused by the scatter epilogue
-  } else if (!make_tmap_2d(&tmOut, OUT_BF16, a.out, a.M, a.N, a.ldo, 32, OUT_BF16 ? 64 : 32)) {
-    return cudaErrorInvalidValue;
-  }
+  if (!make_tmap_2d(&tmOut, OUT_BF16, a.out, a.M, a.N, a.ldo, 32, OUT_BF16 ? 64 : 32)) return cudaErrorInvalidValue;
   tmOut2 = tmOut;
   if (is_lnprep(EPI)) {
     if (!a.out2 || !a.stats || a.stats_slots < a.N / BN) return cudaErrorInvalidValue;
@@ -621,8 +585,7 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   }
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
-  p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.pos = a.pos;
-  p.tokens_in = a.tokens_in; p.tokens_out = a.tokens_out; p.status = dev_status;
+  p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.status = dev_status;
   p.stats = a.stats; p.stats_slots = a.stats_slots; p.colsum = a.colsum;
   static int arrive_release = -1;
   if (arrive_release < 0) {
@@ -669,7 +632,6 @@ cudaError_t launch_bn(const GemmArgs& a, int* st, int sms, cudaStream_t s) {
     case EPI_BIAS_BF16: return launch_cfg<BN, EPI_BIAS_BF16, CTAS>(a, st, sms, s);
     case EPI_BIAS_GELU_BF16: return launch_cfg<BN, EPI_BIAS_GELU_BF16, CTAS>(a, st, sms, s);
     case EPI_BIAS_RESID_F32: return launch_cfg<BN, EPI_BIAS_RESID_F32, CTAS>(a, st, sms, s);
-    case EPI_PATCH_F32: return launch_cfg<BN, EPI_PATCH_F32, CTAS>(a, st, sms, s);
     case EPI_F32: return launch_cfg<BN, EPI_F32, CTAS>(a, st, sms, s);
     case EPI_LNFOLD_BF16: return launch_cfg<BN, EPI_LNFOLD_BF16, CTAS>(a, st, sms, s);
     case EPI_LNFOLD_GELU_BF16: return launch_cfg<BN, EPI_LNFOLD_GELU_BF16, CTAS>(a, st, sms, s);

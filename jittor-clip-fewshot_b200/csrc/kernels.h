@@ -13,7 +13,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,       // out_bf16[m,n]  = acc + bias[n]                       (QKV projection)
   EPI_BIAS_GELU_BF16 = 1,  // out_bf16[m,n]  = quickgelu(acc + bias[n])            (MLP c_fc)
   EPI_BIAS_RESID_F32 = 2,  // out_f32[m,n]  += acc + bias[n]                       (out_proj / c_proj + residual)
-  EPI_PATCH_F32 = 3,       // out_f32[row(m),n] = acc + pos[1 + m % T_in, n], row(m) = (m / T_in) * T_out + 1 + m % T_in
+  // 3 was the conv1 scatter epilogue (direct stores); conv1 now leaves through EPI_F32 and the embed kernel scatters
   EPI_F32 = 4,             // out_f32[m,n]   = acc (+ bias[n] if given)            (tests / generic)
   // ---- LayerNorm folded into the GEMMs (no stand-alone LayerNorm pass over the residual stream) ----
   // LN(x) W^T = r (x (g*W)^T) - r mu S + c  with  S[n] = sum_k g[k] W[n,k],  c[n] = sum_k b[k] W[n,k] + bias[n]:
@@ -35,8 +35,6 @@ struct GemmArgs {
   int epilogue = EPI_BIAS_BF16;
   void* out = nullptr;               // bf16 or fp32 according to the epilogue
   int64_t ldo = 0;
-  const float* pos = nullptr;        // EPI_PATCH_F32: positional embedding [T_out, N]
-  int tokens_in = 49, tokens_out = 50;
   float* stats = nullptr;            // LNFOLD: in, LNPREP: out.  [M, stats_slots, 2] fp32 partial (sum, sum of squares)
   int stats_slots = 0;               // partial slots per row (= N / 256 of the producer; the consumer adds them up)
   const float* colsum = nullptr;     // LNFOLD: S[N]

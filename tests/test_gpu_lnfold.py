@@ -1,5 +1,5 @@
 """GPU: the three LayerNorm schedules of the tower (JCB_LN_FOLD = 0 stand-alone LayerNorm passes, 1 = ln_1 folded
-into c_proj's epilogue + the QKV GEMM (default), 2 = ln_2 folded as well) all meet the embedding tolerance against
+into c_proj's epilogue + the QKV GEMM, 2 = ln_2 folded as well (default)) all meet the embedding tolerance against
 the fp32 oracle.  The mode is read when the context is created, hence one subprocess per mode."""
 import os
 import subprocess
