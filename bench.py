@@ -329,18 +329,20 @@ def main():
         per_kernel[k] = ent
     kernel_ms_step = sum(e["ms_per_step"] for e in per_kernel.values())
     top = max(gemm, key=lambda k: gemm[k]["ms"]) if gemm else None
-    names = {"gemm_fc1": "gemm_bf16_tcgen05_2cta_kernel<256, EPI_BIAS_GELU_BF16> (MLP c_fc, M x 3072 x 768)",
-             "gemm_fc2": "gemm_bf16_tcgen05_2cta_kernel<256, EPI_BIAS_RESID_F32> (MLP c_proj, M x 768 x 3072)",
-             "gemm_qkv": "gemm_bf16_tcgen05_2cta_kernel<256, EPI_BIAS_BF16> (packed QKV, M x 2304 x 768)",
-             "gemm_out": "gemm_bf16_tcgen05_2cta_kernel<256, EPI_BIAS_RESID_F32> (attention out_proj, M x 768 x 768)",
-             "gemm_patch": "gemm_bf16_tcgen05_2cta_kernel<256, EPI_PATCH_F32> (conv1 as im2col GEMM)"}
+    fold = int(os.environ.get("JCB_LN_FOLD", "2"))
+    k2 = "gemm_bf16_tcgen05_2cta_kernel<256, %s>"
+    names = {"gemm_fc1": k2 % ("EPI_LNFOLD_GELU_BF16" if fold >= 2 else "EPI_BIAS_GELU_BF16") + " (MLP c_fc, M x 3072 x 768)",
+             "gemm_fc2": k2 % ("EPI_RESID_LNPREP_LONG" if fold >= 1 else "EPI_BIAS_RESID_F32") + " (MLP c_proj, M x 768 x 3072)",
+             "gemm_qkv": k2 % ("EPI_LNFOLD_BF16" if fold >= 1 else "EPI_BIAS_BF16") + " (packed QKV, M x 2304 x 768)",
+             "gemm_out": k2 % ("EPI_RESID_LNPREP_SHORT" if fold >= 2 else "EPI_BIAS_RESID_F32") + " (attention out_proj, M x 768 x 768)",
+             "gemm_patch": k2 % "EPI_F32" + " (conv1 as im2col GEMM)"}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tj = json.load(f)
         launches_per_step_top = per_kernel[top]["launches_per_step"]
         views_per_launch = I * V * model.visual.layers / launches_per_step_top
-        if abs(views_per_launch - tj["views_per_launch"]) < 0.5:
+        if abs(views_per_launch - tj["views_per_launch"]) < 0.5 and tj.get("ln_fold", 1) == fold:
             traffic = tj["per_kernel_bytes"].get(top)
     except Exception:  # noqa: BLE001
         pass
