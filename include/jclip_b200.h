@@ -76,6 +76,13 @@ int jcb_ctx_set_stream(jcb_ctx* ctx, void* cuda_stream);
  * for host input, so that the copy of pass i+1 overlaps the compute of pass i. */
 int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
 int jcb_ctx_set_host_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
+/* Opt-in schedule for the image tower (default off; env JCB_CLS_ONLY_LAST_BLOCK=1 sets the initial value): run the
+ * LAST transformer block on the class-token row of every view only.  `encode_image` returns
+ * ln_post(x[:, 0, :]) @ proj (jclip/model.py:121-124), so after that block's keys and values no other token row
+ * reaches the result; the reference computes them anyway.  Embeddings agree with the full schedule to rounding
+ * (different attention summation order for that one row).  Ignored by jcb_vit_debug_tokens consumers that read
+ * other rows of the last block: with the option on, only row 0 of every view is defined there. */
+int jcb_ctx_set_cls_only_last_block(jcb_ctx* ctx, int on);
 /* Wait for the context's stream and report any device-side kernel status. */
 int jcb_sync(jcb_ctx* ctx);
 const char* jcb_last_error(const jcb_ctx* ctx);

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "jcb_ctx_set_stream": (c_int, [c_void_p, c_void_p]),
     "jcb_ctx_set_chunk_views": (c_int, [c_void_p, c_int64]),
     "jcb_ctx_set_host_chunk_views": (c_int, [c_void_p, c_int64]),
+    "jcb_ctx_set_cls_only_last_block": (c_int, [c_void_p, c_int]),
     "jcb_sync": (c_int, [c_void_p]),
     "jcb_last_error": (c_char_p, [c_void_p]),
     "jcb_ctx_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),

@@ -36,6 +36,7 @@ struct jcb_ctx {
   cudaEvent_t ticket_done[JCB_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
   int* ticket_status = nullptr;      // pinned host, [JCB_MAX_INFLIGHT]: device status word copied behind each submission
   int64_t next_ticket = 0, waited_ticket = 0;
+  int cls_only_last = 0;             // opt-in: last block of the image tower on the class-token rows only (see tower_blocks)
   bool overlapped = false;           // this submission was enqueued behind an un-waited one: its first upload is hidden
   int64_t launches = 0;
   int ln_fold = 2;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
@@ -282,7 +283,7 @@ int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16*
              const float* bias, int epi, void* out, int64_t ldo, float* stats = nullptr, int stats_slots = 0,
              const float* colsum = nullptr, void* out2 = nullptr) {
   GemmArgs g;
-  g.stats = stats; g.stats_slots = stats_slots; g.colsum = colsum; g.out2 = out2; g.ldo2 = N;
+  g.stats = stats; g.stats_slots = stats_slots; g.colsum = colsum; g.out2 = out2; g.ldo2 = N;   // out2 / stats are dense
   g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo;
   // algorithmic bytes: A + B read once, C written once (read-modify-write for the residual epilogue)
@@ -296,7 +297,7 @@ int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16*
 
 // L pre-LN blocks on `n` sequences of t->tokens tokens: w.ln_out holds ln_1 of block 0 on entry, w.tokens the
 // fp32 residual stream; on exit w.tokens is the output of the last block (reference jclip/model.py:59-62).
-int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
+int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal, bool cls_row0 = false) {
   jcb_ctx* ctx = t->ctx;
   cudaStream_t s = ctx->stream;
   const int W = t->W, T = t->tokens;
@@ -315,9 +316,28 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal) {
     //                 stalled an already starved main loop); with 5 stages a net gain of 1.5-3 ms / step.
     const bool fold2 = ctx->ln_fold >= 2;
     const int slots = (W + 255) / 256;
+    const bool cls_only = cls_row0 && ctx->cls_only_last && fold2 && !causal && T <= 64;
     for (int l = 0; l < t->L; ++l) {
       const LayerDev& L = t->layers[l];
       if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, w.stats, slots, L.in_S))) return rc;
+      if (cls_only && l + 1 == t->L) {
+        // Opt-in (jcb_ctx_set_cls_only_last_block, default off): the caller of the image tower reads nothing but
+        // ln_post(x[:, 0, :]) @ proj (jclip/model.py:121-124), so after the last block's K and V only the class-token
+        // row of every view is live.  Attention, out_proj, ln_2, c_fc and c_proj of that block run on n rows instead
+        // of n * T: the same GEMM kernels with M = n, the residual stream addressed as [n, T * W] (leading dimension
+        // T * W: row v = class token of view v), the bf16 copy / row statistics / MLP hidden dense.  Per output
+        // element the GEMM arithmetic is identical (same k order); the 0.53 GFLOP per view it skips (6 % of the
+        // tower) were never part of the result.  Not the default: bench.py's headline numbers run the full block.
+        const int Mc = static_cast<int>(n);
+        LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * 64, static_cast<double>(n) * T * W * 4 + static_cast<double>(n) * W * 4,
+                 launch_attention_cls(w.qkv, n, T, t->heads, w.attn, s));
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, Mc, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens,
+                           static_cast<int64_t>(T) * W, w.stats, slots, nullptr, w.ln_out))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_wf, Mc, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W, w.stats, slots, L.fc_S))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, Mc, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens,
+                           static_cast<int64_t>(T) * W))) return rc;
+        break;
+      }
       LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
                launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms));
       if (fold2) {
@@ -375,7 +395,7 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->vpt, v->cfg.vpt_tokens, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
                               v->layers[0].ln1_b, w.ln_out, s, (ctx->ln_fold && v->layers[0].in_wf) ? w.stats : nullptr, (W + 255) / 256,
                               patch_out));
-  return tower_blocks(v, n, w, 0);
+  return tower_blocks(v, n, w, 0, /*cls_row0=*/true);   // the tail reads token row 0 only
 }
 
 // Views per pass through the tower.  Host input of a blocking call is cut into small passes so that the upload of
@@ -479,6 +499,8 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   {
+    const char* env_cls = getenv("JCB_CLS_ONLY_LAST_BLOCK");
+    ctx->cls_only_last = (env_cls && env_cls[0] == '1') ? 1 : 0;
     const char* env = getenv("JCB_LN_FOLD");
     ctx->ln_fold = env ? atoi(env) : 2;   // default: both LayerNorms folded (measured, same box: 75.7-76.0 vs
                                           // 77.2-78.7 ms / step for ln_1 only); see tower_blocks
@@ -551,6 +573,12 @@ int jcb_ctx_set_chunk_views(jcb_ctx* ctx, int64_t chunk_views) {
 int jcb_ctx_set_host_chunk_views(jcb_ctx* ctx, int64_t chunk_views) {
   if (!ctx || chunk_views < 1 || chunk_views > 40000) return ctx ? fail(ctx, JCB_E_INVALID, "chunk_views out of range") : JCB_E_INVALID;
   ctx->host_chunk_views = chunk_views;
+  return JCB_OK;
+}
+
+int jcb_ctx_set_cls_only_last_block(jcb_ctx* ctx, int on) {
+  if (!ctx) return JCB_E_INVALID;
+  ctx->cls_only_last = on ? 1 : 0;
   return JCB_OK;
 }
 

@@ -82,6 +82,9 @@ cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int
 // T <= 64, even head count; JCB_ATT_IMPL=mma forces the mma.sync kernel); otherwise the mma.sync kernel (attention.cu)
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
                              cudaStream_t stream, int causal = 0, int* dev_status = nullptr, int num_sms = 0);
+// query row 0 only (no mask, T <= 64): out [n_views, W] bf16, dense
+cudaError_t launch_attention_cls(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                                 cudaStream_t stream);
 bool attention_tc_supported(int T, int heads, int causal);
 cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
                                 cudaStream_t stream, int* dev_status, int num_sms);

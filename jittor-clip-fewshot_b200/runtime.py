@@ -41,6 +41,10 @@ class Context:
     def set_host_chunk_views(self, n):
         check(self.lib.jcb_ctx_set_host_chunk_views(self.handle, int(n)), self.handle)
 
+    def set_cls_only_last_block(self, on):
+        """Opt-in: last block of the image tower on the class-token rows only (include/jclip_b200.h)."""
+        check(self.lib.jcb_ctx_set_cls_only_last_block(self.handle, int(bool(on))), self.handle)
+
     def sync(self):
         check(self.lib.jcb_sync(self.handle), self.handle)
 

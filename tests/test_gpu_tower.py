@@ -203,3 +203,35 @@ def test_real_lora_pickle_if_present(jb, cuda_dev, tmp_path):
     jb.load_lora(args, layers2, path)
     f_b = model2.visual(x, apply_clip_norm=True, normalize=True)
     assert torch.equal(f_a, f_b)
+
+
+@pytest.mark.parametrize("vpt", [0, 4])
+def test_cls_only_last_block_matches_full_schedule(jb, cuda_dev, vpt):
+    """Opt-in schedule (jcb_ctx_set_cls_only_last_block): the last block on the class-token rows only.  Same
+    embeddings as the full schedule to rounding (one attention row summed in another order), same distance to the
+    fp32 oracle; 50- and 54-token towers; batch sizes around the 256-row GEMM tile."""
+    from oracle import vit_encode_image
+    sd = jb.synth.make_vit_state_dict(seed=2, vpt_tokens=vpt)
+    design = dict(jb.clip.IVLP_DESIGN) if vpt else None
+    model = jb.jclip.build_model(sd, design) if design else jb.jclip.build_model(sd)
+    layers = jb.apply_lora(_args(), model)
+    lora = jb.synth.make_lora(seed=9, b_std=0.3)
+    for i, layer in enumerate(layers):
+        for name, (A, B) in lora[i].items():
+            getattr(layer, name).w_lora_A.data = A
+            getattr(layer, name).w_lora_B.data = B
+    ctx = jb.get_context(cuda_dev)
+    imgs = jb.synth.make_views(6, 1, 7).reshape(7, 3, 224, 224)
+    ref = vit_encode_image(sd, imgs, lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    big = torch.from_numpy(jb.synth.make_views(7, 3, 87).reshape(261, 3, 224, 224)).to(cuda_dev)
+    x = torch.from_numpy(imgs).to(cuda_dev)
+    try:
+        full, full_big = model.visual(x, apply_clip_norm=True, normalize=True).cpu(), model.visual(big, apply_clip_norm=True, normalize=True).cpu()
+        ctx.set_cls_only_last_block(True)
+        fast, fast_big = model.visual(x, apply_clip_norm=True, normalize=True).cpu(), model.visual(big, apply_clip_norm=True, normalize=True).cpu()
+    finally:
+        ctx.set_cls_only_last_block(False)
+    assert _cos(fast, ref).min() >= 0.9995
+    assert _cos(fast, full).min() >= 0.99999 and (fast - full).abs().max() <= 2e-3
+    assert _cos(fast_big, full_big).min() >= 0.99999 and (fast_big - full_big).abs().max() <= 2e-3
+    assert torch.equal(model.visual(x, apply_clip_norm=True, normalize=True).cpu(), full)     # switched off again
