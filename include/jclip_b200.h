@@ -207,7 +207,9 @@ typedef struct jcb_view_job {
   int32_t filter, flip, reserved;
 } jcb_view_job;
 /* out_dev [n_jobs, 3, size, size] uint8 (planar, the layout jcb_encode_image / jcb_pipeline take with
- * JCB_IMG_U8).  images / jobs are host arrays; they are validated and copied. */
+ * JCB_IMG_U8).  images / jobs are host arrays; they are validated and copied.  When src_dev is 4-byte aligned the
+ * source is read as whole aligned 32-bit words, so the buffer must be readable up to the next multiple of 4 bytes
+ * past the last image (any cudaMalloc / torch allocation is); an unaligned src_dev takes a slower byte-wise path. */
 int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
                   const jcb_view_job* jobs, int64_t n_jobs, int32_t size, uint8_t* out_dev);
 

@@ -36,6 +36,11 @@ struct jcb_ctx {
   cudaEvent_t ticket_done[JCB_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
   int* ticket_status = nullptr;      // pinned host, [JCB_MAX_INFLIGHT]: device status word copied behind each submission
   int64_t next_ticket = 0, waited_ticket = 0;
+  // jcb_tta_views: pinned, double-buffered staging of the per-view plan (no stream synchronisation in the call)
+  void* tta_plan_host[2] = {nullptr, nullptr};
+  size_t tta_plan_bytes[2] = {0, 0};
+  cudaEvent_t tta_plan_copied[2] = {nullptr, nullptr};
+  int tta_turn = 0;
   int cls_only_last = 0;             // opt-in: last block of the image tower on the class-token rows only (see tower_blocks)
   bool overlapped = false;           // this submission was enqueued behind an un-waited one: its first upload is hidden
   int64_t launches = 0;
@@ -544,6 +549,10 @@ int jcb_ctx_destroy(jcb_ctx* ctx) {
   for (int i = 0; i < JCB_MAX_INFLIGHT; ++i)
     if (ctx->ticket_done[i]) cudaEventDestroy(ctx->ticket_done[i]);
   if (ctx->ticket_status) cudaFreeHost(ctx->ticket_status);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->tta_plan_host[i]) cudaFreeHost(ctx->tta_plan_host[i]);
+    if (ctx->tta_plan_copied[i]) cudaEventDestroy(ctx->tta_plan_copied[i]);
+  }
   for (auto e : ctx->prof_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1066,9 +1075,22 @@ int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* ima
     if (rc) return rc;
     uint8_t* plan_dev = static_cast<uint8_t*>(ctx->ws);
     uint8_t* tmp = plan_dev + plan_b;
-    // the plan lives in pageable host memory: a synchronous-with-respect-to-host copy on the stream
-    CUDA_TRY(ctx, cudaMemcpyAsync(plan_dev, plan.data(), plan.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the plan goes through one of two pinned buffers, so the call never waits for the stream: a buffer is reused only
+    // after the upload that last read it has completed (its event; two calls back, normally long done)
+    const int t = ctx->tta_turn;
+    ctx->tta_turn ^= 1;
+    if (ctx->tta_plan_copied[t]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->tta_plan_copied[t]));
+    else CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->tta_plan_copied[t], cudaEventDisableTiming));
+    if (ctx->tta_plan_bytes[t] < plan.size()) {
+      if (ctx->tta_plan_host[t]) cudaFreeHost(ctx->tta_plan_host[t]);
+      ctx->tta_plan_host[t] = nullptr;
+      ctx->tta_plan_bytes[t] = 0;
+      CUDA_TRY(ctx, cudaMallocHost(&ctx->tta_plan_host[t], plan.size()));
+      ctx->tta_plan_bytes[t] = plan.size();
+    }
+    memcpy(ctx->tta_plan_host[t], plan.data(), plan.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(plan_dev, ctx->tta_plan_host[t], plan.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->tta_plan_copied[t], ctx->stream));
     double macs = 0;
     for (int64_t i = 0; i < nj; ++i) macs += 3.0 * size * (jobs[j0 + i].crop_h + size);
     LAUNCH_P(ctx, JCB_KC_TTA, 0, static_cast<double>(nj) * 3 * size * size,

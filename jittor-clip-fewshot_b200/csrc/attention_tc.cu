@@ -49,6 +49,9 @@ struct AtcDev {
   int* status;
 };
 
+// TCT = the token count as a compile-time constant (50 = plain tower, 54 = IVLP / VPT tower) so the softmax touches only
+// the valid keys; 0 = run-time T (any T <= 64).
+template <int TCT>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut,
                          const AtcDev p) {
@@ -172,22 +175,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
       tmem_ld_32x32b_x32(lane_base + S_COL + static_cast<uint32_t>(head * 64), *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
       tmem_ld_32x32b_x32(lane_base + S_COL + static_cast<uint32_t>(head * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
       tmem_ld_wait();
-      float mx = -INFINITY;
+      // row maximum over the valid keys and the exponentials' sum, each as four independent chains (a single chain of
+      // 64 dependent FMNMX / FADD was a quarter of the per-item critical path); 1/8 and log2(e) ride in the FMA
+      const int T = TCT > 0 ? TCT : p.T;
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float s = c < p.T ? __uint_as_float(sv[c]) * scale_log2 : -INFINITY;
-        sv[c] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
-      }
-      float sum = 0.f;
+      for (int c = 0; c < 64; ++c)
+        if (c < T) m4[c & 3] = fmaxf(m4[c & 3], __uint_as_float(sv[c]));
+      const float nmx = -fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pv[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float p0 = ex2_approx(__uint_as_float(sv[2 * c]) - mx);
-        const float p1 = ex2_approx(__uint_as_float(sv[2 * c + 1]) - mx);
-        sum += p0 + p1;
+        const float p0 = 2 * c < T ? ex2_approx(fmaf(__uint_as_float(sv[2 * c]), scale_log2, nmx)) : 0.f;
+        const float p1 = 2 * c + 1 < T ? ex2_approx(fmaf(__uint_as_float(sv[2 * c + 1]), scale_log2, nmx)) : 0.f;
+        s4[c & 3] += p0 + p1;
         pv[c] = pack_bf16x2(p0, p1);
       }
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       tmem_st_32x32b_x32(lane_base + P_COL + static_cast<uint32_t>(head * 32), pv);
       tmem_st_wait();
       tc_fence_before();
@@ -270,11 +275,13 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, int64_t n_views, int T
     return cudaErrorInvalidValue;
   if (!make_tmap_heads(&tmOut, out, static_cast<uint64_t>(n_views), static_cast<uint64_t>(T), static_cast<uint64_t>(heads)))
     return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  auto kernel = T == 50 ? attention_tcgen05_kernel<50> : T == 54 ? attention_tcgen05_kernel<54> : attention_tcgen05_kernel<0>;
+  static bool attr_set[3] = {false, false, false};
+  const int which = T == 50 ? 0 : T == 54 ? 1 : 2;
+  if (!attr_set[which]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[which] = true;
   }
   AtcDev p;
   p.pairs = heads / 2;
@@ -283,7 +290,7 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, int64_t n_views, int T
   p.status = dev_status;
   const long long max_ctas = 2LL * num_sms;
   const unsigned grid = static_cast<unsigned>(p.n_items < max_ctas ? p.n_items : max_ctas);
-  attention_tcgen05_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(tmQKV, tmOut, p);
+  kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(tmQKV, tmOut, p);
   return cudaGetLastError();
 }
 

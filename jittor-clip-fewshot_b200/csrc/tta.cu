@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -57,8 +58,8 @@ __device__ __forceinline__ double filt(int kind, double x) {
 }
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for ONE output index X of an axis.
-// Writes the taps to k[0..ksize) (zero padded), returns (xmin, n) through the references.
-__device__ __forceinline__ void axis_coeffs(const AxisDev& a, int kind, int X, int* k, int& xmin, int& n) {
+// Writes the taps to k[0], k[kstride], ... (ksize of them, zero padded), returns (xmin, n) through the references.
+__device__ __forceinline__ void axis_coeffs(const AxisDev& a, int kind, int X, int* k, int kstride, int& xmin, int& n) {
   const double center = __dmul_rn(__dadd_rn(static_cast<double>(X), 0.5), a.scale);   // in0 = 0
   int lo = __double2int_rz(__dadd_rn(__dsub_rn(center, a.support), 0.5));
   if (lo < 0) lo = 0;
@@ -75,32 +76,112 @@ __device__ __forceinline__ void axis_coeffs(const AxisDev& a, int kind, int X, i
     double w = filt(kind, arg);
     if (ww != 0.0) w = __ddiv_rn(w, ww);
     const double f = __dmul_rn(w, static_cast<double>(1 << PREC));
-    k[x] = w < 0.0 ? __double2int_rz(__dadd_rn(-0.5, f)) : __double2int_rz(__dadd_rn(0.5, f));
+    k[x * kstride] = w < 0.0 ? __double2int_rz(__dadd_rn(-0.5, f)) : __double2int_rz(__dadd_rn(0.5, f));
   }
-  for (int x = cnt; x < a.ksize; ++x) k[x] = 0;
+  for (int x = cnt; x < a.ksize; ++x) k[x * kstride] = 0;
   xmin = lo;
   n = cnt;
 }
 
-__device__ __forceinline__ uint8_t clip8(int v) {
+__device__ __forceinline__ uint32_t clip8(int v) {
   v >>= PREC;
-  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+  return static_cast<uint32_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// byte B (compile-time) of a little-endian word array
+template <int B, int N>
+__device__ __forceinline__ int byte_of(const uint32_t (&a)[N]) {
+  return static_cast<int>(__byte_perm(a[B >> 2], 0u, 0x4440u + (B & 3)));   // PRMT: byte B & 3, zero extended
 }
 
 // ---------------------------------------------------------------------------------- horizontal pass
+// One thread = one intermediate pixel (row r, column xx), all three channels.  The taps of a pixel are 3 * n
+// CONTIGUOUS bytes of the interleaved source row, at an arbitrary alignment: they are fetched as aligned 32-bit words
+// and realigned with funnel shifts, so a 7-tap pixel costs 6 loads instead of 21 single-byte loads (the byte-load
+// version was bound by the LSU, profiles/r01e_tta_full.md).  Weights are zero padded to KW, bytes past the last tap
+// are multiplied by zero (and never loaded past the last word that holds a tap).
+template <int KW>
+__device__ __forceinline__ void h_rows_fast(const uint8_t* __restrict__ row0p, long long pitch, const int* __restrict__ kk,
+                                            const int* __restrict__ xmin, const int* __restrict__ cnt, int S, int r_begin,
+                                            int r_end, uint8_t* __restrict__ dst, long long plane) {
+  constexpr int NA = (3 * KW + 3) / 4;   // aligned words that hold the 3 * KW tap bytes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // a lane keeps one output column (its KW weights and window live in registers) and walks down the rows of the strip
+  for (int xx = lane; xx < S; xx += 32) {
+    int wt[KW];
+#pragma unroll
+    for (int x = 0; x < KW; ++x) wt[x] = kk[x * S + xx];
+    const uint8_t* colp = row0p + 3LL * xmin[xx];
+    const int nb = 3 * cnt[xx] + 3;
+    uint8_t* d = dst + xx;
+    for (int r = r_begin + warp; r < r_end; r += nwarps) {
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(colp + r * pitch);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+      const int mis = static_cast<int>(addr & 3);
+      const int nw = (mis + nb) >> 2;
+      uint32_t w[NA + 1];
+#pragma unroll
+      for (int j = 0; j <= NA; ++j) w[j] = j < nw ? __ldg(wp + j) : 0u;
+      uint32_t a[NA];
+#pragma unroll
+      for (int j = 0; j < NA; ++j) a[j] = __funnelshift_r(w[j], w[j + 1], 8 * mis);
+      int a0 = 1 << (PREC - 1), a1 = a0, a2 = a0;
+      // static unroll over the taps: the byte positions must be compile-time constants (one PRMT per byte)
+      auto tap = [&](auto X) {
+        constexpr int x = decltype(X)::value;
+        a0 += byte_of<3 * x + 0>(a) * wt[x];
+        a1 += byte_of<3 * x + 1>(a) * wt[x];
+        a2 += byte_of<3 * x + 2>(a) * wt[x];
+      };
+      tap(std::integral_constant<int, 0>{});
+      tap(std::integral_constant<int, 1>{});
+      tap(std::integral_constant<int, 2>{});
+      if constexpr (KW > 3) { tap(std::integral_constant<int, 3>{}); tap(std::integral_constant<int, 4>{}); }
+      if constexpr (KW > 5) { tap(std::integral_constant<int, 5>{}); tap(std::integral_constant<int, 6>{}); }
+      if constexpr (KW > 7) { tap(std::integral_constant<int, 7>{}); tap(std::integral_constant<int, 8>{}); }
+      uint8_t* dr = d + static_cast<long long>(r) * S;
+      dr[0] = static_cast<uint8_t>(clip8(a0));
+      dr[plane] = static_cast<uint8_t>(clip8(a1));
+      dr[2 * plane] = static_cast<uint8_t>(clip8(a2));
+    }
+  }
+}
+
+// any tap count: byte loads, run-time loop (large source images: scale > 4)
+__device__ __forceinline__ void h_rows_generic(const uint8_t* __restrict__ row0p, long long pitch, const int* __restrict__ kk,
+                                               const int* __restrict__ xmin, const int* __restrict__ cnt, int S,
+                                               int r_begin, int r_end, uint8_t* __restrict__ dst, long long plane) {
+  for (int p = threadIdx.x; p < (r_end - r_begin) * S; p += blockDim.x) {
+    const int r = r_begin + p / S, xx = p % S;
+    const uint8_t* s = row0p + r * pitch + 3LL * xmin[xx];
+    const int n = cnt[xx];
+    int a0 = 1 << (PREC - 1), a1 = a0, a2 = a0;
+    for (int x = 0; x < n; ++x) {
+      const int wt = kk[x * S + xx];
+      a0 += static_cast<int>(__ldg(s + 3 * x + 0)) * wt;
+      a1 += static_cast<int>(__ldg(s + 3 * x + 1)) * wt;
+      a2 += static_cast<int>(__ldg(s + 3 * x + 2)) * wt;
+    }
+    uint8_t* d = dst + static_cast<long long>(r) * S + xx;
+    d[0] = static_cast<uint8_t>(clip8(a0));
+    d[plane] = static_cast<uint8_t>(clip8(a1));
+    d[2 * plane] = static_cast<uint8_t>(clip8(a2));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 resample_h_kernel(const uint8_t* __restrict__ src, const ViewDev* __restrict__ views, int S, int kmax,
-                  uint8_t* __restrict__ tmp) {
+                  uint8_t* __restrict__ tmp, int words_ok) {
   extern __shared__ __align__(16) int rs_smem[];
   const ViewDev v = views[blockIdx.y];
   const int r_begin = blockIdx.x * RBH;
   if (r_begin >= v.n_rows) return;
-  int* kk = rs_smem;                 // [S][kmax]
+  int* kk = rs_smem;                 // [kmax][S]: tap x of column xx at kk[x * S + xx] (a warp reads consecutive words)
   int* xmin = kk + S * kmax;         // [S]
   int* cnt = xmin + S;               // [S]
   for (int xx = threadIdx.x; xx < S; xx += blockDim.x) {
     int lo, n;
-    axis_coeffs(v.h, v.filter, xx + v.h.off, kk + xx * kmax, lo, n);
+    axis_coeffs(v.h, v.filter, xx + v.h.off, kk + xx, S, lo, n);
     xmin[xx] = lo;
     cnt[xx] = n;
   }
@@ -108,47 +189,64 @@ resample_h_kernel(const uint8_t* __restrict__ src, const ViewDev* __restrict__ v
   const int r_end = min(r_begin + RBH, v.n_rows);
   const long long pitch = 3LL * v.src_w;
   const long long plane = static_cast<long long>(v.n_rows) * S;
-  for (int p = threadIdx.x; p < (r_end - r_begin) * S; p += blockDim.x) {
-    const int r = r_begin + p / S, xx = p % S;
-    const uint8_t* s = src + v.src_off + (v.top + v.row0 + r) * pitch + 3LL * (v.left + xmin[xx]);
-    const int* k = kk + xx * kmax;
-    const int n = cnt[xx];
-    int a0 = 1 << (PREC - 1), a1 = a0, a2 = a0;
-    for (int x = 0; x < n; ++x) {
-      const int w = k[x];
-      a0 += static_cast<int>(__ldg(s + 3 * x + 0)) * w;
-      a1 += static_cast<int>(__ldg(s + 3 * x + 1)) * w;
-      a2 += static_cast<int>(__ldg(s + 3 * x + 2)) * w;
-    }
-    uint8_t* d = tmp + v.tmp_off + static_cast<long long>(r) * S + xx;
-    d[0] = clip8(a0);
-    d[plane] = clip8(a1);
-    d[2 * plane] = clip8(a2);
+  const uint8_t* row0p = src + v.src_off + (v.top + v.row0) * pitch + 3LL * v.left;
+  uint8_t* dst = tmp + v.tmp_off;
+  switch (words_ok ? v.h.ksize : 0) {   // ksize = 2 * ceil(support) + 1: odd, uniform over the CTA
+    case 3: h_rows_fast<3>(row0p, pitch, kk, xmin, cnt, S, r_begin, r_end, dst, plane); break;
+    case 5: h_rows_fast<5>(row0p, pitch, kk, xmin, cnt, S, r_begin, r_end, dst, plane); break;
+    case 7: h_rows_fast<7>(row0p, pitch, kk, xmin, cnt, S, r_begin, r_end, dst, plane); break;
+    case 9: h_rows_fast<9>(row0p, pitch, kk, xmin, cnt, S, r_begin, r_end, dst, plane); break;
+    default: h_rows_generic(row0p, pitch, kk, xmin, cnt, S, r_begin, r_end, dst, plane);
   }
 }
 
 // ---------------------------------------------------------------------------------- vertical pass
-__global__ void __launch_bounds__(256)
-resample_v_kernel(const uint8_t* __restrict__ tmp, const ViewDev* __restrict__ views, int S, int kmax,
-                  uint8_t* __restrict__ out) {
-  extern __shared__ __align__(16) int rs_smem[];
-  const ViewDev v = views[blockIdx.y];
-  const int y_begin = blockIdx.x * RBV;
-  if (y_begin >= S) return;
-  const int rows = min(RBV, S - y_begin);
-  int* kk = rs_smem;                 // [RBV][kmax]
-  int* ymin = kk + RBV * kmax;       // [RBV]
-  int* cnt = ymin + RBV;             // [RBV]
-  for (int yy = threadIdx.x; yy < rows; yy += blockDim.x) {
-    int lo, n;
-    axis_coeffs(v.v, v.filter, y_begin + yy + v.v.off, kk + yy * kmax, lo, n);
-    ymin[yy] = lo - v.row0;          // rows of the intermediate are stored from row0 on (Pillow: ybox_first)
-    cnt[yy] = n;
+// One thread = four adjacent output pixels of one channel: every tap is one aligned 32-bit load of the planar
+// intermediate (a warp reads 128 contiguous bytes), the four results leave as one 32-bit store (byte-reversed and
+// mirrored in x for a flipped view).  Needs S % 4 == 0 and 4-byte aligned buffers; otherwise the byte version runs.
+template <int KW>
+__device__ __forceinline__ void v_rows_fast(const uint8_t* __restrict__ t, long long plane, const int* __restrict__ kk,
+                                            int kmax, const int* __restrict__ ymin, const int* __restrict__ cnt, int S,
+                                            int y_begin, int rows, int flip, uint8_t* __restrict__ o) {
+  const int G = S >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const long long plane_w = plane >> 2;          // plane = n_rows * S, a multiple of 4
+  // a warp keeps one output row (its KW weights live in registers) and sweeps the 3 * G words of the three channels
+  for (int yy = warp; yy < rows; yy += nwarps) {
+    const int n = cnt[yy];
+    int wt[KW];
+#pragma unroll
+    for (int y = 0; y < KW; ++y) wt[y] = kk[yy * kmax + y];
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(t + static_cast<long long>(ymin[yy]) * S);
+    for (int e = lane; e < 3 * G; e += 32) {
+      const int c = (e >= G) + (e >= 2 * G);
+      const int g = e - c * G;
+      const uint32_t* s = base + c * plane_w + g;
+      int a0 = 1 << (PREC - 1), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+      for (int y = 0; y < KW; ++y) {
+        if (y < n) {                 // rows past the window may lie outside the intermediate
+          const uint32_t w = __ldg(s + y * G);
+          a0 += static_cast<int>(__byte_perm(w, 0u, 0x4440u)) * wt[y];
+          a1 += static_cast<int>(__byte_perm(w, 0u, 0x4441u)) * wt[y];
+          a2 += static_cast<int>(__byte_perm(w, 0u, 0x4442u)) * wt[y];
+          a3 += static_cast<int>(w >> 24) * wt[y];
+        }
+      }
+      uint32_t r4 = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
+      int go = g;
+      if (flip) {                       // RandomHorizontalFlip acts on the finished S x S crop
+        r4 = __byte_perm(r4, 0u, 0x0123);
+        go = G - 1 - g;
+      }
+      reinterpret_cast<uint32_t*>(o + (static_cast<long long>(c) * S + y_begin + yy) * S)[go] = r4;
+    }
   }
-  __syncthreads();
-  const long long plane = static_cast<long long>(v.n_rows) * S;
-  const uint8_t* t = tmp + v.tmp_off;
-  uint8_t* o = out + static_cast<long long>(blockIdx.y) * 3 * S * S;
+}
+
+__device__ __forceinline__ void v_rows_generic(const uint8_t* __restrict__ t, long long plane, const int* __restrict__ kk,
+                                               int kmax, const int* __restrict__ ymin, const int* __restrict__ cnt, int S,
+                                               int y_begin, int rows, int flip, uint8_t* __restrict__ o) {
   for (int p = threadIdx.x; p < rows * S; p += blockDim.x) {
     const int yy = p / S, xx = p % S;
     const int* k = kk + yy * kmax;
@@ -161,11 +259,42 @@ resample_v_kernel(const uint8_t* __restrict__ tmp, const ViewDev* __restrict__ v
       a1 += static_cast<int>(s[plane + static_cast<long long>(y) * S]) * w;
       a2 += static_cast<int>(s[2 * plane + static_cast<long long>(y) * S]) * w;
     }
-    const int xo = v.flip ? S - 1 - xx : xx;           // RandomHorizontalFlip acts on the finished S x S crop
+    const int xo = flip ? S - 1 - xx : xx;
     uint8_t* d = o + static_cast<long long>(y_begin + yy) * S + xo;
-    d[0] = clip8(a0);
-    d[static_cast<long long>(S) * S] = clip8(a1);
-    d[2LL * S * S] = clip8(a2);
+    d[0] = static_cast<uint8_t>(clip8(a0));
+    d[static_cast<long long>(S) * S] = static_cast<uint8_t>(clip8(a1));
+    d[2LL * S * S] = static_cast<uint8_t>(clip8(a2));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+resample_v_kernel(const uint8_t* __restrict__ tmp, const ViewDev* __restrict__ views, int S, int kmax,
+                  uint8_t* __restrict__ out, int words_ok) {
+  extern __shared__ __align__(16) int rs_smem[];
+  const ViewDev v = views[blockIdx.y];
+  const int y_begin = blockIdx.x * RBV;
+  if (y_begin >= S) return;
+  const int rows = min(RBV, S - y_begin);
+  int* kk = rs_smem;                 // [RBV][kmax]: all lanes of a row read the same word (broadcast)
+  int* ymin = kk + RBV * kmax;       // [RBV]
+  int* cnt = ymin + RBV;             // [RBV]
+  for (int yy = threadIdx.x; yy < rows; yy += blockDim.x) {
+    int lo, n;
+    axis_coeffs(v.v, v.filter, y_begin + yy + v.v.off, kk + yy * kmax, 1, lo, n);
+    ymin[yy] = lo - v.row0;          // rows of the intermediate are stored from row0 on (Pillow: ybox_first)
+    cnt[yy] = n;
+  }
+  __syncthreads();
+  const long long plane = static_cast<long long>(v.n_rows) * S;
+  const uint8_t* t = tmp + v.tmp_off;
+  uint8_t* o = out + static_cast<long long>(blockIdx.y) * 3 * S * S;
+  const int ks = words_ok ? v.v.ksize : 0;
+  switch (ks) {
+    case 3: v_rows_fast<3>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
+    case 5: v_rows_fast<5>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
+    case 7: v_rows_fast<7>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
+    case 9: v_rows_fast<9>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
+    default: v_rows_generic(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o);
   }
 }
 
@@ -253,11 +382,16 @@ cudaError_t launch_tta(const uint8_t* src, const void* views_dev, int64_t n_jobs
   }
   const ViewDev* views = static_cast<const ViewDev*>(views_dev);
   dim3 gh(static_cast<unsigned>((max_rows + RBH - 1) / RBH), static_cast<unsigned>(n_jobs));
-  resample_h_kernel<<<gh, 256, smem_h, stream>>>(src, views, S, kmax_h, tmp);
+  // word-wide horizontal pass: whole aligned 32-bit words of the source are read (include/jclip_b200.h states the
+  // contract: src_dev 4-byte aligned and readable up to the next multiple of 4 bytes)
+  const int src_words_ok = (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+  resample_h_kernel<<<gh, 256, smem_h, stream>>>(src, views, S, kmax_h, tmp, src_words_ok);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 gv(static_cast<unsigned>((S + RBV - 1) / RBV), static_cast<unsigned>(n_jobs));
-  resample_v_kernel<<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, out);
+  // word-wide vertical pass: rows of the intermediate start on 4-byte boundaries (tmp_off is 256-byte aligned)
+  const int words_ok = S % 4 == 0 && (reinterpret_cast<uintptr_t>(tmp) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  resample_v_kernel<<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, out, words_ok);
   return cudaGetLastError();
 }
 

@@ -68,6 +68,35 @@ def test_explicit_boxes_on_the_image_border(jb, cuda_dev):
         assert np.array_equal(out[k], C.pil_crop_view(im, t, l, h, w, f)), boxes[k]
 
 
+def test_byte_paths_unaligned_source_and_odd_size(jb, cuda_dev):
+    """The word-wide resample passes need a 4-byte aligned source and size % 4 == 0; everything else takes the
+    byte-wise bodies of the same kernels.  Both must equal Pillow: a source pointer 1 byte off, and size = 222."""
+    import ctypes
+    from oracle import crops as C
+    get_context, check = jb.get_context, jb._capi.check
+    rng = np.random.default_rng(7)
+    im = _img(rng, 333, 421)
+    boxes = [(0, 0, 333, 421, 0), (5, 7, 200, 260, 1), (100, 120, 233, 301, 0), (3, 1, 64, 80, 1)]
+    ctx = get_context(cuda_dev)
+    for size, shift in [(224, 1), (224, 3), (222, 0), (222, 2)]:
+        jobs = (jb._capi.ViewJob * len(boxes))()
+        for j, (t, l, h, w, f) in zip(jobs, boxes):
+            j.image, j.top, j.left, j.crop_h, j.crop_w = 0, t, l, h, w
+            j.out_h, j.out_w, j.off_y, j.off_x, j.filter, j.flip = size, size, 0, 0, 0, f
+        buf = torch.zeros(im.size + 64, dtype=torch.uint8, device=cuda_dev)
+        buf[shift:shift + im.size] = torch.from_numpy(im.reshape(-1)).to(cuda_dev)
+        desc = (jb._capi.SrcImage * 1)()
+        desc[0].offset, desc[0].height, desc[0].width = 0, im.shape[0], im.shape[1]
+        out = torch.empty((len(boxes), 3, size, size), dtype=torch.uint8, device=cuda_dev)
+        with torch.cuda.device(cuda_dev):
+            ctx.bind_current_stream()
+            check(ctx.lib.jcb_tta_views(ctx.handle, ctypes.c_void_p(buf.data_ptr() + shift), desc, 1, jobs, len(boxes), size,
+                                        ctypes.c_void_p(out.data_ptr())), ctx.handle)
+        got = out.cpu().numpy()
+        for k, (t, l, h, w, f) in enumerate(boxes):
+            assert np.array_equal(got[k], C.pil_crop_view(im, t, l, h, w, f, size)), (size, shift, boxes[k])
+
+
 def test_rejects_bad_jobs(jb, cuda_dev):
     im = np.zeros((100, 100, 3), np.uint8)
     gen = jb.TTAViews(n_crops=0)

@@ -219,3 +219,18 @@ def test_u8_normalise_fma_is_exact_in_bf16():
         b = -mean[c] / std[c]
         fma = (u.astype(np.float64) * np.float64(a) + np.float64(b)).astype(np.float32)   # one rounding, as fmaf
         assert torch.equal(bf16(fma), bf16(exact)), c
+
+
+def test_alias_package_has_single_module_copies():
+    """`jclip_b200.x` must be the same module object as the real package's `x` (a second copy would carry its own
+    ctypes structure classes and its own context cache)."""
+    import importlib
+    import jclip_b200
+    from jclip_b200.runtime import get_context
+    import jclip_b200._capi as capi
+    real = importlib.import_module("jittor-clip-fewshot_b200")
+    assert jclip_b200 is real
+    assert capi is importlib.import_module("jittor-clip-fewshot_b200._capi") and capi is jclip_b200._capi
+    assert get_context is real.runtime.get_context
+    import jclip_b200.build as b
+    assert b is importlib.import_module("jittor-clip-fewshot_b200.build")
