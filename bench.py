@@ -58,6 +58,22 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(args, world, views_mib=None):
+    """The `config` of both arms: the workload BASELINE.json's metric is quoted on (configs[2]/[3] at N = 64 crops)."""
+    I, V = args.images_per_gpu, args.crops + 1
+    if views_mib is None:
+        views_mib = I * V * 3 * 224 * 224 * (1 if args.img_dtype == "u8" else 4) / 2**20
+    return {
+        "workload": f"ViT-B/32 LoRA(r=4 on q,k,v, merged) encode_image over {I} images x {V} views (N={args.crops} crops + "
+                    f"centre) per GPU per step, {'uint8' if args.img_dtype == 'u8' else 'fp32'} 224x224 pixels (ToTensor scaling + CLIP "
+                    f"normalisation fused on the device), MTA x3, LP++ head, "
+                    f"top-5 of 403 classes",
+        "images_per_gpu_per_step": I, "views_per_image": V, "parallelism": f"image-sharded dp{world}",
+        "l2_policy": f"inputs larger than L2 ({views_mib:.0f} MiB of views per step)",
+        "chunk_views_bound": args.chunk_views or 16384, "img_dtype": args.img_dtype, "gflop_per_view": GFLOP_PER_VIEW,
+    }
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -158,8 +174,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"ViT-B/32 LoRA(r=4,qkv) encode_image x {V} views/image + MTA x3 + LP++ head, top-5 of 403",
-                   "views_per_image": V, "images_per_step": 1},
+        # the b200 arm's config; every step of THIS arm is a bounded sample of it (cpu_baseline.sample): one of the
+        # step's images with all its views, so value = images/s of the same pipeline on the host cores
+        "config": dict(workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))), reference_sample_images_per_step=1),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -412,15 +429,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {
-            "workload": f"ViT-B/32 LoRA(r=4 on q,k,v, merged) encode_image over {I} images x {V} views (N={args.crops} crops + "
-                        f"centre) per GPU per step, {'uint8' if args.img_dtype == 'u8' else 'fp32'} 224x224 pixels (ToTensor scaling + CLIP "
-                        f"normalisation fused on the device), MTA x3, LP++ head, "
-                        f"top-5 of 403 classes",
-            "images_per_gpu_per_step": I, "views_per_image": V, "parallelism": f"image-sharded dp{world}",
-            "l2_policy": f"inputs larger than L2 ({images.numel() * images.element_size() / 2**20:.0f} MiB of views per step)",
-            "chunk_views_bound": args.chunk_views or 16384, "img_dtype": args.img_dtype, "gflop_per_view": GFLOP_PER_VIEW,
-        },
+        "config": workload_config(args, world, images.numel() * images.element_size() / 2**20),
         "e2e": e2e, "e2e_from_images": e2e_img, "cls_only_last_block": cls_only, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

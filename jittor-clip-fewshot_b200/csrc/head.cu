@@ -103,19 +103,47 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   float* cs3 = s_sc + SCORE_CS3 * C;
   float* cs4 = s_sc + SCORE_CS4 * C;
   float* cs5 = s_sc + SCORE_CS5 * C;
-  for (int c = warp; c < C; c += HEAD_WARPS) {   // one warp per class, rows of [C, D] read coalesced
+  // one warp per class, rows of [C, D] read coalesced.  D = 512 with 16-byte aligned banks (every real call): all
+  // sixteen 16-byte loads of a class are issued before the first FMA -- the scalar loop below kept one L2 round trip
+  // per 32 columns on the critical path (0.7 ms per 128 images, profiles/r01u_bench_n1.json)
+  const bool vec = D == 512 && a.vec_ok;
+  for (int c = warp; c < C; c += HEAD_WARPS) {
     const float* w = a.fc_w + static_cast<long long>(c) * D;
     const float* tp = a.T_pt + static_cast<long long>(c) * D;
     const float* th = a.T_hand + static_cast<long long>(c) * D;
     const float* tz = a.T_zs + static_cast<long long>(c) * D;
     float z1 = 0.f, z2 = 0.f, d0 = 0.f, d1 = 0.f, d3 = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float ww = __ldg(w + d);
-      z1 = fmaf(s_u1[d], ww, z1);
-      z2 = fmaf(s_u2[d], ww, z2);
-      d0 = fmaf(s_hand[d], __ldg(th + d), d0);
-      d1 = fmaf(s_pt[d], __ldg(tp + d), d1);
-      d3 = fmaf(s_zs[d], __ldg(tz + d), d3);
+    if (vec) {
+      float4 vw[4], vp[4], vh[4], vz[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i4 = lane + 32 * q;
+        vw[q] = __ldg(reinterpret_cast<const float4*>(w) + i4);
+        vp[q] = __ldg(reinterpret_cast<const float4*>(tp) + i4);
+        vh[q] = __ldg(reinterpret_cast<const float4*>(th) + i4);
+        vz[q] = __ldg(reinterpret_cast<const float4*>(tz) + i4);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i4 = lane + 32 * q;
+        const float4 u1 = reinterpret_cast<const float4*>(s_u1)[i4], u2 = reinterpret_cast<const float4*>(s_u2)[i4];
+        const float4 sh = reinterpret_cast<const float4*>(s_hand)[i4], sp = reinterpret_cast<const float4*>(s_pt)[i4];
+        const float4 sz = reinterpret_cast<const float4*>(s_zs)[i4];
+        z1 = fmaf(u1.x, vw[q].x, z1); z1 = fmaf(u1.y, vw[q].y, z1); z1 = fmaf(u1.z, vw[q].z, z1); z1 = fmaf(u1.w, vw[q].w, z1);
+        z2 = fmaf(u2.x, vw[q].x, z2); z2 = fmaf(u2.y, vw[q].y, z2); z2 = fmaf(u2.z, vw[q].z, z2); z2 = fmaf(u2.w, vw[q].w, z2);
+        d0 = fmaf(sh.x, vh[q].x, d0); d0 = fmaf(sh.y, vh[q].y, d0); d0 = fmaf(sh.z, vh[q].z, d0); d0 = fmaf(sh.w, vh[q].w, d0);
+        d1 = fmaf(sp.x, vp[q].x, d1); d1 = fmaf(sp.y, vp[q].y, d1); d1 = fmaf(sp.z, vp[q].z, d1); d1 = fmaf(sp.w, vp[q].w, d1);
+        d3 = fmaf(sz.x, vz[q].x, d3); d3 = fmaf(sz.y, vz[q].y, d3); d3 = fmaf(sz.z, vz[q].z, d3); d3 = fmaf(sz.w, vz[q].w, d3);
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const float ww = __ldg(w + d);
+        z1 = fmaf(s_u1[d], ww, z1);
+        z2 = fmaf(s_u2[d], ww, z2);
+        d0 = fmaf(s_hand[d], __ldg(th + d), d0);
+        d1 = fmaf(s_pt[d], __ldg(tp + d), d1);
+        d3 = fmaf(s_zs[d], __ldg(tz + d), d3);
+      }
     }
     z1 = warp_sum(z1); z2 = warp_sum(z2); d0 = warp_sum(d0); d1 = warp_sum(d1); d3 = warp_sum(d3);
     if (lane == 0) {
@@ -257,7 +285,10 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  head_kernel<<<static_cast<unsigned>(a.I), HEAD_THREADS, smem, stream>>>(a);
+  HeadArgs b = a;
+  b.vec_ok = ((reinterpret_cast<uintptr_t>(a.T_pt) | reinterpret_cast<uintptr_t>(a.T_hand) |
+               reinterpret_cast<uintptr_t>(a.T_zs) | reinterpret_cast<uintptr_t>(a.fc_w)) & 15) == 0;
+  head_kernel<<<static_cast<unsigned>(a.I), HEAD_THREADS, smem, stream>>>(b);
   return cudaGetLastError();
 }
 

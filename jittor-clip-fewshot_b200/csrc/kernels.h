@@ -132,6 +132,7 @@ struct HeadArgs {
   int32_t* out_topk;                  // [I, k]
   float* out_scores;                  // [I, C] (the ranked score) or nullptr
   float* out_all;                     // [I, SCORE_COUNT, C] or nullptr (tests)
+  int vec_ok = 0;                     // set by launch_head: banks and fc_w are 16-byte aligned (float4 loads)
 };
 cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream);
 // Stand-alone pieces of the head (drop-in functions of the reference's Python API)

@@ -20,8 +20,11 @@ __constant__ float c_clip_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
 // ------------------------------------------------------------------------------------------ im2col
-// One block = the K / EPT 16-byte chunks of a patch row (192 threads for u8, 384 for bf16 / fp32 pixels); a thread
-// keeps its (channel, row, column) offset for the whole kernel and walks over patches, UNROLL of them in flight.
+// One block = the K / 8 eight-pixel chunks of a patch row (384 threads for patch 32); a thread keeps its (channel, row,
+// column) offset for the whole kernel and walks over patches, UNROLL of them in flight.  Eight pixels per thread for
+// every input type: a warp's store is then 512 contiguous bytes (with 16 uint8 pixels per thread each lane wrote two
+// 16-byte halves 32 bytes apart -- every store instruction touched 32 half-filled sectors and the kernel sat in the
+// LSU queue, ncu: 41 % lg_throttle).
 // ToTensor's 1/255 and tfm_clip's (x - mean_c) / std_c are one FMA per pixel, x * a_c + b_c with a_c = 1 / (255 std_c),
 // b_c = -mean_c / std_c: for all 3 x 256 possible uint8 inputs the bf16-rounded result equals the reference's
 // ((u / 255) - mean) / std evaluated in fp32 (tests/test_host_logic.py::test_u8_normalise_fma_is_exact_in_bf16).
@@ -33,7 +36,7 @@ template <int DT>
 __global__ void __launch_bounds__(384)
 im2col_kernel(const void* __restrict__ images, unsigned n_patches, int R, int P, int G, int apply_norm,
               __nv_bfloat16* __restrict__ patches) {
-  constexpr int EPT = DT == IMG_U8 ? 16 : 8;
+  constexpr int EPT = 8;   // 8 pixels per thread for every input type: one fully coalesced 16-byte store per lane
   const int K = 3 * P * P;
   const int col = static_cast<int>(threadIdx.x) * EPT;  // (c, i, j) with j % EPT == 0
   const int c = col / (P * P);
@@ -47,52 +50,65 @@ im2col_kernel(const void* __restrict__ images, unsigned n_patches, int R, int P,
     a = 1.0f / ((DT == IMG_U8 ? 255.0f : 1.0f) * c_clip_std[c]);
     b = -c_clip_mean[c] / c_clip_std[c];
   }
-  for (unsigned p0 = blockIdx.x * IM2COL_UNROLL; p0 < n_patches; p0 += gridDim.x * IM2COL_UNROLL) {
-    uint4 raw[IM2COL_UNROLL][DT == IMG_F32 ? 2 : 1];
+  constexpr int NR = DT == IMG_F32 ? 2 : 1;
+  auto load = [&](unsigned p, uint4 (&raw)[NR]) {
+    const unsigned view = p / GG, pidx = p - view * GG;
+    const unsigned py = pidx / G, px = pidx - py * G;
+    const long long src = view * view_elems + thread_off + (static_cast<long long>(py) * R + px) * P;
+    if (DT == IMG_F32) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(static_cast<const float*>(images) + src);
+      raw[0] = __ldg(s4);
+      raw[NR - 1] = __ldg(s4 + 1);
+    } else if (DT == IMG_BF16) {
+      raw[0] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(images) + src));
+    } else {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(images) + src));
+      raw[0] = make_uint4(t.x, t.y, 0u, 0u);
+    }
+  };
+  auto emit = [&](unsigned p, const uint4 (&raw)[NR]) {
+    float f[EPT];
+    if (DT == IMG_F32) {
+      const float* v = reinterpret_cast<const float*>(&raw[0]);
 #pragma unroll
-    for (int u = 0; u < IM2COL_UNROLL; ++u) {
-      const unsigned p = p0 + u < n_patches ? p0 + u : n_patches - 1;
-      const unsigned view = p / GG, pidx = p - view * GG;
-      const unsigned py = pidx / G, px = pidx - py * G;
-      const long long src = view * view_elems + thread_off + (static_cast<long long>(py) * R + px) * P;
-      if (DT == IMG_F32) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(static_cast<const float*>(images) + src);
-        raw[u][0] = __ldg(s4);
-        raw[u][DT == IMG_F32 ? 1 : 0] = __ldg(s4 + 1);
-      } else if (DT == IMG_BF16) {
-        raw[u][0] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(images) + src));
-      } else {
-        raw[u][0] = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(images) + src));
-      }
+      for (int e = 0; e < 8; ++e) f[e] = v[e];
+    } else if (DT == IMG_BF16) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[0]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+    } else {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[0]);
+      // uint8 -> fp32 without the quarter-rate I2F: one PRMT drops the byte into the mantissa of 2^23 (0x4B000000),
+      // one FADD removes the 2^23 again -- exact for 0..255
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+        f[e] = __uint_as_float(__byte_perm(w[e >> 2], 0x4B000000u, 0x7540u + (e & 3))) - 8388608.0f;
     }
 #pragma unroll
-    for (int u = 0; u < IM2COL_UNROLL; ++u) {
-      if (p0 + u >= n_patches) break;
-      float f[EPT];
-      if (DT == IMG_F32) {
-        const float* v = reinterpret_cast<const float*>(&raw[u][0]);
+    for (int e = 0; e < EPT; ++e) f[e] = fmaf(f[e], a, b);
+    uint4* dst = reinterpret_cast<uint4*>(patches + static_cast<long long>(p) * K + col);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = v[e];
-      } else if (DT == IMG_BF16) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][0]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
-      } else {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[u][0]);
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) f[e] = static_cast<float>((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
-      }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) f[e] = fmaf(f[e], a, b);
-      uint4* dst = reinterpret_cast<uint4*>(patches + static_cast<long long>(p0 + u) * K + col);
-#pragma unroll
-      for (int h = 0; h < EPT / 8; ++h) {
-        uint4 o;
-        o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]); o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
-        o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]); o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
-        dst[h] = o;
-      }
+    for (int h = 0; h < EPT / 8; ++h) {
+      uint4 o;
+      o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]); o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
+      o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]); o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
+      dst[h] = o;
     }
+  };
+  // full groups of UNROLL patches: no exit between the loads and their uses, so all UNROLL loads are in flight together
+  // (with a tail check inside the group the compiler sank every load to its use: one 16-byte load in flight per thread)
+  const unsigned n_full = n_patches / IM2COL_UNROLL * IM2COL_UNROLL;
+  for (unsigned p0 = blockIdx.x * IM2COL_UNROLL; p0 < n_full; p0 += gridDim.x * IM2COL_UNROLL) {
+    uint4 raw[IM2COL_UNROLL][NR];
+#pragma unroll
+    for (int u = 0; u < IM2COL_UNROLL; ++u) load(p0 + u, raw[u]);
+#pragma unroll
+    for (int u = 0; u < IM2COL_UNROLL; ++u) emit(p0 + u, raw[u]);
+  }
+  for (unsigned p = n_full + blockIdx.x; p < n_patches; p += gridDim.x) {
+    uint4 raw[NR];
+    load(p, raw);
+    emit(p, raw);
   }
 }
 
@@ -430,8 +446,8 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
                           int apply_norm, __nv_bfloat16* patches, cudaStream_t stream) {
   if (resolution % patch != 0 || patch % 16 != 0) return cudaErrorInvalidValue;
   const int G = resolution / patch;
-  const int ept = img_dtype == IMG_U8 ? 16 : 8;
-  const int threads = 3 * patch * patch / ept;           // one thread per 16-byte chunk of a patch row
+  const int ept = 8;
+  const int threads = 3 * patch * patch / ept;           // one thread per 8 pixels (16 bytes of bf16 output) of a patch row
   if (threads > 384 || threads % 32 != 0) return cudaErrorInvalidValue;   // patch 32: 192 (u8) / 384
   const int64_t n_patches = n_views * G * G;
   if (n_patches == 0) return cudaSuccess;
