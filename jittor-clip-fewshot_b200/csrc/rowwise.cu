@@ -297,7 +297,7 @@ text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, i
 }
 
 // ------------------------------------------------------------------------------------------ tail
-constexpr int TAIL_VIEWS = 8;
+constexpr int TAIL_VIEWS = 16;   // sequences per CTA: proj [W, E] is streamed from L2 once per CTA
 constexpr int TAIL_THREADS = 256;
 
 template <int NV, int E>
@@ -307,12 +307,13 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
             const int* __restrict__ row_idx) {
   constexpr int W = NV * 128;
   constexpr int EPT = E / TAIL_THREADS;  // outputs per thread
-  __shared__ __align__(16) float s_x[TAIL_VIEWS][W];
-  __shared__ float s_part[TAIL_VIEWS][TAIL_THREADS / 32];
+  extern __shared__ __align__(16) float tail_smem[];
+  float (*s_x)[W] = reinterpret_cast<float (*)[W]>(tail_smem);                                     // [TAIL_VIEWS][W]
+  float (*s_part)[TAIL_THREADS / 32] = reinterpret_cast<float (*)[TAIL_THREADS / 32]>(tail_smem + TAIL_VIEWS * W);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long v0 = static_cast<long long>(blockIdx.x) * TAIL_VIEWS;
-  {  // ln_post on the CLS row of view v0 + warp  (jclip/model.py:121)
-    const long long view = v0 + warp;
+  for (int vv = warp; vv < TAIL_VIEWS; vv += TAIL_THREADS / 32) {  // ln_post on the CLS row of view v0 + vv  (jclip/model.py:121)
+    const long long view = v0 + vv;
     float4 v[NV];
     if (view < n_views) {
       const long long trow = view * T + (row_idx ? row_idx[view] : 0);
@@ -327,7 +328,7 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
       for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(s_x[warp])[lane + 32 * i] = v[i];
+    for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(s_x[vv])[lane + 32 * i] = v[i];
   }
   __syncthreads();
   float acc[TAIL_VIEWS][EPT];
@@ -335,15 +336,23 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
   for (int v = 0; v < TAIL_VIEWS; ++v)
 #pragma unroll
     for (int e = 0; e < EPT; ++e) acc[v][e] = 0.f;
-  for (int k = 0; k < W; ++k) {  // x @ proj  (jclip/model.py:123-124), fp32
-    float pw[EPT];
+  for (int k = 0; k < W; k += 4) {  // x @ proj  (jclip/model.py:123-124), fp32; four k per step, x read as float4
+    float pw[4][EPT];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) pw[e] = __ldg(proj + static_cast<long long>(k) * E + threadIdx.x + e * TAIL_THREADS);
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+        pw[kk][e] = __ldg(proj + static_cast<long long>(k + kk) * E + threadIdx.x + e * TAIL_THREADS);
 #pragma unroll
     for (int v = 0; v < TAIL_VIEWS; ++v) {
-      const float xv = s_x[v][k];
+      const float4 xv = *reinterpret_cast<const float4*>(&s_x[v][k]);
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) acc[v][e] = fmaf(xv, pw[e], acc[v][e]);
+      for (int e = 0; e < EPT; ++e) {
+        acc[v][e] = fmaf(xv.x, pw[0][e], acc[v][e]);
+        acc[v][e] = fmaf(xv.y, pw[1][e], acc[v][e]);
+        acc[v][e] = fmaf(xv.z, pw[2][e], acc[v][e]);
+        acc[v][e] = fmaf(xv.w, pw[3][e], acc[v][e]);
+      }
     }
   }
   // f / ||f||_2  (test.py:1706)
@@ -506,8 +515,20 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
   if (W % 128 != 0 || E != 512) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((n_views + TAIL_VIEWS - 1) / TAIL_VIEWS);
-  JCB_DISPATCH_NV(W, (tail_kernel<NV, 512><<<grid, TAIL_THREADS, 0, stream>>>(tokens, n_views, T, g, b, proj,
-                                                                             normalize, out, row_idx)));
+  const size_t smem = sizeof(float) * (static_cast<size_t>(TAIL_VIEWS) * W + TAIL_VIEWS * (TAIL_THREADS / 32));
+  if (smem > 48 * 1024) {
+    static bool attr_set[16] = {false};
+    bool& done = attr_set[(W / 128) & 15];
+    if (!done) {
+      cudaError_t e = cudaSuccess;
+      JCB_DISPATCH_NV(W, (e = cudaFuncSetAttribute(tail_kernel<NV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(smem))));
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+  }
+  JCB_DISPATCH_NV(W, (tail_kernel<NV, 512><<<grid, TAIL_THREADS, smem, stream>>>(tokens, n_views, T, g, b, proj,
+                                                                                normalize, out, row_idx)));
   return cudaGetLastError();
 }
 
