@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -13,6 +15,23 @@
 #include "kernels.h"
 
 using namespace jcb;
+
+namespace jcb {
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = granted[std::make_pair(func, dev)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+}  // namespace jcb
 
 // ------------------------------------------------------------------------------------------------
 struct jcb_ctx {

@@ -267,12 +267,9 @@ cudaError_t launch_attention_cfg(const __nv_bfloat16* qkv, int64_t n_views, int 
                                  cudaStream_t stream) {
   constexpr int SMEM = HPC * 3 * TP * LDS * 2;
   constexpr int THREADS = HPC * (TP / 16 / MT) * 32;
-  static bool attr_set = false;
-  if (!attr_set && SMEM > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HPC, MT, TP, CAUSAL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {
+    cudaError_t e = ensure_dynamic_smem(attention_kernel<HPC, MT, TP, CAUSAL>, SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const long long grid = n_views * (heads / HPC);
   attention_kernel<HPC, MT, TP, CAUSAL><<<static_cast<unsigned>(grid), THREADS, SMEM, stream>>>(qkv, T, heads, out);

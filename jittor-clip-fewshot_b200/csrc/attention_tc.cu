@@ -276,12 +276,9 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, int64_t n_views, int T
   if (!make_tmap_heads(&tmOut, out, static_cast<uint64_t>(n_views), static_cast<uint64_t>(T), static_cast<uint64_t>(heads)))
     return cudaErrorInvalidValue;
   auto kernel = T == 50 ? attention_tcgen05_kernel<50> : T == 54 ? attention_tcgen05_kernel<54> : attention_tcgen05_kernel<0>;
-  static bool attr_set[3] = {false, false, false};
-  const int which = T == 50 ? 0 : T == 54 ? 1 : 2;
-  if (!attr_set[which]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+  {
+    cudaError_t e = ensure_dynamic_smem(kernel, ATC_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set[which] = true;
   }
   AtcDev p;
   p.pairs = heads / 2;

@@ -577,11 +577,9 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   }
   if (is_lnfold(EPI) && (!a.stats || !a.colsum || a.stats_slots < 1)) return cudaErrorInvalidValue;
   auto kern = CTAS == 2 ? gemm_bf16_tcgen05_2cta_kernel<BN, EPI> : gemm_bf16_tcgen05_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  {
+    cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;

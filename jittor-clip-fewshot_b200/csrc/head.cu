@@ -279,11 +279,9 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream) {
   if (a.I == 0) return cudaSuccess;
   const size_t smem = sizeof(float) * (5 * a.D + (SCORE_COUNT + 1) * a.C + 32) + sizeof(int) * 32;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  {
+    cudaError_t e = ensure_dynamic_smem(head_kernel, smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
   }
   HeadArgs b = a;
   b.vec_ok = ((reinterpret_cast<uintptr_t>(a.T_pt) | reinterpret_cast<uintptr_t>(a.T_hand) |

@@ -120,6 +120,15 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
                        float* scratch, cudaStream_t stream);
 
 enum HeadScore : int { SCORE_LOGITS = 0, SCORE_CS = 1, SCORE_CS1 = 2, SCORE_CS2 = 3, SCORE_CS3 = 4, SCORE_CS4 = 5, SCORE_CS5 = 6, SCORE_COUNT = 7 };
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  cudaFuncSetAttribute acts on the current
+// device's context, so the cache is keyed by (function, device): a process that drives several GPUs through several
+// contexts gets the attribute on each of them (a per-process `static bool` would leave the second device at 48 KB).
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+template <class F>
+inline cudaError_t ensure_dynamic_smem(F* func, size_t bytes) {
+  return ensure_dynamic_smem(reinterpret_cast<const void*>(func), bytes);
+}
+
 struct HeadArgs {
   const float *m_pt, *m_hand, *m_zs;  // [I, D] modes
   const float *T_pt, *T_hand, *T_zs;  // [C, D] text features (unit rows)

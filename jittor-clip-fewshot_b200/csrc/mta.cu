@@ -748,11 +748,9 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     for (int s2 = 0; s2 < MTA_MAX_SETS; ++s2) pd.sets[s2] = a.sets[s2];
     pd.rows = static_cast<long long>(I) * V;
     pd.C = C; pd.D = D; pd.scale = 100.0f / p.temperature; pd.P = scratch;
-    static bool pattr = false;
-    if (!pattr) {
-      cudaError_t e = cudaFuncSetAttribute(mta_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM);
+    {
+      cudaError_t e = ensure_dynamic_smem(mta_probs_kernel, PB_SMEM);
       if (e != cudaSuccess) return e;
-      pattr = true;
     }
     dim3 pgrid(static_cast<unsigned>((pd.rows + PB_ROWS - 1) / PB_ROWS), static_cast<unsigned>(n_sets));
     mta_probs_kernel<<<pgrid, 256, PB_SMEM, stream>>>(pd);
@@ -767,12 +765,9 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     a.in_smem = 1;
     a.scratch = nullptr;
     a.scratch_stride = 0;
-    static bool fattr = false;
-    if (!fattr) {
-      cudaError_t e = cudaFuncSetAttribute(mta_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(MTA_SMEM_LIMIT));
+    {
+      cudaError_t e = ensure_dynamic_smem(mta_fast_kernel, MTA_SMEM_LIMIT);
       if (e != cudaSuccess) return e;
-      fattr = true;
     }
     dim3 fgrid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
     mta_fast_kernel<<<fgrid, MF_THREADS, mf_smem_bytes(V, C, D), stream>>>(a);
@@ -782,12 +777,9 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
   a.scratch = scratch;
   a.scratch_stride = be;
   const size_t smem = a.in_smem ? small + static_cast<size_t>(be) * sizeof(float) : small;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(MTA_SMEM_LIMIT));
+  {
+    cudaError_t e = ensure_dynamic_smem(mta_kernel, MTA_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   dim3 grid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
   mta_kernel<<<grid, MTA_THREADS, smem, stream>>>(a);

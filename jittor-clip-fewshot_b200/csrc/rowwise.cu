@@ -457,7 +457,7 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
   const int G = resolution / patch;
   const int ept = 8;
   const int threads = 3 * patch * patch / ept;           // one thread per 8 pixels (16 bytes of bf16 output) of a patch row
-  if (threads > 384 || threads % 32 != 0) return cudaErrorInvalidValue;   // patch 32: 192 (u8) / 384
+  if (threads > 384 || threads % 32 != 0) return cudaErrorInvalidValue;   // patch 32: 384 threads
   const int64_t n_patches = n_views * G * G;
   if (n_patches == 0) return cudaSuccess;
   if (n_patches > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -516,16 +516,10 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
   if (n_views == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((n_views + TAIL_VIEWS - 1) / TAIL_VIEWS);
   const size_t smem = sizeof(float) * (static_cast<size_t>(TAIL_VIEWS) * W + TAIL_VIEWS * (TAIL_THREADS / 32));
-  if (smem > 48 * 1024) {
-    static bool attr_set[16] = {false};
-    bool& done = attr_set[(W / 128) & 15];
-    if (!done) {
-      cudaError_t e = cudaSuccess;
-      JCB_DISPATCH_NV(W, (e = cudaFuncSetAttribute(tail_kernel<NV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   static_cast<int>(smem))));
-      if (e != cudaSuccess) return e;
-      done = true;
-    }
+  {
+    cudaError_t e = cudaSuccess;
+    JCB_DISPATCH_NV(W, (e = ensure_dynamic_smem(tail_kernel<NV, 512>, smem)));
+    if (e != cudaSuccess) return e;
   }
   JCB_DISPATCH_NV(W, (tail_kernel<NV, 512><<<grid, TAIL_THREADS, smem, stream>>>(tokens, n_views, T, g, b, proj,
                                                                                 normalize, out, row_idx)));

@@ -369,16 +369,10 @@ cudaError_t launch_tta(const uint8_t* src, const void* views_dev, int64_t n_jobs
   const size_t smem_h = static_cast<size_t>(S) * (kmax_h + 2) * sizeof(int);
   const size_t smem_v = static_cast<size_t>(RBV) * (kmax_v + 2) * sizeof(int);
   if (smem_h > 200 * 1024 || smem_v > 200 * 1024 || n_jobs > 65535) return cudaErrorInvalidValue;
-  static size_t attr_h = 0, attr_v = 0;
-  if (smem_h > 48 * 1024 && smem_h > attr_h) {
-    cudaError_t e = cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_h));
+  {
+    cudaError_t e = ensure_dynamic_smem(resample_h_kernel, smem_h);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(resample_v_kernel, smem_v);
     if (e != cudaSuccess) return e;
-    attr_h = smem_h;
-  }
-  if (smem_v > 48 * 1024 && smem_v > attr_v) {
-    cudaError_t e = cudaFuncSetAttribute(resample_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_v));
-    if (e != cudaSuccess) return e;
-    attr_v = smem_v;
   }
   const ViewDev* views = static_cast<const ViewDev*>(views_dev);
   dim3 gh(static_cast<unsigned>((max_rows + RBH - 1) / RBH), static_cast<unsigned>(n_jobs));
