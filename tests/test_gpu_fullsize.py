@@ -86,3 +86,64 @@ def test_pipeline_sweep_sizes(jb, cuda_dev, lora_model, n_crops, n_images):
         t5, sc, _ = pipeline_image(fi, fi, Ts[0], Ts[1], Ts[2], lp_t, score="cs5")
         assert (scores[i].cpu() - sc["cs5"][0]).abs().max() <= 1e-2
         assert set(t5.tolist()) == set(topk[i].cpu().tolist())
+
+
+@pytest.mark.parametrize("I,V", [(64, 9), (24, 65)])
+def test_end_to_end_agreement_with_fp32_oracle(jb, cuda_dev, lora_model, I, V):
+    """The whole path against the fp32 oracle END TO END (oracle tower -> oracle MTA x3 -> oracle head), full
+    12-layer LoRA tower, 64 images x 9 views and 24 images x 65 views (the headline N = 64): embedding cosine >= 0.999 (north star), top-5 label agreement, and
+    the logit deviation.  The other parity tests hold MTA / head to 1e-2 and 99.5 % GIVEN THE SAME embeddings; here
+    the x100 logits also carry the bf16 tower's embedding error (cosine 0.999997 -> 0.02-0.07 logits), and a top-5
+    set can only differ where the oracle's 5th and 6th scores are closer than twice that error -- asserted per image.  The
+    measured numbers are written to gpurun_out/e2e_agreement_<I>x<V>.json (copies under profiles/)."""
+    import json
+    import os
+    from oracle import pipeline_image, vit_encode_image
+    sd, lora, model = lora_model
+    imgs = jb.synth.make_views(21, I, V)                       # float32 [I, V, 3, 224, 224] in [0, 1]
+    Ts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
+    lp_np = jb.synth.make_head(2, Ts[2].numpy())
+    lp_t = tuple(torch.from_numpy(a) for a in lp_np)
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = lp_np
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    res = {}
+    for rank_by in ("cs5", "cs1"):
+        hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by=rank_by)
+        topk, feats, scores = hp.evaluate_base(torch.from_numpy(imgs).to(cuda_dev), return_feats=True, return_scores=True)
+        topk, feats, scores = topk.cpu(), feats.cpu(), scores.cpu()
+        agree, same_set, cos_min, dlogit, gap_at_flips = 0, 0, 1.0, 0.0, 0.0
+        for i in range(I):
+            f = vit_encode_image(sd_t, imgs[i], lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+            cos_min = min(cos_min, float(_cos(feats[i], f).min()))
+            t5, sc, _ = pipeline_image(f, f, Ts[0], Ts[1], Ts[2], lp_t, score=rank_by)
+            ref_scores = sc[rank_by][0]
+            d_i = float((scores[i] - ref_scores).abs().max())
+            dlogit = max(dlogit, d_i)
+            n = len(set(t5.tolist()) & set(topk[i].tolist()))
+            agree += n
+            same_set += n == 5
+            if n < 5:
+                # a different top-5 set is only possible at a near-tie: the oracle's own 5th and 6th scores are closer
+                # than twice the logit deviation of this image
+                srt = ref_scores.sort(descending=True).values
+                gap = float(srt[4] - srt[5])
+                assert gap <= 2.0 * d_i + 1e-6, (i, gap, d_i)
+                assert n == 4, (i, n)                         # and then exactly one label is exchanged
+                gap_at_flips = max(gap_at_flips, gap)
+        res[rank_by] = {"images": I, "views": V, "top5_label_agreement": agree / (5 * I), "identical_top5_sets": same_set / I,
+                        "min_embedding_cosine": cos_min, "max_abs_logit_diff": dlogit,
+                        "largest_oracle_5th_6th_gap_where_sets_differ": gap_at_flips}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/e2e_agreement_{I}x{V}.json", "w") as fh:
+        json.dump(res, fh, indent=1)
+    print(res)
+    # measured (profiles/r01y_e2e_agreement_*.json): cs1 (the score test.py ranks by) 99.7 % / 100 %, cs5 99.1 % / 97.5 %
+    # label agreement at 64x9 / 24x65; logits within 0.07.  Every differing set is a one-label exchange at a 5th/6th gap
+    # below 0.1 logits -- the three averaged random text banks put neighbouring cs5 scores ~0.2 apart at rank 5.
+    assert res["cs1"]["top5_label_agreement"] >= 0.985 and res["cs5"]["top5_label_agreement"] >= 0.95, res
+    for r in res.values():
+        assert r["min_embedding_cosine"] >= 0.999
+        assert r["max_abs_logit_diff"] <= 0.15, res
+        assert r["largest_oracle_5th_6th_gap_where_sets_differ"] <= 0.15, res
