@@ -4,15 +4,17 @@
 set -u
 mkdir -p gpurun_out
 G=${GPUS:-1}
-for cfg in "1 4160" "16 489" "64 128"; do
-  set -- $cfg
+PORT=29540
+for cfg in ${CONFIGS:-1:4160 16:489 64:128}; do      # crops:images-per-GPU-per-step
+  set -- ${cfg%%:*} ${cfg##*:}
   out=gpurun_out/sweep_g${G}_n$1.json
   if [ "$G" = 1 ]; then
     timeout 600 python bench.py --crops $1 --images-per-gpu $2 --steps 10 --warmup 3 --no-cpu-baseline > $out 2> gpurun_out/sweep_err.log
   else
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 2952$1 \
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $PORT \
       bench.py --gpus $G --crops $1 --images-per-gpu $2 --steps 10 --warmup 3 --no-cpu-baseline > $out 2> gpurun_out/sweep_err.log
   fi
+  PORT=$((PORT + 1))
   python - <<PY
 import json
 d = json.loads([l for l in open("$out") if l.startswith("{")][-1])
