@@ -53,6 +53,10 @@ def parse():
                     help="pixel format of the views: u8 (0..255, what an image decoder / the reference's PIL pipeline "
                          "produces before ToTensor; scaled by 1/255 on the device, bit-identical to ToTensor) or f32 in [0,1]")
     ap.add_argument("--host-chunk-views", type=int, default=0, help="views per pass when the input is in host memory")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep equal shards instead of sizing them by each rank's measured speed")
+    ap.add_argument("--gather-every", type=int, default=0,
+                    help="N > 1: all-gather the top-5 every G steps (1 = every step); 0 = once, at the end of the timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -220,18 +224,68 @@ def main():
     if args.host_chunk_views:
         ctx.set_host_chunk_views(args.host_chunk_views)
 
-    # this rank's shard of the step's images: I images x V views, generated on the device
-    images = jb.synth.make_views_torch(1000 + rank, I, V, dev)
-    if args.img_dtype == "u8":
-        images = (images * 255.0).round_().to(torch.uint8)
-    n_total = I * world
+    # this rank's shard of the step's images: I_r images x V views, generated on the device
+    def make_images(n):
+        im = jb.synth.make_views_torch(1000 + rank, n, V, dev)
+        return (im * 255.0).round_().to(torch.uint8) if args.img_dtype == "u8" else im
+
+    n_total = I * world                      # the step's global batch: fixed, I images per GPU on average
+    sizes = [I] * world
+    images = make_images(I)
+    balance = None
+    if world > 1 and not args.no_balance:
+        # The GPUs of one box differ by a few per cent under the power cap, and every step ends in an all-gather: with
+        # equal shards all ranks run at the pace of the slowest.  Images are independent, so the shard boundaries are
+        # free: time this rank alone on the equal shard (no collective inside), exchange the timings, and size the shards
+        # of the SAME global batch in proportion to speed (dist.balanced_shard_sizes).
+        for _ in range(2):
+            hp.evaluate_base(images, topk_to_host=False)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        jb.dist.barrier()
+        c0.record()
+        for _ in range(4):
+            hp.evaluate_base(images, topk_to_host=False)
+        c1.record()
+        torch.cuda.synchronize()
+        ms_rank = c0.elapsed_time(c1) / 4
+        ms_all = jb.dist.all_gather_floats(ms_rank, dev)
+        sizes = jb.dist.balanced_shard_sizes(n_total, [m / I for m in ms_all])
+        balance = {"calibration_ms_per_step_by_rank": [round(m, 2) for m in ms_all], "shard_images": sizes}
+        if sizes[rank] != I:
+            images = make_images(sizes[rank])
+    I_r = sizes[rank]
+    lo_r = sum(sizes[:rank])
+
+    # ... and the per-image top-5 to everyone (the path's other collective).  Default: the predictions of the K timed
+    # steps are kept on the device and all-gathered ONCE, inside the timed region, the way the reference writes one result
+    # file at the end of its loop; --gather-every 1 gathers after every step instead (asynchronously, so that the stream
+    # computing step k+1 does not wait for the slowest rank's step k: dist.AsyncTopkGather).  Either way the ranks are not
+    # in lockstep, and the timed region ends only when every gather has completed.
+    G = max(args.gather_every, 0)
+    gather = jb.dist.AsyncTopkGather(n_total, 5, dev, sizes=sizes, depth=4)
+    gather_all = jb.dist.AsyncTopkGather(n_total * K, 5, dev, sizes=[x * K for x in sizes], depth=1) if G != 1 else None
+    kept = torch.empty((K, I_r, 5), dtype=torch.int32, device=dev)
+    step_no = [0]
 
     def step_device():
         topk = hp.evaluate_base(images, topk_to_host=False)
-        return jb.dist.all_gather_topk(topk, n_total)      # ... and the per-image top-5 to everyone
+        if G == 1:
+            return gather.submit(topk)
+        kept[step_no[0] % K].copy_(topk, non_blocking=True)
+        step_no[0] += 1
+        return topk
+
+    def finish_steps():
+        """Inside the timed region, after the K steps: every rank's predictions of all K steps on every rank."""
+        if G == 1:
+            gather.drain()
+        else:
+            gather_all.result(gather_all.submit(kept.view(K * I_r, 5)))
 
     for _ in range(max(W, 1)):
-        out = step_device()
+        r = step_device()
+        out = gather.result(r if G == 1 else gather.submit(r))
     torch.cuda.synchronize()
     assert out.shape == (n_total, 5)
 
@@ -243,8 +297,10 @@ def main():
     n0 = ctx.launch_count
     ctx.profile_start()
     ev0.record()
+    step_no[0] = 0
     for _ in range(K):
         step_device()
+    finish_steps()
     ev1.record()
     torch.cuda.synchronize()
     jb.dist.barrier()
@@ -261,12 +317,15 @@ def main():
         ctx.set_cls_only_last_block(True)
         try:
             for _ in range(2):
-                out_c = step_device()
+                r = step_device()
+                out_c = gather.result(r if G == 1 else gather.submit(r))
             jb.dist.barrier()
             torch.cuda.synchronize()
+            step_no[0] = 0
             ev0.record()
             for _ in range(K):
                 step_device()
+            finish_steps()
             ev1.record()
             torch.cuda.synchronize()
         finally:
@@ -285,14 +344,18 @@ def main():
         torch.cuda.synchronize()
         for _ in range(max(W, 1)):
             tk = hp.evaluate_base(host_images)
-        assert not tk.is_cuda and torch.equal(tk, out[rank * I:(rank + 1) * I].cpu())
+        assert not tk.is_cuda and torch.equal(tk, out[lo_r:lo_r + I_r].cpu())
         # (a) one blocking call per step: nothing hides the first upload of a step or the final read
         jb.dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(K):
+        for k in range(K):
             tk = hp.evaluate_base(host_images)
-            jb.dist.all_gather_topk(tk.to(dev), n_total)
+            if G == 1:
+                gather.submit(tk.to(dev))
+            else:
+                kept[k].copy_(tk, non_blocking=True)
+        finish_steps()
         torch.cuda.synchronize()
         dt_block = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
         # (b) the streaming form of the same call (HotPath.evaluate_stream, the reference's `for images in loader`
@@ -303,14 +366,18 @@ def main():
         jb.dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for tk2 in hp.evaluate_stream(host_images for _ in range(K)):
+        for k, tk2 in enumerate(hp.evaluate_stream(host_images for _ in range(K))):
             # stream-ordered (a blocking .to() would make the host wait for the batch submitted after this one)
-            jb.dist.all_gather_topk(tk2.to(dev, non_blocking=True), n_total)
+            if G == 1:
+                gather.submit(tk2.to(dev, non_blocking=True))
+            else:
+                kept[k].copy_(tk2, non_blocking=True)
+        finish_steps()
         torch.cuda.synchronize()
         dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
         assert torch.equal(tk2, tk)
         e2e = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
-               "h2d_bytes_per_step": int(images.numel() * images.element_size()), "d2h_bytes_per_step": int(I * 5 * 4),
+               "h2d_bytes_per_step": int(images.numel() * images.element_size()), "d2h_bytes_per_step": int(I_r * 5 * 4),
                "api": "HotPath.evaluate_stream(batches, depth=2): pinned host views in, host top-5 out, two batches in flight",
                "blocking_call": {"value": n_total * K / dt_block, "ms_per_step": 1e3 * dt_block / K,
                                  "api": "HotPath.evaluate_base(host_views), one blocking call per step"}}
@@ -320,7 +387,7 @@ def main():
     e2e_img = None
     if not args.no_e2e:
         rng = np.random.default_rng(2000 + rank)
-        src = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I)]
+        src = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I_r)]
         gen = jb.TTAViews(n_crops=args.crops, scale=(0.5, 1.0), seed=rank)
 
         def run_images(steps):
@@ -342,7 +409,7 @@ def main():
         torch.cuda.synchronize()
         dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
         e2e_img = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
-                   "h2d_bytes_per_step": int(sum(a.size for a in src)), "d2h_bytes_per_step": int(I * 5 * 4),
+                   "h2d_bytes_per_step": int(sum(a.size for a in src)), "d2h_bytes_per_step": int(I_r * 5 * 4),
                    "note": "host: 500x375 uint8 decoded images + crop-box draw; device: Pillow-exact centre view + "
                            f"{args.crops} RandomResizedCrop(0.5-1)+flip views per image, then the hot path"}
     sampler.stop_flag.set()
@@ -381,7 +448,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tj = json.load(f)
         launches_per_step_top = per_kernel[top]["launches_per_step"]
-        views_per_launch = I * V * model.visual.layers / launches_per_step_top
+        views_per_launch = I_r * V * model.visual.layers / launches_per_step_top
         if abs(views_per_launch - tj["views_per_launch"]) < 0.5 and tj.get("ln_fold", 1) == fold:
             traffic = tj["per_kernel_bytes"].get(top)
     except Exception:  # noqa: BLE001
@@ -398,6 +465,7 @@ def main():
         "gemm_family_tflops": family, "gemm_family_frac": (family / peaks["tflops"]) if family else None,
         "gemm_ms_per_step": g_ms / K,
         "gemm_share_of_kernel_time": (g_ms / K) / kernel_ms_step if kernel_ms_step else None,
+        # per GPU on average: the step's global batch / world (shards may be sized by rank speed)
         "whole_step_tflops": I * V * GFLOP_PER_VIEW / 1e3 / (ms_step / 1e3),
         "whole_step_frac": I * V * GFLOP_PER_VIEW / 1e3 / (ms_step / 1e3) / peaks["tflops"],
         "per_kernel": per_kernel,
@@ -429,7 +497,12 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": workload_config(args, world, images.numel() * images.element_size() / 2**20),
+        "config": dict(workload_config(args, world, I * V * 3 * 224 * 224 * (1 if args.img_dtype == "u8" else 4) / 2**20),
+                       **({"shard_balance": dict(balance, note="same global batch (images_per_gpu_per_step x n_gpus); shards "
+                                                               "sized by each rank's measured speed, dist.balanced_shard_sizes")}
+                          if balance else {}),
+                       **({"topk_all_gather": "every step, asynchronous (dist.AsyncTopkGather)" if G == 1 else
+                           f"once per {K} timed steps, inside the timed region"} if world > 1 else {})),
         "e2e": e2e, "e2e_from_images": e2e_img, "cls_only_last_block": cls_only, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

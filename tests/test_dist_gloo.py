@@ -36,6 +36,22 @@ def _worker(rank, world, port, n_images, ret):
     full = jb.dist.all_gather_topk(local, n_images)
     assert full.shape == (n_images, 5)
     assert torch.equal(full[:, 0], torch.arange(n_images, dtype=torch.int32))
+    # speed-balanced shards: rank 0 is "twice as fast", so it takes about two thirds of the images
+    times = jb.dist.all_gather_floats(1.0 + rank, "cpu")
+    assert times == [1.0, 2.0]
+    sizes = jb.dist.balanced_shard_sizes(n_images, times)
+    assert sum(sizes) == n_images and sizes[0] > sizes[1] >= 1
+    lo2, hi2 = jb.dist.shard_range_from_sizes(sizes, rank)
+    local2 = (torch.arange(lo2, hi2, dtype=torch.int32).view(-1, 1) + torch.arange(5, dtype=torch.int32).view(1, -1))
+    full2 = jb.dist.all_gather_topk(local2, n_images, sizes)
+    assert torch.equal(full2, full)
+    # the asynchronous form: several gathers in flight, slots reused
+    g = jb.dist.AsyncTopkGather(n_images, 5, "cpu", sizes=sizes, depth=2)
+    tickets = [g.submit(local2 + step) for step in range(3)]
+    assert torch.equal(g.result(tickets[2]), full + 2) and torch.equal(g.result(tickets[1]), full + 1)
+    g.drain()
+    with pytest.raises(ValueError):
+        jb.dist.all_gather_topk(local2, n_images, [n_images, 0] if sizes != [n_images, 0] else [0, n_images])
     assert jb.dist.max_over_ranks(10.0 + rank, "cpu") == 10.0 + world - 1
     assert jb.dist.sum_over_ranks(1.0, "cpu") == world
     jb.dist.barrier()
@@ -63,5 +79,22 @@ def test_single_process_helpers_are_noops():
     import jclip_b200 as jb
     t = torch.ones(3, 5, dtype=torch.int32)
     assert jb.dist.all_gather_topk(t, 3) is t
+    g = jb.dist.AsyncTopkGather(3, 5, "cpu")
+    assert g.result(g.submit(t)) is t
+    g.drain()
     assert jb.dist.max_over_ranks(2.5, "cpu") == 2.5
     jb.dist.barrier()
+
+
+def test_balanced_shard_sizes():
+    sys.path.insert(0, ROOT)
+    import jclip_b200 as jb
+    f = jb.dist.balanced_shard_sizes
+    assert f(1024, [1.0] * 8) == [128] * 8
+    s = f(1024, [75, 76, 77, 80, 75, 74, 79, 78])
+    assert sum(s) == 1024 and max(s) == s[5] and min(s) == s[3] and max(s) - min(s) <= 12
+    # the predicted step time (size x seconds per item) is flatter than with equal shards
+    t = [75, 76, 77, 80, 75, 74, 79, 78]
+    assert max(a * b for a, b in zip(s, t)) < 128 * max(t)
+    assert f(7, [1, 1]) in ([4, 3], [3, 4]) and f(2, [1, 100]) == [1, 1] and sum(f(1, [1, 2, 3])) == 1 and f(0, [1, 2]) == [0, 0]
+    assert jb.dist.shard_range_from_sizes([3, 4, 5], 1) == (3, 7)
