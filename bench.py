@@ -238,22 +238,26 @@ def main():
         # equal shards all ranks run at the pace of the slowest.  Images are independent, so the shard boundaries are
         # free: time this rank alone on the equal shard (no collective inside), exchange the timings, and size the shards
         # of the SAME global batch in proportion to speed (dist.balanced_shard_sizes).
-        for _ in range(2):
-            hp.evaluate_base(images, topk_to_host=False)
+        # Two rounds: the second one measures the re-sized shards themselves (and a warmer GPU) and corrects the first.
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        jb.dist.barrier()
-        c0.record()
-        for _ in range(4):
-            hp.evaluate_base(images, topk_to_host=False)
-        c1.record()
-        torch.cuda.synchronize()
-        ms_rank = c0.elapsed_time(c1) / 4
-        ms_all = jb.dist.all_gather_floats(ms_rank, dev)
-        sizes = jb.dist.balanced_shard_sizes(n_total, [m / I for m in ms_all])
-        balance = {"calibration_ms_per_step_by_rank": [round(m, 2) for m in ms_all], "shard_images": sizes}
-        if sizes[rank] != I:
-            images = make_images(sizes[rank])
+        rounds = []
+        for _round in range(2):
+            for _ in range(3):
+                hp.evaluate_base(images, topk_to_host=False)
+            torch.cuda.synchronize()
+            jb.dist.barrier()
+            c0.record()
+            for _ in range(5):
+                hp.evaluate_base(images, topk_to_host=False)
+            c1.record()
+            torch.cuda.synchronize()
+            ms_all = jb.dist.all_gather_floats(c0.elapsed_time(c1) / 5, dev)
+            rounds.append({"shard_images": list(sizes), "ms_per_step_by_rank": [round(m, 2) for m in ms_all]})
+            new_sizes = jb.dist.balanced_shard_sizes(n_total, [m / max(n, 1) for m, n in zip(ms_all, sizes)])
+            if new_sizes[rank] != sizes[rank]:
+                images = make_images(new_sizes[rank])
+            sizes = new_sizes
+        balance = {"calibration": rounds, "shard_images": sizes}
     I_r = sizes[rank]
     lo_r = sum(sizes[:rank])
 
@@ -308,6 +312,8 @@ def main():
     launches = ctx.launch_count - n0
     ms_total = jb.dist.max_over_ranks(ev0.elapsed_time(ev1), dev)
     ms_step = ms_total / K
+    if balance is not None:
+        balance["timed_ms_per_step_by_rank"] = [round(m / K, 2) for m in jb.dist.all_gather_floats(ev0.elapsed_time(ev1), dev)]
     value = n_total * K / (ms_total / 1e3)
 
     # ---- informational: the opt-in schedule that runs the last block on the class-token rows only (results agree to
