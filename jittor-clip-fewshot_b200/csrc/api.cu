@@ -1138,6 +1138,10 @@ MtaParams to_params(const jcb_mta_params* p) {
 }
 }  // namespace
 
+// fp32 work of one solve_mta: P = softmax(100 X T) (2 V C D), the two V x V Gram matrices over the upper triangle
+// (V^2 (C + D)) and <= 50 density / mode passes over X (4 V D each): the figure the MTA profile class reports
+static double mta_flops(double I, double V, double C, double D) { return I * (2 * V * C * D + V * V * (C + D) + 50 * 4 * V * D); }
+
 int jcb_mta(jcb_ctx* ctx, const float* feats_dev, const float* text_dev, int64_t n_images, int32_t n_views,
             int32_t n_classes, int32_t dim, const jcb_mta_params* params, float* out_mode_dev, float* out_logits_dev) {
   if (!ctx) return JCB_E_INVALID;
@@ -1147,7 +1151,7 @@ int jcb_mta(jcb_ctx* ctx, const float* feats_dev, const float* text_dev, int64_t
   int rc = ws_reserve(ctx, scratch);
   if (rc) return rc;
   MtaSet set{feats_dev, text_dev, out_mode_dev, out_logits_dev};
-  LAUNCH_P(ctx, JCB_KC_MTA, 0, static_cast<double>(n_images) * (n_views + 1) * dim * 4,
+  LAUNCH_P(ctx, JCB_KC_MTA, mta_flops(n_images, n_views, n_classes, dim), static_cast<double>(n_images) * (n_views + 1) * dim * 4,
            launch_mta(&set, 1, n_images, n_views, n_classes, dim, to_params(params),
                       scratch ? static_cast<float*>(ctx->ws) : nullptr, ctx->stream));
   return JCB_OK;
@@ -1246,7 +1250,7 @@ int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) 
   MtaSet sets[3] = {{feats, a->text_pt_t_dev, m_pt, nullptr},
                     {feats, a->text_hand_t_dev, m_hand, nullptr},
                     {feats_zs, a->text_zs_t_dev, m_zs, nullptr}};
-  LAUNCH_P(ctx, JCB_KC_MTA, 0, 3.0 * I * (V + 1) * E * 4, launch_mta(sets, 3, I, V, C, E, MtaParams(), scratch, ctx->stream));
+  LAUNCH_P(ctx, JCB_KC_MTA, 3.0 * mta_flops(I, V, C, E), 3.0 * I * (V + 1) * E * 4, launch_mta(sets, 3, I, V, C, E, MtaParams(), scratch, ctx->stream));
   // Channel_LP, logit_normalize, fusion, top-k                        test.py:1710-1738
   HeadArgs h;
   h.m_pt = m_pt; h.m_hand = m_hand; h.m_zs = m_zs;
@@ -1254,7 +1258,7 @@ int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) 
   h.scale1 = a->lp.scale1; h.bias1 = a->lp.bias1; h.fc_w = a->lp.fc_w; h.fc_b = a->lp.fc_b;
   h.I = I; h.C = C; h.D = E; h.rank_by = a->rank_by; h.k = a->k;
   h.out_topk = topk_dev; h.out_scores = a->out_scores_dev; h.out_all = nullptr;
-  LAUNCH_P(ctx, JCB_KC_HEAD, 0, static_cast<double>(I) * (3 * E + a->k) * 4, launch_head(h, ctx->stream));
+  LAUNCH_P(ctx, JCB_KC_HEAD, 10.0 * I * C * E, static_cast<double>(I) * (3 * E + a->k) * 4, launch_head(h, ctx->stream));
   if (a->topk_on_host)
     CUDA_TRY(ctx, cudaMemcpyAsync(a->out_topk, topk_dev, static_cast<size_t>(I) * a->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
   return JCB_OK;
