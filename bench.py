@@ -477,6 +477,32 @@ def main():
         "per_kernel": per_kernel,
     }
 
+    # context for roofline.frac: the plain library GEMM (cuBLAS through torch.matmul: no bias / activation / LayerNorm work)
+    # on the dominant kernel's own shape, back to back for ~0.5 s under the same power cap, after the timed region
+    if world == 1 and top == "gemm_fc1" and not args.no_e2e:
+        try:
+            Mrows = I_r * V * 50
+            ga = torch.randn(Mrows, 768, device=dev).to(torch.bfloat16)
+            gw = torch.randn(3072, 768, device=dev).to(torch.bfloat16)
+            go = torch.empty(Mrows, 3072, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                torch.matmul(ga, gw.t(), out=go)
+            torch.cuda.synchronize()
+            n_it = 300
+            ev0.record()
+            for _ in range(n_it):
+                torch.matmul(ga, gw.t(), out=go)
+            ev1.record()
+            torch.cuda.synchronize()
+            lib_ms = ev0.elapsed_time(ev1) / n_it
+            roofline["library_same_shape"] = {
+                "tflops": 2.0 * Mrows * 3072 * 768 / lib_ms / 1e9, "ms": lib_ms,
+                "what": f"torch.matmul (cuBLAS) bf16 {Mrows} x 3072 x 768, plain GEMM without epilogue work, {n_it} launches "
+                        "back to back after the timed region; informational, not the roofline denominator"}
+            del ga, gw, go
+        except Exception as e:  # noqa: BLE001
+            roofline["library_same_shape"] = {"error": f"{type(e).__name__}: {e}"}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
