@@ -36,6 +36,10 @@ struct MtaDev {
   long long scratch_stride;
   int in_smem;
   int ldx, ldp;         // fast kernel: padded row strides of X and P in shared memory
+  // large view counts (the problem does not fit in shared memory): affinity and bandwidths come from the batched
+  // pre-pass kernels (mta_gram_big_kernel, mta_bw_big_kernel); this kernel is then only the iterative solver
+  const float* A_pre;   // [n_sets * I, V, ldA] or nullptr
+  const float* bw_pre;  // [n_sets * I, V] or nullptr
 };
 
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
@@ -196,6 +200,128 @@ __global__ void __launch_bounds__(256, 1) mta_probs_kernel(const ProbsDev a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Large view counts (V = 513 in the reference's test.py: 512 crops + the centre view).  One CTA per (image, bank) cannot
+// hold the problem on chip, and doing its two V x V x {C, D} Gram matrices and the V^3 rank select inside that one CTA
+// took 76 ms per 16 images (3 banks) -- 48 CTAs on 148 SMs.  Those three pieces are batched over ALL problems here:
+//   mta_gram_big_kernel   G = M M^T per problem, fp32, 64 x 64 tiles of the upper triangle (mirrored on store); M = P
+//                         (affinity, test.py:1411) or M = X (dot products for cdist, test.py:1314-1318)
+//   mta_bw_big_kernel     one warp per (problem, view): distances from the Gram row, rank select, bandwidth (:1403-1408)
+// and mta_kernel below runs only the iterations, reading the affinity from global memory (L2 resident).
+constexpr int GB_TILE = 64, GB_KC = 16;
+
+struct GramBigDev {
+  MtaSet sets[MTA_MAX_SETS];
+  long long I;
+  int V, K, ld, ldg, from_feats;   // from_feats: M = sets[set].feats + img * V * ld, else M = P + problem * V * ld
+  const float* P;
+  float* G;                        // [n_sets * I, V, ldg]
+};
+
+__global__ void __launch_bounds__(256) mta_gram_big_kernel(const GramBigDev a) {
+  __shared__ float As[GB_KC][GB_TILE + 4];   // As[k][i]: k-major so that a thread's 4 rows are one LDS.128
+  __shared__ float Bs[GB_KC][GB_TILE + 4];
+  const int nt = (a.V + GB_TILE - 1) / GB_TILE;
+  // blockIdx.x enumerates the upper-triangle tile pairs (ti <= tj)
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+  const int tj = ti + rem;
+  const long long problem = blockIdx.y;
+  const int set = static_cast<int>(problem / a.I);
+  const long long img = problem % a.I;
+  const float* __restrict__ M = a.from_feats ? a.sets[set].feats + img * a.V * a.ld : a.P + problem * a.V * a.ld;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int k0 = 0; k0 < a.K; k0 += GB_KC) {
+    // 64 rows x 16 k per operand tile: thread t loads row t / 4, k-quad t % 4 (4 consecutive k of one row)
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        const int row = (op == 0 ? ti : tj) * GB_TILE + r;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k0 + kq + e;
+          v[e] = (row < a.V && k < a.K) ? __ldg(M + static_cast<long long>(row) * a.ld + k) : 0.f;
+        }
+        float (*dst)[GB_TILE + 4] = op == 0 ? As : Bs;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[kq + e][r] = v[e];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GB_KC; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(ar[r], br[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+  float* G = a.G + problem * a.V * a.ldg;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = ti * GB_TILE + 4 * ty + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = tj * GB_TILE + 4 * tx + c;
+      if (i < a.V && j < a.V) {
+        G[static_cast<long long>(i) * a.ldg + j] = acc[r][c];
+        if (ti != tj) G[static_cast<long long>(j) * a.ldg + i] = acc[r][c];
+      }
+    }
+  }
+}
+
+struct BwBigDev {
+  const float* G;      // [problems, V, ldg] Gram of X
+  float* bw;           // [problems, V]
+  int V, ldg, k;
+};
+
+__global__ void __launch_bounds__(256) mta_bw_big_kernel(const BwBigDev a) {
+  extern __shared__ __align__(16) float bw_smem[];
+  const int V = a.V;
+  float* s_sq = bw_smem;                 // [V] ||x_j||^2 = the Gram diagonal (same summation as the dots)
+  float* s_rows = bw_smem + V;           // [8][V] one distance row per warp
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long problem = blockIdx.y;
+  const float* __restrict__ G = a.G + problem * V * a.ldg;
+  for (int j = tid; j < V; j += 256) s_sq[j] = __ldg(G + static_cast<long long>(j) * a.ldg + j);
+  __syncthreads();
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= V) return;
+  float* my_row = s_rows + warp * V;
+  const float sqi = s_sq[i];
+  for (int j = lane; j < V; j += 32) {
+    const float d2 = sqi - 2.0f * __ldg(G + static_cast<long long>(i) * a.ldg + j) + s_sq[j];
+    my_row[j] = sqrtf(fmaxf(d2, 0.0f));
+  }
+  __syncwarp();
+  // mean of the squared k smallest distances, skipping rank 0 (the point itself); ties broken by index
+  float acc = 0.f;
+  for (int j = lane; j < V; j += 32) {
+    const float dj = my_row[j];
+    int rank = 0;
+    for (int l = 0; l < V; ++l) {
+      const float dl = my_row[l];
+      rank += (dl < dj || (dl == dj && l < j)) ? 1 : 0;
+    }
+    if (rank >= 1 && rank <= a.k) acc += dj * dj;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) a.bw[problem * V + i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
+}
+
 __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   extern __shared__ __align__(16) float mta_smem[];
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA;
@@ -220,9 +346,15 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   big = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(big) + 15) & ~static_cast<uintptr_t>(15));
   // region R (probabilities, later the view embeddings) and the V x V matrix
   const long long r_elems = static_cast<long long>(V) * (C > D ? C : D);
-  float* R = a.in_smem ? big : a.scratch + problem * a.scratch_stride;
-  float* A = a.in_smem ? big + ((r_elems + 3) & ~3LL) : a.scratch + problem * a.scratch_stride + ((r_elems + 3) & ~3LL);
-
+  const bool pre = a.A_pre != nullptr;   // affinity + bandwidths precomputed (large V): only the solver runs here
+  float* R = a.in_smem ? big : (pre ? nullptr : a.scratch + problem * a.scratch_stride);
+  const float* A = pre ? a.A_pre + problem * static_cast<long long>(V) * ldA
+                       : (a.in_smem ? big + ((r_elems + 3) & ~3LL) : a.scratch + problem * a.scratch_stride + ((r_elems + 3) & ~3LL));
+  float* Aw = const_cast<float*>(A);     // written only when !pre
+  const float* X = Xg;
+  if (pre) {
+    for (int i = tid; i < V; i += MTA_THREADS) s_bw[i] = __ldg(a.bw_pre + problem * V + i);
+  } else {
   if (a.P != nullptr) {
     // ---- 1+2. probabilities were computed for the whole batch by mta_probs_kernel: bring this problem's
     //           V x C block on chip (or use it in place when the problem does not fit in shared memory)
@@ -285,11 +417,10 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
     const int i = idx / V, j = idx % V;
     float s = 0.f;
     for (int c = 0; c < C; ++c) s = fmaf(R[i * C + c], R[j * C + c], s);
-    A[i * ldA + j] = s;
+    Aw[i * ldA + j] = s;
   }
   __syncthreads();
   // ---- 4. bring the view embeddings on chip (region R is free now)
-  const float* X;
   if (a.in_smem) {
     for (int i = tid; i < V * D / 4; i += MTA_THREADS)
       reinterpret_cast<float4*>(R)[i] = __ldg(reinterpret_cast<const float4*>(Xg) + i);
@@ -335,6 +466,7 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
       __syncwarp();
     }
   }
+  }  // !pre
   __syncthreads();
   // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
   for (int i = tid; i < V; i += MTA_THREADS) s_y[i] = 1.0f / static_cast<float>(V);
@@ -346,12 +478,25 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
     density_step(X, s_mode, s_bw, s_dens, V, D);                   // :1426
     for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
       float zmax = -INFINITY;
-      for (int i = tid; i < V; i += MTA_THREADS) {
-        float s = 0.f;
-        for (int j = 0; j < V; ++j) s = fmaf(A[i * ldA + j], s_y[j], s);
-        const float z = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
-        s_z[i] = z;
-        zmax = fmaxf(zmax, z);
+      if (pre) {
+        // A lives in global memory (L2): one warp per row, lanes along the row (coalesced)
+        for (int i = warp; i < V; i += MTA_WARPS) {
+          const float* Ar = A + static_cast<long long>(i) * ldA;
+          float s = 0.f;
+          for (int j = lane; j < V; j += 32) s = fmaf(__ldg(Ar + j), s_y[j], s);
+          s = warp_sum(s);
+          if (lane == 0) s_z[i] = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
+        }
+        __syncthreads();
+        for (int i = tid; i < V; i += MTA_THREADS) zmax = fmaxf(zmax, s_z[i]);
+      } else {
+        for (int i = tid; i < V; i += MTA_THREADS) {
+          float s = 0.f;
+          for (int j = 0; j < V; ++j) s = fmaf(A[i * ldA + j], s_y[j], s);
+          const float z = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
+          s_z[i] = z;
+          zmax = fmaxf(zmax, z);
+        }
       }
       zmax = block_max(zmax, s_red);
       float zs = 0.f;
@@ -714,11 +859,22 @@ static bool mta_fast_enabled() {   // JCB_MTA_FAST=0 keeps the first (256-thread
   return v != 0;
 }
 
+// floats per problem of the large-V path: affinity [V, ldA] + Gram of X [V, ldA] + bandwidths [V]
+static long long big_pre_elems(int V, int ldA) {
+  const long long m = (static_cast<long long>(V) * ldA + 3) & ~3LL;
+  return 2 * m + ((V + 3) & ~3);
+}
+static bool mta_fast_fits(int V, int C, int D) {
+  return mta_use_probs_kernel(C, D) && D % 128 == 0 && mf_smem_bytes(V, C, D) <= MTA_SMEM_LIMIT && mta_fast_enabled();
+}
+
 size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D) {
   size_t b = 0;
   if (mta_use_probs_kernel(C, D)) b += (static_cast<size_t>(n_problems) * V * C * sizeof(float) + 255) / 256 * 256;
-  if (!mta_fits_smem(V, C, D))
-    b += static_cast<size_t>(n_problems) * static_cast<size_t>(big_elems(V, C, D, V | 1)) * sizeof(float);
+  if (!mta_fast_fits(V, C, D) && !mta_fits_smem(V, C, D)) {
+    const long long be = big_elems(V, C, D, V | 1), bp = big_pre_elems(V, V | 1);
+    b += static_cast<size_t>(n_problems) * static_cast<size_t>(be > bp ? be : bp) * sizeof(float);
+  }
   return b;
 }
 
@@ -741,6 +897,8 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
   const long long be = big_elems(V, C, D, a.ldA);
   a.in_smem = mta_fits_smem(V, C, D) ? 1 : 0;
   a.P = nullptr;
+  a.A_pre = nullptr;
+  a.bw_pre = nullptr;
   if (mta_use_probs_kernel(C, D)) {
     if (scratch == nullptr) return cudaErrorInvalidValue;
     const size_t p_bytes = (static_cast<size_t>(n_sets) * I * V * C * sizeof(float) + 255) / 256 * 256;
@@ -776,6 +934,39 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
   if (!a.in_smem && scratch == nullptr) return cudaErrorInvalidValue;
   a.scratch = scratch;
   a.scratch_stride = be;
+  if (!a.in_smem && a.P != nullptr) {
+    // large V: affinity, distances and bandwidths batched over all problems, then one solver CTA per problem
+    const long long n_prob = static_cast<long long>(n_sets) * I;
+    const long long m = (static_cast<long long>(V) * a.ldA + 3) & ~3LL;
+    float* A_all = scratch;
+    float* G_all = scratch + n_prob * m;
+    float* bw_all = scratch + 2 * n_prob * m;
+    if (n_prob > 65535) return cudaErrorInvalidValue;
+    const int nt = (V + GB_TILE - 1) / GB_TILE;
+    GramBigDev g;
+    for (int s2 = 0; s2 < MTA_MAX_SETS; ++s2) g.sets[s2] = a.sets[s2];
+    g.I = I; g.V = V; g.ldg = a.ldA; g.P = a.P;
+    dim3 ggrid(static_cast<unsigned>(nt * (nt + 1) / 2), static_cast<unsigned>(n_prob));
+    g.K = C; g.ld = C; g.from_feats = 0; g.G = A_all;
+    mta_gram_big_kernel<<<ggrid, 256, 0, stream>>>(g);
+    g.K = D; g.ld = D; g.from_feats = 1; g.G = G_all;
+    mta_gram_big_kernel<<<ggrid, 256, 0, stream>>>(g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    BwBigDev b;
+    b.G = G_all; b.bw = bw_all; b.V = V; b.ldg = a.ldA; b.k = a.k;
+    const size_t bw_smem = sizeof(float) * static_cast<size_t>(9) * V;
+    e = ensure_dynamic_smem(mta_bw_big_kernel, bw_smem);
+    if (e != cudaSuccess) return e;
+    dim3 bgrid(static_cast<unsigned>((V + 7) / 8), static_cast<unsigned>(n_prob));
+    mta_bw_big_kernel<<<bgrid, 256, bw_smem, stream>>>(b);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    a.A_pre = A_all;
+    a.bw_pre = bw_all;
+    a.scratch = nullptr;
+    a.scratch_stride = 0;
+  }
   const size_t smem = a.in_smem ? small + static_cast<size_t>(be) * sizeof(float) : small;
   {
     cudaError_t e = ensure_dynamic_smem(mta_kernel, MTA_SMEM_LIMIT);
