@@ -42,6 +42,7 @@ struct MtaDev {
   const float* bw_pre;  // [n_sets * I, V] or nullptr
 };
 
+template <int NW>
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
   v = warp_sum(v);
   __syncthreads();  // protect s_red from the previous use
@@ -49,9 +50,10 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int w = 0; w < MTA_WARPS; ++w) t += s_red[w];
+  for (int w = 0; w < NW; ++w) t += s_red[w];
   return t;
 }
+template <int NW>
 __device__ __forceinline__ float block_max(float v, float* s_red) {
   v = warp_max(v);
   __syncthreads();
@@ -59,15 +61,14 @@ __device__ __forceinline__ float block_max(float v, float* s_red) {
   __syncthreads();
   float t = -INFINITY;
 #pragma unroll
-  for (int w = 0; w < MTA_WARPS; ++w) t = fmaxf(t, s_red[w]);
+  for (int w = 0; w < NW; ++w) t = fmaxf(t, s_red[w]);
   return t;
 }
-
-// gaussian_kernel(mode, bandwidth, X)  (test.py:1310-1313): one warp per view
+template <int NW>
 __device__ __forceinline__ void density_step(const float* __restrict__ X, const float* s_mode, const float* s_bw,
                                              float* s_dens, int V, int D) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = warp; i < V; i += MTA_WARPS) {
+  for (int i = warp; i < V; i += NW) {
     float q = 0.f;
     for (int d = lane; d < D; d += 32) {
       const float t = X[i * D + d] - s_mode[d];
@@ -322,7 +323,11 @@ __global__ void __launch_bounds__(256) mta_bw_big_kernel(const BwBigDev a) {
   if (lane == 0) a.bw[problem * V + i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
 }
 
-__global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
+// NT threads per CTA: 256 for problems held in shared memory, 1024 for the large-V solver (every pass streams X or the
+// affinity from L2: four times the warps, four times the loads in flight)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) mta_kernel(const MtaDev a) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float mta_smem[];
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -341,8 +346,8 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   float* s_z = s_dens + V;            // [V]
   float* s_sq = s_z + V;              // [V]
   float* s_red = s_sq + V;            // [32]
-  float* s_rows = s_red + 32;         // [MTA_WARPS][V] one distance row per warp
-  float* big = s_rows + MTA_WARPS * V;
+  float* s_rows = s_red + 32;         // [NW][V] one distance row per warp
+  float* big = s_rows + 8 * V;   // layout of small_state_bytes(); s_rows is only used by the NT = 256 path
   big = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(big) + 15) & ~static_cast<uintptr_t>(15));
   // region R (probabilities, later the view embeddings) and the V x V matrix
   const long long r_elems = static_cast<long long>(V) * (C > D ? C : D);
@@ -353,19 +358,19 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   float* Aw = const_cast<float*>(A);     // written only when !pre
   const float* X = Xg;
   if (pre) {
-    for (int i = tid; i < V; i += MTA_THREADS) s_bw[i] = __ldg(a.bw_pre + problem * V + i);
+    for (int i = tid; i < V; i += NT) s_bw[i] = __ldg(a.bw_pre + problem * V + i);
   } else {
   if (a.P != nullptr) {
     // ---- 1+2. probabilities were computed for the whole batch by mta_probs_kernel: bring this problem's
     //           V x C block on chip (or use it in place when the problem does not fit in shared memory)
     const float* Pg = a.P + (static_cast<long long>(blockIdx.y) * a.I + img) * V * C;
-    for (int i = tid; i < V * C; i += MTA_THREADS) R[i] = __ldg(Pg + i);
+    for (int i = tid; i < V * C; i += NT) R[i] = __ldg(Pg + i);
     __syncthreads();
   } else {
     // ---- 1. logits = 100 * X T / temperature -> R[v*C + c]      (test.py:1393)
     {
       const float scale = 100.0f / a.p.temperature;
-      for (int c0 = 0; c0 < C; c0 += MTA_THREADS) {
+      for (int c0 = 0; c0 < C; c0 += NT) {
         const int c = c0 + tid;
         const int cc = c < C ? c : C - 1;
         for (int v0 = 0; v0 < V; v0 += VB) {
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
     }
     __syncthreads();
     // ---- 2. row softmax in place
-    for (int v = warp; v < V; v += MTA_WARPS) {
+    for (int v = warp; v < V; v += NW) {
       float mx = -INFINITY;
       for (int c = lane; c < C; c += 32) mx = fmaxf(mx, R[v * C + c]);
       mx = warp_max(mx);
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
     __syncthreads();
   }
   // ---- 3. affinity A = P P^T                                    (test.py:1411)
-  for (int idx = tid; idx < V * V; idx += MTA_THREADS) {
+  for (int idx = tid; idx < V * V; idx += NT) {
     const int i = idx / V, j = idx % V;
     float s = 0.f;
     for (int c = 0; c < C; ++c) s = fmaf(R[i * C + c], R[j * C + c], s);
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   __syncthreads();
   // ---- 4. bring the view embeddings on chip (region R is free now)
   if (a.in_smem) {
-    for (int i = tid; i < V * D / 4; i += MTA_THREADS)
+    for (int i = tid; i < V * D / 4; i += NT)
       reinterpret_cast<float4*>(R)[i] = __ldg(reinterpret_cast<const float4*>(Xg) + i);
     X = R;
   } else {
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   }
   __syncthreads();
   // ---- 5. pairwise distances and per-view bandwidth             (test.py:1314-1318, :1403-1408)
-  for (int i = warp; i < V; i += MTA_WARPS) {
+  for (int i = warp; i < V; i += NW) {
     float q = 0.f;
     for (int d = lane; d < D; d += 32) q = fmaf(X[i * D + d], X[i * D + d], q);
     q = warp_sum(q);
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   __syncthreads();
   {
     float* my_row = s_rows + warp * V;
-    for (int i = warp; i < V; i += MTA_WARPS) {
+    for (int i = warp; i < V; i += NW) {
       for (int j = 0; j < V; ++j) {
         float dot = 0.f;
         for (int d = lane; d < D; d += 32) dot = fmaf(X[i * D + d], X[j * D + d], dot);
@@ -469,18 +474,18 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
   }  // !pre
   __syncthreads();
   // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
-  for (int i = tid; i < V; i += MTA_THREADS) s_y[i] = 1.0f / static_cast<float>(V);
-  for (int d = tid; d < D; d += MTA_THREADS) s_mode[d] = X[d];
+  for (int i = tid; i < V; i += NT) s_y[i] = 1.0f / static_cast<float>(V);
+  for (int d = tid; d < D; d += NT) s_mode[d] = X[d];
   __syncthreads();
 
   const float inv_lambda_y = 1.0f / a.p.lambda_y;
   for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
-    density_step(X, s_mode, s_bw, s_dens, V, D);                   // :1426
+    density_step<NW>(X, s_mode, s_bw, s_dens, V, D);                   // :1426
     for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
       float zmax = -INFINITY;
       if (pre) {
         // A lives in global memory (L2): one warp per row, lanes along the row (coalesced)
-        for (int i = warp; i < V; i += MTA_WARPS) {
+        for (int i = warp; i < V; i += NW) {
           const float* Ar = A + static_cast<long long>(i) * ldA;
           float s = 0.f;
           for (int j = lane; j < V; j += 32) s = fmaf(__ldg(Ar + j), s_y[j], s);
@@ -488,9 +493,9 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
           if (lane == 0) s_z[i] = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
         }
         __syncthreads();
-        for (int i = tid; i < V; i += MTA_THREADS) zmax = fmaxf(zmax, s_z[i]);
+        for (int i = tid; i < V; i += NT) zmax = fmaxf(zmax, s_z[i]);
       } else {
-        for (int i = tid; i < V; i += MTA_THREADS) {
+        for (int i = tid; i < V; i += NT) {
           float s = 0.f;
           for (int j = 0; j < V; ++j) s = fmaf(A[i * ldA + j], s_y[j], s);
           const float z = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
@@ -498,65 +503,65 @@ __global__ void __launch_bounds__(MTA_THREADS, 1) mta_kernel(const MtaDev a) {
           zmax = fmaxf(zmax, z);
         }
       }
-      zmax = block_max(zmax, s_red);
+      zmax = block_max<NW>(zmax, s_red);
       float zs = 0.f;
-      for (int i = tid; i < V; i += MTA_THREADS) {
+      for (int i = tid; i < V; i += NT) {
         const float e = expf(s_z[i] - zmax);
         s_z[i] = e;
         zs += e;
       }
-      zs = block_sum(zs, s_red);
+      zs = block_sum<NW>(zs, s_red);
       const float inv = 1.0f / zs;
       float diff = 0.f;
-      for (int i = tid; i < V; i += MTA_THREADS) {
+      for (int i = tid; i < V; i += NT) {
         const float yn = s_z[i] * inv;
         const float t = s_y[i] - yn;
         diff = fmaf(t, t, diff);
         s_z[i] = yn;
       }
-      diff = block_sum(diff, s_red);
+      diff = block_sum<NW>(diff, s_red);
       // all threads finished reading s_y inside the A*y products before block_max's barrier
-      for (int i = tid; i < V; i += MTA_THREADS) s_y[i] = s_z[i];
+      for (int i = tid; i < V; i += NT) s_y[i] = s_z[i];
       __syncthreads();
       if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1436
     }
     for (int it = 1;; ++it) {                                      // mode loop :1443-1453
-      density_step(X, s_mode, s_bw, s_dens, V, D);                 // :1446
+      density_step<NW>(X, s_mode, s_bw, s_dens, V, D);                 // :1446
       float wsum = 0.f;
-      for (int i = tid; i < V; i += MTA_THREADS) {
+      for (int i = tid; i < V; i += NT) {
         const float w = s_dens[i] * s_y[i];                        // :1447
         s_z[i] = w;
         wsum += w;
       }
-      wsum = block_sum(wsum, s_red);
+      wsum = block_sum<NW>(wsum, s_red);
       float nrm = 0.f;
-      for (int d = tid; d < D; d += MTA_THREADS) {
+      for (int d = tid; d < D; d += NT) {
         float s = 0.f;
         for (int i = 0; i < V; ++i) s = fmaf(s_z[i], X[i * D + d], s);
         s = s / wsum;                                              // :1448
         s_new[d] = s;
         nrm = fmaf(s, s, nrm);
       }
-      nrm = block_sum(nrm, s_red);
+      nrm = block_sum<NW>(nrm, s_red);
       const float inv = 1.0f / sqrtf(nrm);                         // :1449
       float diff = 0.f;
-      for (int d = tid; d < D; d += MTA_THREADS) {
+      for (int d = tid; d < D; d += NT) {
         const float m = s_new[d] * inv;
         const float t = s_mode[d] - m;
         diff = fmaf(t, t, diff);
         s_new[d] = m;
       }
-      diff = block_sum(diff, s_red);
-      for (int d = tid; d < D; d += MTA_THREADS) s_mode[d] = s_new[d];
+      diff = block_sum<NW>(diff, s_red);
+      for (int d = tid; d < D; d += NT) s_mode[d] = s_new[d];
       __syncthreads();
       if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
     }
   }
 
   // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
-  for (int d = tid; d < D; d += MTA_THREADS) set.out_mode[img * D + d] = s_mode[d];
+  for (int d = tid; d < D; d += NT) set.out_mode[img * D + d] = s_mode[d];
   if (set.out_logits) {
-    for (int c = tid; c < C; c += MTA_THREADS) {
+    for (int c = tid; c < C; c += NT) {
       float s = 0.f;
       for (int d = 0; d < D; ++d) s = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s);
       set.out_logits[img * C + c] = s * 100.0f;
@@ -968,12 +973,16 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     a.scratch_stride = 0;
   }
   const size_t smem = a.in_smem ? small + static_cast<size_t>(be) * sizeof(float) : small;
-  {
-    cudaError_t e = ensure_dynamic_smem(mta_kernel, MTA_SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-  }
   dim3 grid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
-  mta_kernel<<<grid, MTA_THREADS, smem, stream>>>(a);
+  if (a.A_pre != nullptr) {
+    cudaError_t e = ensure_dynamic_smem(mta_kernel<1024>, smem);
+    if (e != cudaSuccess) return e;
+    mta_kernel<1024><<<grid, 1024, smem, stream>>>(a);
+  } else {
+    cudaError_t e = ensure_dynamic_smem(mta_kernel<MTA_THREADS>, MTA_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    mta_kernel<MTA_THREADS><<<grid, MTA_THREADS, smem, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 

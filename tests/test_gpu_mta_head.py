@@ -137,13 +137,15 @@ def test_fused_head_all_scores(jb, cuda_dev):
             assert set(topk[i].cpu().tolist()) == set(topk_lowest_index_first(ref[name], 5)[0].tolist())
 
 
-def test_pipeline_matches_oracle_given_same_embeddings(jb, cuda_dev):
+@pytest.mark.parametrize("I,V", [(12, 9), (3, 100)])
+def test_pipeline_matches_oracle_given_same_embeddings(jb, cuda_dev, I, V):
     """jcb_pipeline end to end (2-layer tower to keep the oracle fast): the views' embeddings come back
-    from the call, the oracle runs MTA x3 + head on THOSE embeddings, top-5 must agree."""
+    from the call, the oracle runs MTA x3 + head on THOSE embeddings, top-5 must agree.  V = 100 does not fit in
+    shared memory: the three banks go through the batched large-V path (mta_gram_big_kernel / mta_bw_big_kernel and
+    the 1024-thread solver), the route the reference's own 512 crops take."""
     from oracle import pipeline_image
     sd = jb.synth.make_vit_state_dict(seed=4, layers=2)
     model = jb.jclip.build_model(sd)
-    I, V = 12, 9
     imgs = torch.from_numpy(jb.synth.make_views(11, I, V))
     Ts = _texts(jb, 3)
     lp_np = jb.synth.make_head(2, Ts[2].numpy())
