@@ -305,21 +305,37 @@ __global__ void __launch_bounds__(256) mta_bw_big_kernel(const BwBigDev a) {
   const float sqi = s_sq[i];
   for (int j = lane; j < V; j += 32) {
     const float d2 = sqi - 2.0f * __ldg(G + static_cast<long long>(i) * a.ldg + j) + s_sq[j];
-    my_row[j] = sqrtf(fmaxf(d2, 0.0f));
+    my_row[j] = fabsf(sqrtf(fmaxf(d2, 0.0f)));   // never -0: the bisection below orders bit patterns
   }
   __syncwarp();
-  // mean of the squared k smallest distances, skipping rank 0 (the point itself); ties broken by index
-  float acc = 0.f;
+  // Mean of the squared k smallest distances, skipping rank 0 (test.py:1404-1408: sorted_dist[:, 1:k+1]).  Counting
+  // every element's rank is V^2 compares per row (V^3 per problem: 135 M at V = 513); instead find the value t of rank
+  // k by bisection on the bit pattern (distances are >= 0, so their uint32 images order like the floats): ranks 0..k
+  // are the elements below t plus (k + 1 - #below) copies of t, and rank 0 is the row minimum -- equal values are
+  // interchangeable in a sum of squares, so the index tie-break of the sort does not matter.
+  const int kk = a.k < V - 1 ? a.k : V - 1;          // rank of the threshold element (0-based)
+  uint32_t lo = 0u, hi = 0x7f800000u;                 // invariant: #(d <= lo - 1) <= kk < #(d <= hi)
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int cnt = 0;
+    for (int j = lane; j < V; j += 32) cnt += __float_as_uint(my_row[j]) <= mid ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (cnt > kk) hi = mid; else lo = mid + 1;
+  }
+  const float t = __uint_as_float(lo);                // the (kk + 1)-th smallest distance
+  float below = 0.f, mn = INFINITY;
+  int n_below = 0;
   for (int j = lane; j < V; j += 32) {
     const float dj = my_row[j];
-    int rank = 0;
-    for (int l = 0; l < V; ++l) {
-      const float dl = my_row[l];
-      rank += (dl < dj || (dl == dj && l < j)) ? 1 : 0;
-    }
-    if (rank >= 1 && rank <= a.k) acc += dj * dj;
+    mn = fminf(mn, dj);
+    if (dj < t) { below = fmaf(dj, dj, below); ++n_below; }
   }
-  acc = warp_sum(acc);
+  below = warp_sum(below);
+  mn = -warp_max(-mn);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_below += __shfl_xor_sync(0xffffffffu, n_below, o);
+  const float acc = below + static_cast<float>(kk + 1 - n_below) * t * t - mn * mn;
   if (lane == 0) a.bw[problem * V + i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
 }
 
