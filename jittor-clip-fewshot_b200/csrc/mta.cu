@@ -604,14 +604,16 @@ __host__ __device__ inline int mf_pad(int n) {
   return ld;
 }
 
+template <int NT>
 __device__ __forceinline__ float mf_block_sum(float v, float* s_red) {
+  constexpr int NW = NT / 32;
   v = warp_sum(v);
   __syncthreads();  // protect s_red from the previous use
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int w = 0; w < MF_WARPS; ++w) t += s_red[w];
+  for (int w = 0; w < NW; ++w) t += s_red[w];
   return t;
 }
 
@@ -619,10 +621,11 @@ __device__ __forceinline__ float mf_block_sum(float v, float* s_red) {
 // zero).  One thread = one 4 x 4 tile of the upper triangle; tile t of a dimension owns rows t, t + nt, t + 2 nt,
 // t + 3 nt so that neighbouring threads (neighbouring column tiles) read neighbouring rows: conflict-free LDS.128,
 // and the row tile they share is a broadcast.
+template <int NT>
 __device__ void mf_gram(const float* __restrict__ M, int ld, int K4, int V, float* __restrict__ G, int ldg) {
   const int nt = (V + 3) >> 2;
   const int npairs = nt * (nt + 1) / 2;
-  for (int p = threadIdx.x; p < npairs; p += MF_THREADS) {
+  for (int p = threadIdx.x; p < npairs; p += NT) {
     int ta = 0, rem = p;
     while (rem >= nt - ta) { rem -= nt - ta; ++ta; }
     const int tb = ta + rem;
@@ -668,15 +671,17 @@ __device__ void mf_gram(const float* __restrict__ M, int ld, int K4, int V, floa
 }
 
 // gaussian_kernel(mode, bandwidth, X)  (test.py:1310-1313): one warp per view, the mode in registers
+template <int NT>
 __device__ __forceinline__ void mf_density(const float* __restrict__ X, int ldx, const float* s_mode,
                                            const float* s_bw, float* s_dens, int V, int D) {
+  constexpr int NW = NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nq = D >> 7;  // float4 per lane, D % 128 == 0, D <= 1024
   float4 m[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q)
     if (q < nq) m[q] = *reinterpret_cast<const float4*>(s_mode + 128 * q + 4 * lane);
-  for (int i = warp; i < V; i += MF_WARPS) {
+  for (int i = warp; i < V; i += NW) {
     const float* xr = X + i * ldx + 4 * lane;
     float acc = 0.f;
 #pragma unroll
@@ -698,7 +703,12 @@ __device__ __forceinline__ void mf_density(const float* __restrict__ X, int ldx,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(MF_THREADS, 1) mta_fast_kernel(const MtaDev a) {
+// NT = 512 threads and one CTA per SM for the headline view counts (V = 65: 168 KB of shared memory); NT = 128 and up to
+// four CTAs per SM for V <= 32, where a problem is a few KB and 512 threads mostly wait at barriers (N = 1 and N = 16
+// crops: thousands of tiny problems per step).
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : 4) mta_fast_kernel(const MtaDev a) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float mta_smem[];
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA, ldx = a.ldx, ldp = a.ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -725,34 +735,34 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mta_fast_kernel(const MtaDev a)
   // ---- 1+2. this problem's V x C block of softmax(100 X T) (mta_probs_kernel), zero padded to ldp columns
   {
     const float* Pg = a.P + (static_cast<long long>(blockIdx.y) * a.I + img) * V * C;
-    for (int i = tid; i < V * ldp; i += MF_THREADS) {
+    for (int i = tid; i < V * ldp; i += NT) {
       const int v = i / ldp, c = i - v * ldp;
       R[i] = c < C ? __ldg(Pg + v * C + c) : 0.f;
     }
   }
   __syncthreads();
   // ---- 3. affinity A = P P^T                                    (test.py:1411)
-  mf_gram(R, ldp, ldp >> 2, V, A, ldA);
+  mf_gram<NT>(R, ldp, ldp >> 2, V, A, ldA);
   __syncthreads();
   // ---- 4. the view embeddings replace P on chip
-  for (int i = tid; i < V * (D >> 2); i += MF_THREADS) {
+  for (int i = tid; i < V * (D >> 2); i += NT) {
     const int v = i / (D >> 2), c4 = i - v * (D >> 2);
     *reinterpret_cast<float4*>(R + v * ldx + 4 * c4) = __ldg(reinterpret_cast<const float4*>(Xg + v * D) + c4);
   }
   __syncthreads();
   const float* X = R;
   // ---- 5. pairwise distances and per-view bandwidth             (test.py:1314-1318, :1403-1408)
-  mf_gram(X, ldx, D >> 2, V, Dm, ldA);
+  mf_gram<NT>(X, ldx, D >> 2, V, Dm, ldA);
   __syncthreads();
-  for (int i = tid; i < V; i += MF_THREADS) s_sq[i] = Dm[i * ldA + i];   // ||x_i||^2, same summation as the dots
+  for (int i = tid; i < V; i += NT) s_sq[i] = Dm[i * ldA + i];   // ||x_i||^2, same summation as the dots
   __syncthreads();
-  for (int idx = tid; idx < V * V; idx += MF_THREADS) {
+  for (int idx = tid; idx < V * V; idx += NT) {
     const int i = idx / V, j = idx - i * V;
     const float d2 = s_sq[i] - 2.0f * Dm[i * ldA + j] + s_sq[j];
     Dm[i * ldA + j] = sqrtf(fmaxf(d2, 0.0f));
   }
   __syncthreads();
-  for (int i = warp; i < V; i += MF_WARPS) {
+  for (int i = warp; i < V; i += NW) {
     // mean of the squared k smallest distances, skipping rank 0 (the point itself)
     const float* my_row = Dm + i * ldA;
     float acc = 0.f;
@@ -769,15 +779,15 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mta_fast_kernel(const MtaDev a)
     if (lane == 0) s_bw[i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
   }
   // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
-  for (int i = tid; i < V; i += MF_THREADS) s_y[i] = 1.0f / static_cast<float>(V);
-  for (int d = tid; d < D; d += MF_THREADS) s_mode[d] = X[d];
+  for (int i = tid; i < V; i += NT) s_y[i] = 1.0f / static_cast<float>(V);
+  for (int d = tid; d < D; d += NT) s_mode[d] = X[d];
   __syncthreads();
 
   const float inv_lambda_y = 1.0f / a.p.lambda_y;
   for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
-    mf_density(X, ldx, s_mode, s_bw, s_dens, V, D);                // :1426
+    mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);                // :1426
     for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
-      for (int i = warp; i < V; i += MF_WARPS) {                   // z = (rho + lambda_q A y) / lambda_y
+      for (int i = warp; i < V; i += NW) {                   // z = (rho + lambda_q A y) / lambda_y
         float s = 0.f;
         for (int j = lane; j < V; j += 32) s = fmaf(A[i * ldA + j], s_y[j], s);
         s = warp_sum(s);
@@ -810,9 +820,9 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mta_fast_kernel(const MtaDev a)
       if (sqrtf(s_red[31]) < a.p.th || it >= a.p.max_iter) break;  // :1436
     }
     for (int it = 1;; ++it) {                                      // mode loop :1443-1453
-      mf_density(X, ldx, s_mode, s_bw, s_dens, V, D);              // :1446
+      mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);              // :1446
       float nrm = 0.f;
-      for (int d = tid; d < D; d += MF_THREADS) {
+      for (int d = tid; d < D; d += NT) {
         float s = 0.f, wsum = 0.f;
         for (int i = 0; i < V; ++i) {
           const float w = s_dens[i] * s_y[i];                      // :1447
@@ -823,26 +833,26 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mta_fast_kernel(const MtaDev a)
         s_new[d] = s;
         nrm = fmaf(s, s, nrm);
       }
-      nrm = mf_block_sum(nrm, s_red);
+      nrm = mf_block_sum<NT>(nrm, s_red);
       const float inv = 1.0f / sqrtf(nrm);                         // :1449
       float diff = 0.f;
-      for (int d = tid; d < D; d += MF_THREADS) {
+      for (int d = tid; d < D; d += NT) {
         const float m = s_new[d] * inv;
         const float t = s_mode[d] - m;
         diff = fmaf(t, t, diff);
         s_new[d] = m;
       }
-      diff = mf_block_sum(diff, s_red);
-      for (int d = tid; d < D; d += MF_THREADS) s_mode[d] = s_new[d];
+      diff = mf_block_sum<NT>(diff, s_red);
+      for (int d = tid; d < D; d += NT) s_mode[d] = s_new[d];
       __syncthreads();
       if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
     }
   }
 
   // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
-  for (int d = tid; d < D; d += MF_THREADS) set.out_mode[img * D + d] = s_mode[d];
+  for (int d = tid; d < D; d += NT) set.out_mode[img * D + d] = s_mode[d];
   if (set.out_logits) {
-    for (int c = tid; c < C; c += MF_THREADS) {
+    for (int c = tid; c < C; c += NT) {
       float s = 0.f;
       for (int d = 0; d < D; ++d) s = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s);
       set.out_logits[img * C + c] = s * 100.0f;
@@ -944,12 +954,17 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     a.in_smem = 1;
     a.scratch = nullptr;
     a.scratch_stride = 0;
-    {
-      cudaError_t e = ensure_dynamic_smem(mta_fast_kernel, MTA_SMEM_LIMIT);
-      if (e != cudaSuccess) return e;
-    }
     dim3 fgrid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
-    mta_fast_kernel<<<fgrid, MF_THREADS, mf_smem_bytes(V, C, D), stream>>>(a);
+    const size_t fsmem = mf_smem_bytes(V, C, D);
+    if (V <= 32) {
+      cudaError_t e = ensure_dynamic_smem(mta_fast_kernel<128>, fsmem);
+      if (e != cudaSuccess) return e;
+      mta_fast_kernel<128><<<fgrid, 128, fsmem, stream>>>(a);
+    } else {
+      cudaError_t e = ensure_dynamic_smem(mta_fast_kernel<MF_THREADS>, MTA_SMEM_LIMIT);
+      if (e != cudaSuccess) return e;
+      mta_fast_kernel<MF_THREADS><<<fgrid, MF_THREADS, fsmem, stream>>>(a);
+    }
     return cudaGetLastError();
   }
   if (!a.in_smem && scratch == nullptr) return cudaErrorInvalidValue;
