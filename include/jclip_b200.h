@@ -35,7 +35,7 @@ extern "C" {
 #define JCB_E_KERNEL (-5)      /* a kernel reported a device-side status (pipeline timeout) */
 #define JCB_E_NOMEM (-6)
 
-#define JCB_ABI_VERSION 2
+#define JCB_ABI_VERSION 3
 
 typedef struct jcb_ctx jcb_ctx;
 typedef struct jcb_vit jcb_vit;
@@ -83,6 +83,19 @@ int jcb_ctx_set_host_chunk_views(jcb_ctx* ctx, int64_t chunk_views);
  * (different attention summation order for that one row).  Ignored by jcb_vit_debug_tokens consumers that read
  * other rows of the last block: with the option on, only row 0 of every view is defined there. */
 int jcb_ctx_set_cls_only_last_block(jcb_ctx* ctx, int on);
+/* Element type of every 16-bit GEMM operand of the towers packed AFTER this call (weights, the residual copy the
+ * LayerNorm-folded GEMMs read, q|k|v, softmax numerators, attention output, MLP hidden); accumulation is fp32 in
+ * TMEM either way and tcgen05.mma kind::f16 runs both at the same rate.
+ *   JCB_OPERAND_F16  (default; env JCB_OPERANDS=f16): 11-bit significands -- end to end the x100 logits stay within
+ *                    1e-2 of the fp32 reference (BASELINE north star; measured 0.005-0.008), conversions saturate at
+ *                    +-65504 instead of overflowing.
+ *   JCB_OPERAND_BF16 (env JCB_OPERANDS=bf16): the north star's literal wording; 8-bit significands put the logits
+ *                    0.02-0.07 off.
+ * A tower keeps the type it was finalized with (jcb_vit_operand_type); re-finalize to change it. */
+#define JCB_OPERAND_BF16 0
+#define JCB_OPERAND_F16 1
+int jcb_ctx_set_operand_type(jcb_ctx* ctx, int operand_type);
+int jcb_ctx_get_operand_type(const jcb_ctx* ctx);
 /* Wait for the context's stream and report any device-side kernel status. */
 int jcb_sync(jcb_ctx* ctx);
 const char* jcb_last_error(const jcb_ctx* ctx);
@@ -142,6 +155,8 @@ int jcb_vit_clear_lora(jcb_vit* vit);
  * bias / embedding / final projection parameters stay fp32.  Must be called after the last set_param /
  * set_lora and before jcb_encode_image; may be called again after the adapters change. */
 int jcb_vit_finalize(jcb_vit* vit);
+/* JCB_OPERAND_* the device weights were packed with by the last jcb_vit_finalize. */
+int jcb_vit_operand_type(const jcb_vit* vit);
 
 /* `CLIP.encode_image(image)` (jclip/model.py:199-200 -> VisionTransformer.execute :104-126).
  *   images_dev   [n_views, 3, R, R] on the device, element type `img_dtype`
@@ -180,6 +195,7 @@ int jcb_text_set_param(jcb_text* text, const char* name, const float* data, int6
 int jcb_text_set_lora(jcb_text* text, int layer, int proj, const float* A, const float* B, int r, float scaling);
 int jcb_text_clear_lora(jcb_text* text);
 int jcb_text_finalize(jcb_text* text);
+int jcb_text_operand_type(const jcb_text* text);
 /* tokens_dev [n_seq, context_length] int64 (what `clip.tokenize` returns); out_dev [n_seq, embed_dim] float32;
  * normalize != 0 fuses `/ norm(dim=-1)` (test.py:929) */
 int jcb_encode_text(jcb_text* text, const int64_t* tokens_dev, int64_t n_seq, int normalize, float* out_dev);
@@ -307,17 +323,53 @@ int jcb_pipeline_submit(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* 
 int jcb_pipeline_wait(jcb_ctx* ctx, int64_t ticket);
 
 /* ---------------------------------------------------------------- building blocks (tests) ---- */
-/* C[M,N] = A[M,K] (bf16) * B[N,K]^T (bf16) with the fused epilogues of the tower; see csrc/kernels.h. */
-int jcb_gemm_bf16(jcb_ctx* ctx, const void* A_dev, const void* B_dev, int32_t M, int32_t N, int32_t K,
-                  const float* bias_dev, int32_t epilogue, void* out_dev, int64_t ldo);
-int jcb_layernorm_bf16(jcb_ctx* ctx, const float* x_dev, int64_t rows, int32_t width, const float* gamma_dev,
-                       const float* beta_dev, void* out_bf16_dev);
+/* GEMM epilogues fused into the tcgen05 kernel (csrc/kernels.h GemmEpilogue) */
+#define JCB_EPI_BIAS_16 0            /* out16 = acc + bias                                   (QKV projection) */
+#define JCB_EPI_BIAS_GELU_16 1       /* out16 = quickgelu(acc + bias)   jclip/model.py:27   (MLP c_fc) */
+#define JCB_EPI_BIAS_RESID_F32 2     /* out32 += acc + bias             jclip/model.py:60-61 */
+#define JCB_EPI_F32 4                /* out32 = acc (+ bias) */
+#define JCB_EPI_LNFOLD_16 5          /* out16 = r[m] acc - r[m] mu[m] colsum[n] + bias[n]: LayerNorm folded into the GEMM */
+#define JCB_EPI_LNFOLD_GELU_16 6     /* quickgelu of that */
+#define JCB_EPI_RESID_LNPREP_SHORT 7 /* out32 += acc + bias; out2_16 = out32 - shift[m]; stats[m, n / 256] = (sum, sumsq) of out2 */
+#define JCB_EPI_RESID_LNPREP_LONG 8  /* same, staging tuned for long K */
+/* C[M,N] = A[M,K] * B[N,K]^T, A / B 16-bit operands of `operand_type`, with the fused epilogues of the tower
+ * (jclip/model.py:38-39, :59-62, jclip/mha.py:129-146, :461).  The LayerNorm-fold fields are what the tower passes
+ * between its GEMMs (csrc/api.cu tower_blocks): tests drive the epilogues directly through them. */
+typedef struct jcb_gemm_args {
+  const void* A_dev;        /* [M, K] row-major */
+  const void* B_dev;        /* [N, K] row-major (nn.Linear weight layout) */
+  int32_t M, N, K;
+  int32_t operand_type;     /* JCB_OPERAND_* */
+  const float* bias_dev;    /* [N] or NULL */
+  int32_t epilogue;         /* JCB_EPI_* */
+  int32_t stats_slots;      /* partial-sum slots per row (N / 256 of the producer) */
+  void* out_dev;            /* 16-bit or fp32 according to the epilogue */
+  int64_t ldo;
+  float* stats_dev;         /* LNFOLD: in, LNPREP: out; [M, stats_slots, 2] */
+  const float* colsum_dev;  /* LNFOLD: S[N] = sum_k of the rounded folded weight */
+  void* out2_dev;           /* LNPREP: centred 16-bit copy [M, N] */
+  const float* stats_in_dev;   /* LNPREP: previous LayerNorm point's statistics / shift, or NULL (shift 0) */
+  const float* shift_in_dev;
+  float* shift_out_dev;     /* LNPREP: [M] or NULL */
+  int64_t stats_in_row_stride;
+} jcb_gemm_args;
+int jcb_gemm(jcb_ctx* ctx, const jcb_gemm_args* args);
+/* Weight preparation of a LayerNorm-folded GEMM: Wf[n,k] = round16(gamma[k] W[n,k]); S[n] = sum_k Wf[n,k];
+ * c[n] = sum_k beta[k] W[n,k] + bias[n]   (LN(x) W^T + b = r (x Wf^T) - r mu S + c; jclip/model.py:17-21, :59-62) */
+int jcb_fold_ln(jcb_ctx* ctx, const float* W_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev,
+                int32_t N, int32_t K, int32_t operand_type, void* Wf_dev, float* S_dev, float* c_dev);
+int jcb_layernorm(jcb_ctx* ctx, const float* x_dev, int64_t rows, int32_t width, const float* gamma_dev,
+                  const float* beta_dev, int32_t operand_type, void* out16_dev);
 /* `tfm_clip` + the patch extraction of conv1 (test.py:1301, jclip/model.py:105-108): images_dev [n_views, 3, R, R]
- * (JCB_IMG_*) -> patches_bf16_dev [n_views * (R/P)^2, 3 * P * P], row = (view, py, px), column = (c, i, j). */
-int jcb_im2col_bf16(jcb_ctx* ctx, const void* images_dev, int32_t img_dtype, int64_t n_views, int32_t resolution,
-                    int32_t patch, int32_t apply_clip_norm, void* patches_bf16_dev);
-int jcb_attention_bf16(jcb_ctx* ctx, const void* qkv_bf16_dev, int64_t n_views, int32_t tokens, int32_t heads,
-                       void* out_bf16_dev);
+ * (JCB_IMG_*) -> patches16_dev [n_views * (R/P)^2, 3 * P * P], row = (view, py, px), column = (c, i, j). */
+int jcb_im2col(jcb_ctx* ctx, const void* images_dev, int32_t img_dtype, int64_t n_views, int32_t resolution,
+               int32_t patch, int32_t apply_clip_norm, int32_t operand_type, void* patches16_dev);
+/* softmax(q k^T / 8 [+ causal mask]) v per (sequence, head) (jclip/mha.py:55-83; mask jclip/model.py:189-193):
+ * qkv16_dev [n_views * tokens, 3 * 64 * heads] -> out16_dev [n_views * tokens, 64 * heads]; tokens <= 128 */
+int jcb_attention(jcb_ctx* ctx, const void* qkv16_dev, int64_t n_views, int32_t tokens, int32_t heads, int32_t causal,
+                  int32_t operand_type, void* out16_dev);
+/* hits / misses of the process-wide cache of encoded TMA tensor maps (one entry per (pointer, shape) launched) */
+void jcb_tensor_map_cache_stats(uint64_t* hits, uint64_t* misses);
 
 /* ---------------------------------------------------------------- DLPack hand-off ------------ */
 /* Zero-copy variant of jcb_encode_image taking DLManagedTensor* (dlpack.h ABI v0.x).  Tensors are

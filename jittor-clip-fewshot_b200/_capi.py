@@ -15,7 +15,7 @@ LIB_PATH = PKG_DIR / "libjclip_b200.so"
 
 JCB_OK = 0
 JCB_E_INVALID, JCB_E_CUDA, JCB_E_STATE, JCB_E_NO_DEVICE, JCB_E_KERNEL, JCB_E_NOMEM = -1, -2, -3, -4, -5, -6
-JCB_ABI_VERSION = 2
+JCB_ABI_VERSION = 3
 MAX_INFLIGHT = 4   # JCB_MAX_INFLIGHT
 IMG_F32, IMG_BF16, IMG_U8 = 0, 1, 2
 PROJ_Q, PROJ_K, PROJ_V, PROJ_O = 0, 1, 2, 3
@@ -23,7 +23,12 @@ SCORE_NAMES = ("logits", "cs", "cs1", "cs2", "cs3", "cs4", "cs5")
 SCORE_INDEX = {n: i for i, n in enumerate(SCORE_NAMES)}
 KC_COUNT = 14
 FILTER_BILINEAR, FILTER_BICUBIC = 0, 1
-EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32, EPI_F32 = 0, 1, 2, 3, 4
+# JCB_EPI_* (epilogue 3, the conv1 scatter, no longer exists)
+EPI_BIAS_16, EPI_BIAS_GELU_16, EPI_BIAS_RESID_F32, EPI_F32 = 0, 1, 2, 4
+EPI_LNFOLD_16, EPI_LNFOLD_GELU_16, EPI_RESID_LNPREP_SHORT, EPI_RESID_LNPREP_LONG = 5, 6, 7, 8
+OPERAND_BF16, OPERAND_F16 = 0, 1
+OPERAND_NAMES = {"bf16": OPERAND_BF16, "f16": OPERAND_F16, "fp16": OPERAND_F16, "float16": OPERAND_F16,
+                 "bfloat16": OPERAND_BF16}
 
 _ERR_NAMES = {-1: "JCB_E_INVALID", -2: "JCB_E_CUDA", -3: "JCB_E_STATE", -4: "JCB_E_NO_DEVICE", -5: "JCB_E_KERNEL",
               -6: "JCB_E_NOMEM"}
@@ -58,6 +63,14 @@ class ViewJob(Structure):
                 ("flip", c_int32), ("reserved", c_int32)]
 
 
+class GemmArgs(Structure):
+    _fields_ = [("A_dev", c_void_p), ("B_dev", c_void_p), ("M", c_int32), ("N", c_int32), ("K", c_int32),
+                ("operand_type", c_int32), ("bias_dev", c_void_p), ("epilogue", c_int32), ("stats_slots", c_int32),
+                ("out_dev", c_void_p), ("ldo", c_int64), ("stats_dev", c_void_p), ("colsum_dev", c_void_p),
+                ("out2_dev", c_void_p), ("stats_in_dev", c_void_p), ("shift_in_dev", c_void_p),
+                ("shift_out_dev", c_void_p), ("stats_in_row_stride", c_int64)]
+
+
 class PipelineArgs(Structure):
     _fields_ = [
         ("images", c_void_p), ("img_dtype", c_int32), ("images_on_host", c_int32), ("n_images", c_int64),
@@ -79,6 +92,10 @@ PROTOTYPES = {
     "jcb_ctx_set_chunk_views": (c_int, [c_void_p, c_int64]),
     "jcb_ctx_set_host_chunk_views": (c_int, [c_void_p, c_int64]),
     "jcb_ctx_set_cls_only_last_block": (c_int, [c_void_p, c_int]),
+    "jcb_ctx_set_operand_type": (c_int, [c_void_p, c_int]),
+    "jcb_ctx_get_operand_type": (c_int, [c_void_p]),
+    "jcb_vit_operand_type": (c_int, [c_void_p]),
+    "jcb_text_operand_type": (c_int, [c_void_p]),
     "jcb_sync": (c_int, [c_void_p]),
     "jcb_last_error": (c_char_p, [c_void_p]),
     "jcb_ctx_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
@@ -119,11 +136,13 @@ PROTOTYPES = {
     "jcb_pipeline": (c_int, [c_void_p, c_void_p, POINTER(PipelineArgs)]),
     "jcb_pipeline_submit": (c_int, [c_void_p, c_void_p, POINTER(PipelineArgs), POINTER(c_int64)]),
     "jcb_pipeline_wait": (c_int, [c_void_p, c_int64]),
-    "jcb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32,
-                              c_void_p, c_int64]),
-    "jcb_layernorm_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
-    "jcb_attention_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
-    "jcb_im2col_bf16": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "jcb_gemm": (c_int, [c_void_p, POINTER(GemmArgs)]),
+    "jcb_fold_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                            c_void_p, c_void_p]),
+    "jcb_layernorm": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "jcb_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "jcb_im2col": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "jcb_tensor_map_cache_stats": (None, [POINTER(ctypes.c_uint64), POINTER(ctypes.c_uint64)]),
     "jcb_encode_image_dlpack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
 }
 

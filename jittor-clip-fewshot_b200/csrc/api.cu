@@ -65,6 +65,7 @@ struct jcb_ctx {
   int64_t launches = 0;
   int ln_fold = 2;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
                                      // 0 none, 1 ln_1 only (c_proj -> QKV), 2 ln_1 and ln_2
+  int operand_f16 = 1;               // 16-bit operand type towers are packed with: 1 = fp16 (default), 0 = bf16
   char err[512] = {0};
   // per-kernel-class CUDA-event profile (jcb_ctx_profile): event pairs recorded on the launch stream
   bool prof_on = false;
@@ -206,6 +207,7 @@ struct LayerDev {
 // device arena the packed weights live in.
 struct TowerBase {
   jcb_ctx* ctx = nullptr;
+  int f16 = 0;                                       // operand type the device weights were packed with (jcb_*_finalize)
   int W = 0, L = 0, heads = 0, tokens = 0;           // width, blocks, heads (W / 64), tokens per sequence
   std::string prefix;                                // state-dict prefix of the blocks
   std::map<std::string, std::vector<float>> host;   // fp32 staging by reference key name
@@ -279,12 +281,16 @@ struct TowerWs {
   __nv_bfloat16* ln_out;  // [n*T, W]
   __nv_bfloat16* qkv;     // [n*T, 3W]
   __nv_bfloat16* attn;    // [n*T, W]
-  float* stats;           // [n*T, W/256, 2] partial (sum, sum of squares) of the residual rows (LayerNorm fold)
+  // LayerNorm fold: per-row partial (sum, sum of squares) [n*T, W/256, 2] of the centred 16-bit copy of the residual
+  // stream and the per-row shift [n*T] it was centred by; two of each, because the producer GEMM of LayerNorm point
+  // i + 1 reads the statistics of point i while its other tiles already write those of point i + 1
+  float* stats[2];
+  float* shift[2];
 };
 size_t tower_ws_bytes_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n) {
   const size_t big = std::max(n * GG * KP, n * T * 4 * W) * 2;
   return align_up(big) + align_up(n * T * W * 4) + align_up(n * T * W * 2) + align_up(n * T * 3 * W * 2) +
-         align_up(n * T * W * 2) + align_up(n * T * ((W + 255) / 256) * 8);
+         align_up(n * T * W * 2) + 2 * align_up(n * T * ((W + 255) / 256) * 8) + 2 * align_up(n * T * 4);
 }
 size_t tower_ws_bytes(const jcb_vit* v, int64_t n) {
   return tower_ws_bytes_dims(v->W, v->tokens, static_cast<size_t>(v->grid) * v->grid, v->kpatch, n);
@@ -296,19 +302,34 @@ TowerWs tower_ws_carve_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n,
   w.ln_out = b.take<__nv_bfloat16>(n * T * W);
   w.qkv = b.take<__nv_bfloat16>(n * T * 3 * W);
   w.attn = b.take<__nv_bfloat16>(n * T * W);
-  w.stats = b.take<float>(n * T * ((W + 255) / 256) * 2);
+  for (int i = 0; i < 2; ++i) w.stats[i] = b.take<float>(n * T * ((W + 255) / 256) * 2);
+  for (int i = 0; i < 2; ++i) w.shift[i] = b.take<float>(n * T);
   return w;
 }
 TowerWs tower_ws_carve(const jcb_vit* v, int64_t n, Bump& b) {
   return tower_ws_carve_dims(v->W, v->tokens, static_cast<size_t>(v->grid) * v->grid, v->kpatch, n, b);
 }
 
-int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
-             const float* bias, int epi, void* out, int64_t ldo, float* stats = nullptr, int stats_slots = 0,
-             const float* colsum = nullptr, void* out2 = nullptr) {
+// LayerNorm-fold plumbing of one GEMM launch: the consumer (EPI_LNFOLD_*) reads `stats` / `colsum`; the producer
+// (EPI_RESID_LNPREP_*) writes `stats` / `shift_out` / the centred copy `out2` and reads the previous point's
+// `stats_in` / `shift_in` (row r of this GEMM = row r * in_stride there).
+struct LnArgs {
+  float* stats = nullptr;
+  int slots = 0;
+  const float* colsum = nullptr;
+  void* out2 = nullptr;
+  const float* stats_in = nullptr;
+  const float* shift_in = nullptr;
+  float* shift_out = nullptr;
+  int64_t in_stride = 1;
+};
+
+int run_gemm(jcb_ctx* ctx, int cls, int f16, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
+             const float* bias, int epi, void* out, int64_t ldo, const LnArgs& ln = LnArgs()) {
   GemmArgs g;
-  g.stats = stats; g.stats_slots = stats_slots; g.colsum = colsum; g.out2 = out2; g.ldo2 = N;   // out2 / stats are dense
-  g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K;
+  g.stats = ln.stats; g.stats_slots = ln.slots; g.colsum = ln.colsum; g.out2 = ln.out2; g.ldo2 = N;   // out2 / stats are dense
+  g.stats_in = ln.stats_in; g.shift_in = ln.shift_in; g.shift_out = ln.shift_out; g.stats_in_row_stride = ln.in_stride;
+  g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K; g.f16 = f16;
   g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo;
   // algorithmic bytes: A + B read once, C written once (read-modify-write for the residual epilogue)
   const bool lnprep = epi == EPI_RESID_LNPREP_SHORT || epi == EPI_RESID_LNPREP_LONG;
@@ -324,14 +345,15 @@ int run_gemm(jcb_ctx* ctx, int cls, const __nv_bfloat16* A, const __nv_bfloat16*
 int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal, bool cls_row0 = false) {
   jcb_ctx* ctx = t->ctx;
   cudaStream_t s = ctx->stream;
-  const int W = t->W, T = t->tokens;
+  const int W = t->W, T = t->tokens, f16 = t->f16;
   const int M = static_cast<int>(n * T);
   const double MW = static_cast<double>(M) * W;
   int rc;
   if (ctx->ln_fold && t->layers[0].in_wf != nullptr) {
-    // LayerNorm folded into the GEMMs: for a folded LayerNorm, w.ln_out holds the RAW bf16 copy of the residual
-    // stream and w.stats its per-row partial sums (written by the embed kernel for block 0, then by the residual
-    // epilogue of the producing GEMM), and no stand-alone pass reads the fp32 residual stream.
+    // LayerNorm folded into the GEMMs: for a folded LayerNorm, w.ln_out holds the CENTRED 16-bit copy of the residual
+    // stream (x - shift[row]), w.stats[cur] its per-row partial sums and w.shift[cur] the shift (written by the embed
+    // kernel for block 0, then by the residual epilogue of the producing GEMM), and no stand-alone pass reads the
+    // fp32 residual stream.
     //   ln_fold >= 1: ln_1 (c_proj of block l-1 -> QKV of block l).  c_proj's 48 k-blocks per tile hide the heavier
     //                 epilogue; measured net gain (-1.5 ms / step).
     //   ln_fold == 2: ln_2 as well (out_proj -> c_fc); the default.  out_proj is HBM-bound and pays 12 instead of 10
@@ -341,40 +363,67 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal, bool cls
     const bool fold2 = ctx->ln_fold >= 2;
     const int slots = (W + 255) / 256;
     const bool cls_only = cls_row0 && ctx->cls_only_last && fold2 && !causal && T <= 64;
+    int cur = 0;   // which of w.stats / w.shift describes the copy in w.ln_out
+    auto consumer = [&]() { LnArgs a; a.stats = w.stats[cur]; a.slots = slots; return a; };
+    auto producer = [&](int64_t in_stride) {
+      LnArgs a;
+      a.stats = w.stats[cur ^ 1]; a.slots = slots; a.out2 = w.ln_out; a.shift_out = w.shift[cur ^ 1];
+      a.stats_in = w.stats[cur]; a.shift_in = w.shift[cur]; a.in_stride = in_stride;
+      cur ^= 1;
+      return a;
+    };
     for (int l = 0; l < t->L; ++l) {
       const LayerDev& L = t->layers[l];
-      if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, w.stats, slots, L.in_S))) return rc;
+      {
+        LnArgs a = consumer();
+        a.colsum = L.in_S;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, f16, w.ln_out, L.in_wf, M, 3 * W, W, L.in_c, EPI_LNFOLD_BF16, w.qkv, 3 * W, a))) return rc;
+      }
       if (cls_only && l + 1 == t->L) {
         // Opt-in (jcb_ctx_set_cls_only_last_block, default off): the caller of the image tower reads nothing but
         // ln_post(x[:, 0, :]) @ proj (jclip/model.py:121-124), so after the last block's K and V only the class-token
         // row of every view is live.  Attention, out_proj, ln_2, c_fc and c_proj of that block run on n rows instead
         // of n * T: the same GEMM kernels with M = n, the residual stream addressed as [n, T * W] (leading dimension
-        // T * W: row v = class token of view v), the bf16 copy / row statistics / MLP hidden dense.  Per output
+        // T * W: row v = class token of view v), the 16-bit copy / row statistics / MLP hidden dense.  Per output
         // element the GEMM arithmetic is identical (same k order); the 0.53 GFLOP per view it skips (6 % of the
         // tower) were never part of the result.  Not the default: bench.py's headline numbers run the full block.
         const int Mc = static_cast<int>(n);
         LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * 64, static_cast<double>(n) * T * W * 4 + static_cast<double>(n) * W * 4,
-                 launch_attention_cls(w.qkv, n, T, t->heads, w.attn, s));
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, Mc, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens,
-                           static_cast<int64_t>(T) * W, w.stats, slots, nullptr, w.ln_out))) return rc;
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_wf, Mc, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W, w.stats, slots, L.fc_S))) return rc;
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, Mc, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens,
+                 launch_attention_cls(w.qkv, n, T, t->heads, w.attn, s, f16));
+        {
+          LnArgs a = producer(T);   // row v of this GEMM = token row v * T of the previous LayerNorm point
+          if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, f16, w.attn, L.out_w, Mc, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens,
+                             static_cast<int64_t>(T) * W, a))) return rc;
+        }
+        {
+          LnArgs a = consumer();
+          a.colsum = L.fc_S;
+          if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, f16, w.ln_out, L.fc_wf, Mc, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W, a))) return rc;
+        }
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, f16, w.big, L.proj_w, Mc, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens,
                            static_cast<int64_t>(T) * W))) return rc;
         break;
       }
       LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
-               launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms));
+               launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms, f16));
       if (fold2) {
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens, W, w.stats, slots, nullptr, w.ln_out))) return rc;
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_wf, M, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W, w.stats, slots, L.fc_S))) return rc;
+        {
+          LnArgs a = producer(1);
+          if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, f16, w.attn, L.out_w, M, W, W, L.out_b, EPI_RESID_LNPREP_SHORT, w.tokens, W, a))) return rc;
+        }
+        LnArgs a = consumer();
+        a.colsum = L.fc_S;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, f16, w.ln_out, L.fc_wf, M, 4 * W, W, L.fc_c, EPI_LNFOLD_GELU_BF16, w.big, 4 * W, a))) return rc;
       } else {
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
-        LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, f16, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+        // ln_1's centred copy in w.ln_out was consumed by the QKV GEMM above; ln_2's stand-alone output replaces it
+        LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s, f16));
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, f16, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
       }
       if (l + 1 < t->L) {
-        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_RESID_LNPREP_LONG, w.tokens, W, w.stats, slots, nullptr, w.ln_out))) return rc;
-      } else if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) {
+        LnArgs a = producer(1);
+        if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, f16, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_RESID_LNPREP_LONG, w.tokens, W, a))) return rc;
+      } else if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, f16, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) {
         return rc;
       }
     }
@@ -382,16 +431,16 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal, bool cls
   }
   for (int l = 0; l < t->L; ++l) {
     const LayerDev& L = t->layers[l];
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, f16, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
     LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
-             launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms));
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
-    LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s));
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+             launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms, f16));
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, f16, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+    LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s, f16));
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, f16, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
+    if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, f16, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
     if (l + 1 < t->L) {
       const LayerDev& Nx = t->layers[l + 1];
-      LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, Nx.ln1_g, Nx.ln1_b, w.ln_out, s));
+      LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, Nx.ln1_g, Nx.ln1_b, w.ln_out, s, f16));
     }
   }
   return JCB_OK;
@@ -408,17 +457,17 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   const double MW = static_cast<double>(M) * W;  // elements of one [tokens, width] tensor
   const double img_b = static_cast<double>(n) * 3 * v->cfg.resolution * v->cfg.resolution;
   LAUNCH_P(ctx, JCB_KC_IM2COL, 0, img_b * img_elem_bytes(dt) + img_b * 2,
-           launch_im2col(images, dt, n, v->cfg.resolution, v->cfg.patch, apply_norm, w.big, s));
+           launch_im2col(images, dt, n, v->cfg.resolution, v->cfg.patch, apply_norm, w.big, s, v->f16));
   // conv1 output as a dense [n * GG, W] fp32 matrix through the TMA-store epilogue, parked in the (not yet used)
   // QKV buffer; the embed kernel moves each row to its token slot while adding the positional embedding.  The
   // scatter epilogue (EPI_PATCH_F32: direct stores, one row per thread) ran the GEMM at 0.81-1.0 of the others' rate.
   float* patch_out = reinterpret_cast<float*>(w.qkv);
-  int rc = run_gemm(ctx, JCB_KC_GEMM_PATCH, w.big, v->conv_w, static_cast<int>(n * GG), W, KP, nullptr, EPI_F32, patch_out, W);
+  int rc = run_gemm(ctx, JCB_KC_GEMM_PATCH, v->f16, w.big, v->conv_w, static_cast<int>(n * GG), W, KP, nullptr, EPI_F32, patch_out, W);
   if (rc) return rc;
   // class token + positional embedding + ln_pre (residual stream) + layer 0's ln_1
   LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->vpt, v->cfg.vpt_tokens, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
-                              v->layers[0].ln1_b, w.ln_out, s, (ctx->ln_fold && v->layers[0].in_wf) ? w.stats : nullptr, (W + 255) / 256,
-                              patch_out));
+                              v->layers[0].ln1_b, w.ln_out, s, (ctx->ln_fold && v->layers[0].in_wf) ? w.stats[0] : nullptr, (W + 255) / 256,
+                              patch_out, w.shift[0], v->f16));
   return tower_blocks(v, n, w, 0, /*cls_row0=*/true);   // the tail reads token row 0 only
 }
 
@@ -525,6 +574,8 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
   {
     const char* env_cls = getenv("JCB_CLS_ONLY_LAST_BLOCK");
     ctx->cls_only_last = (env_cls && env_cls[0] == '1') ? 1 : 0;
+    const char* env_op = getenv("JCB_OPERANDS");   // "bf16" | "f16" (default): see jcb_ctx_set_operand_type
+    ctx->operand_f16 = (env_op && (env_op[0] == 'b' || env_op[0] == 'B')) ? 0 : 1;
     const char* env = getenv("JCB_LN_FOLD");
     ctx->ln_fold = env ? atoi(env) : 2;   // default: both LayerNorms folded (measured, same box: 75.7-76.0 vs
                                           // 77.2-78.7 ms / step for ln_1 only); see tower_blocks
@@ -609,6 +660,20 @@ int jcb_ctx_set_cls_only_last_block(jcb_ctx* ctx, int on) {
   ctx->cls_only_last = on ? 1 : 0;
   return JCB_OK;
 }
+
+int jcb_ctx_set_operand_type(jcb_ctx* ctx, int operand_type) {
+  if (!ctx) return JCB_E_INVALID;
+  if (operand_type != JCB_OPERAND_BF16 && operand_type != JCB_OPERAND_F16)
+    return fail(ctx, JCB_E_INVALID, "operand_type must be JCB_OPERAND_BF16 (0) or JCB_OPERAND_F16 (1)");
+  ctx->operand_f16 = operand_type == JCB_OPERAND_F16 ? 1 : 0;
+  return JCB_OK;
+}
+
+int jcb_ctx_get_operand_type(const jcb_ctx* ctx) { return ctx ? (ctx->operand_f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
+
+int jcb_vit_operand_type(const jcb_vit* v) { return v ? (v->f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
+
+int jcb_text_operand_type(const jcb_text* t) { return t ? (t->f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
 
 int jcb_sync(jcb_ctx* ctx) {
   if (!ctx) return JCB_E_INVALID;
@@ -749,6 +814,7 @@ struct Packer {
 
   int begin(size_t arena_bytes, size_t max_tensor_elems) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    t->f16 = ctx->operand_f16;   // the tower keeps the operand type it was packed with until the next finalize
     if (!t->arena || t->arena_bytes < arena_bytes) {
       if (t->arena) cudaFree(t->arena);
       t->arena = nullptr;
@@ -779,14 +845,14 @@ struct Packer {
     const std::vector<float>& h = t->host[key];
     *dst = b.take<__nv_bfloat16>(h.size());
     CUDA_TRY(ctx, cudaMemcpyAsync(tmp_w, h.data(), h.size() * 4, cudaMemcpyHostToDevice, s));
-    LAUNCH(ctx, launch_cast_bf16(tmp_w, *dst, static_cast<int64_t>(rows * cols), s));
+    LAUNCH(ctx, launch_cast_bf16(tmp_w, *dst, static_cast<int64_t>(rows * cols), s, t->f16));
     for (auto& ad : adapters) {
       const LoraAdapter* a = ad.second;
       CUDA_TRY(ctx, cudaMemcpyAsync(tmp_A, a->A.data(), a->A.size() * 4, cudaMemcpyHostToDevice, s));
       CUDA_TRY(ctx, cudaMemcpyAsync(tmp_B, a->B.data(), a->B.size() * 4, cudaMemcpyHostToDevice, s));
       // rows [off, off + W) of the packed weight: W' = W + s * B A
       LAUNCH(ctx, launch_merge_lora_cast(tmp_w + ad.first * cols, tmp_A, tmp_B, t->W, static_cast<int>(cols), a->r,
-                                         a->scaling, *dst + ad.first * cols, s));
+                                         a->scaling, *dst + ad.first * cols, s, t->f16));
       CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the staging buffers are reused by the next adapter
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
@@ -811,7 +877,7 @@ struct Packer {
       CUDA_TRY(ctx, cudaStreamSynchronize(s));
     }
     LAUNCH(ctx, launch_fold_ln(tmp_w, gamma_dev, beta_dev, bias_dev, static_cast<int>(rows), static_cast<int>(cols), *wf,
-                               *S, *c, s));
+                               *S, *c, s, t->f16));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return JCB_OK;
   }
@@ -1020,7 +1086,8 @@ int jcb_encode_text(jcb_text* t, const int64_t* tokens_dev, int64_t n_seq, int n
     LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2),
              launch_text_embed_ln(reinterpret_cast<const long long*>(tokens_dev) + off * T, m, T, W, t->cfg.vocab_size,
                                   t->tok_emb, t->pos, t->layers[0].ln1_g, t->layers[0].ln1_b, w.tokens, w.ln_out, eot,
-                                  ctx->stream, (ctx->ln_fold && t->layers[0].in_wf) ? w.stats : nullptr, (W + 255) / 256));
+                                  ctx->stream, (ctx->ln_fold && t->layers[0].in_wf) ? w.stats[0] : nullptr, (W + 255) / 256,
+                                  w.shift[0], t->f16));
     if ((rc = tower_blocks(t, m, w, 1))) return rc;
     LAUNCH_P(ctx, JCB_KC_TAIL, 2.0 * m * W * E, static_cast<double>(m) * (W + E) * 4,
              launch_tail(w.tokens, m, T, W, t->ln_final_g, t->ln_final_b, t->text_projection, E, normalize,
@@ -1231,8 +1298,17 @@ int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) 
   const size_t scratch_b = align_up(mta_scratch_bytes(3 * I, V, C, E));
   const bool own_feats = a->out_feats_dev == nullptr;
   const size_t head_bytes = (own_feats ? feats_b : 0) + (vit_zs ? feats_b : 0) + 3 * modes_b + topk_b + scratch_b;
-  if ((rc = ws_reserve(ctx, head_bytes + tower_ws_bytes(vit, balanced_chunk(NV, views_bound(ctx, a->images_on_host != 0)))))) return rc;
+  // ONE reservation for everything below: the persistent part and the larger of the two towers' pass workspaces.
+  // (encode_views reserves again per tower; if the second tower needed MORE than the first, ws_reserve would free
+  // the buffer the first tower's embeddings, the modes and the scratch were carved from.)
+  {
+    const int64_t chunk = balanced_chunk(NV, views_bound(ctx, a->images_on_host != 0));
+    size_t tower_b = tower_ws_bytes(vit, chunk);
+    if (vit_zs) tower_b = std::max(tower_b, tower_ws_bytes(vit_zs, chunk));
+    if ((rc = ws_reserve(ctx, head_bytes + tower_b))) return rc;
+  }
   Bump b(ctx->ws);
+  const void* ws_at_carve = ctx->ws;
   float* feats = own_feats ? b.take<float>(static_cast<size_t>(NV) * E) : a->out_feats_dev;
   float* feats_zs = vit_zs ? b.take<float>(static_cast<size_t>(NV) * E) : feats;
   float* m_pt = b.take<float>(static_cast<size_t>(I) * E);
@@ -1246,6 +1322,7 @@ int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) 
   // encode_image + L2 normalise over every view                      test.py:1705-1706 (:1711-1712)
   if ((rc = encode_views(vit, a->images, a->img_dtype, a->images_on_host != 0, NV, a->apply_clip_norm, 1, feats, head_bytes))) return rc;
   if (vit_zs && (rc = encode_views(vit_zs, a->images, a->img_dtype, a->images_on_host != 0, NV, a->apply_clip_norm, 1, feats_zs, head_bytes))) return rc;
+  if (ctx->ws != ws_at_carve) return fail(ctx, JCB_E_STATE, "internal: the workspace moved while the pipeline held pointers into it");
   // solve_mta x3 in one launch                                        test.py:1708-1709, :1713
   MtaSet sets[3] = {{feats, a->text_pt_t_dev, m_pt, nullptr},
                     {feats, a->text_hand_t_dev, m_hand, nullptr},
@@ -1311,44 +1388,64 @@ int jcb_pipeline_wait(jcb_ctx* ctx, int64_t ticket) {
 }
 
 // ------------------------------------------------------------------------------------------------
-int jcb_gemm_bf16(jcb_ctx* ctx, const void* A, const void* B, int32_t M, int32_t N, int32_t K, const float* bias,
-                  int32_t epilogue, void* out, int64_t ldo) {
+int jcb_gemm(jcb_ctx* ctx, const jcb_gemm_args* g) {
   if (!ctx) return JCB_E_INVALID;
-  if (!A || !B || !out) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: null pointer");
-  if (epilogue == 3) return fail(ctx, JCB_E_INVALID, "jcb_gemm_bf16: epilogue 3 (conv1 scatter) no longer exists");
-  DeviceGuard g(ctx->device);
-  return run_gemm(ctx, JCB_KC_OTHER, static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(B), M, N, K, bias,
-                  epilogue, out, ldo);
+  if (!g || !g->A_dev || !g->B_dev || !g->out_dev) return fail(ctx, JCB_E_INVALID, "jcb_gemm: null pointer");
+  if (g->epilogue == 3) return fail(ctx, JCB_E_INVALID, "jcb_gemm: epilogue 3 (conv1 scatter) no longer exists");
+  if (g->operand_type != JCB_OPERAND_BF16 && g->operand_type != JCB_OPERAND_F16) return fail(ctx, JCB_E_INVALID, "jcb_gemm: bad operand_type");
+  DeviceGuard guard(ctx->device);
+  LnArgs ln;
+  ln.stats = g->stats_dev; ln.slots = g->stats_slots; ln.colsum = g->colsum_dev; ln.out2 = g->out2_dev;
+  ln.stats_in = g->stats_in_dev; ln.shift_in = g->shift_in_dev; ln.shift_out = g->shift_out_dev;
+  ln.in_stride = g->stats_in_row_stride > 0 ? g->stats_in_row_stride : 1;
+  return run_gemm(ctx, JCB_KC_OTHER, g->operand_type == JCB_OPERAND_F16, static_cast<const __nv_bfloat16*>(g->A_dev),
+                  static_cast<const __nv_bfloat16*>(g->B_dev), g->M, g->N, g->K, g->bias_dev, g->epilogue, g->out_dev, g->ldo, ln);
 }
 
-int jcb_layernorm_bf16(jcb_ctx* ctx, const float* x, int64_t rows, int32_t width, const float* gamma, const float* beta,
-                       void* out) {
+int jcb_fold_ln(jcb_ctx* ctx, const float* W_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev,
+                int32_t N, int32_t K, int32_t operand_type, void* Wf_dev, float* S_dev, float* c_dev) {
   if (!ctx) return JCB_E_INVALID;
-  if (!x || !gamma || !beta || !out) return fail(ctx, JCB_E_INVALID, "jcb_layernorm_bf16: null pointer");
+  if (!W_dev || !gamma_dev || !beta_dev || !bias_dev || !Wf_dev || !S_dev || !c_dev || N < 1 || K < 1)
+    return fail(ctx, JCB_E_INVALID, "jcb_fold_ln: bad arguments");
   DeviceGuard g(ctx->device);
-  LAUNCH(ctx, launch_layernorm(x, rows, width, gamma, beta, static_cast<__nv_bfloat16*>(out), ctx->stream));
+  LAUNCH(ctx, launch_fold_ln(W_dev, gamma_dev, beta_dev, bias_dev, N, K, static_cast<__nv_bfloat16*>(Wf_dev), S_dev, c_dev,
+                             ctx->stream, operand_type == JCB_OPERAND_F16));
   return JCB_OK;
 }
 
-int jcb_im2col_bf16(jcb_ctx* ctx, const void* images, int32_t img_dtype, int64_t n_views, int32_t resolution,
-                    int32_t patch, int32_t apply_clip_norm, void* patches) {
+int jcb_layernorm(jcb_ctx* ctx, const float* x, int64_t rows, int32_t width, const float* gamma, const float* beta,
+                  int32_t operand_type, void* out) {
   if (!ctx) return JCB_E_INVALID;
-  if (!images || !patches) return fail(ctx, JCB_E_INVALID, "jcb_im2col_bf16: null pointer");
-  if (img_dtype < 0 || img_dtype > 2 || n_views < 0) return fail(ctx, JCB_E_INVALID, "jcb_im2col_bf16: bad dtype / count");
+  if (!x || !gamma || !beta || !out) return fail(ctx, JCB_E_INVALID, "jcb_layernorm: null pointer");
+  DeviceGuard g(ctx->device);
+  LAUNCH(ctx, launch_layernorm(x, rows, width, gamma, beta, static_cast<__nv_bfloat16*>(out), ctx->stream,
+                               operand_type == JCB_OPERAND_F16));
+  return JCB_OK;
+}
+
+int jcb_im2col(jcb_ctx* ctx, const void* images, int32_t img_dtype, int64_t n_views, int32_t resolution,
+               int32_t patch, int32_t apply_clip_norm, int32_t operand_type, void* patches) {
+  if (!ctx) return JCB_E_INVALID;
+  if (!images || !patches) return fail(ctx, JCB_E_INVALID, "jcb_im2col: null pointer");
+  if (img_dtype < 0 || img_dtype > 2 || n_views < 0) return fail(ctx, JCB_E_INVALID, "jcb_im2col: bad dtype / count");
   DeviceGuard g(ctx->device);
   LAUNCH(ctx, launch_im2col(images, img_dtype, n_views, resolution, patch, apply_clip_norm,
-                            static_cast<__nv_bfloat16*>(patches), ctx->stream));
+                            static_cast<__nv_bfloat16*>(patches), ctx->stream, operand_type == JCB_OPERAND_F16));
   return JCB_OK;
 }
 
-int jcb_attention_bf16(jcb_ctx* ctx, const void* qkv, int64_t n_views, int32_t tokens, int32_t heads, void* out) {
+int jcb_attention(jcb_ctx* ctx, const void* qkv, int64_t n_views, int32_t tokens, int32_t heads, int32_t causal,
+                  int32_t operand_type, void* out) {
   if (!ctx) return JCB_E_INVALID;
-  if (!qkv || !out) return fail(ctx, JCB_E_INVALID, "jcb_attention_bf16: null pointer");
+  if (!qkv || !out) return fail(ctx, JCB_E_INVALID, "jcb_attention: null pointer");
   DeviceGuard g(ctx->device);
   LAUNCH(ctx, launch_attention(static_cast<const __nv_bfloat16*>(qkv), n_views, tokens, heads,
-                               static_cast<__nv_bfloat16*>(out), ctx->stream, 0, ctx->dev_status, ctx->num_sms));
+                               static_cast<__nv_bfloat16*>(out), ctx->stream, causal, ctx->dev_status, ctx->num_sms,
+                               operand_type == JCB_OPERAND_F16));
   return JCB_OK;
 }
+
+void jcb_tensor_map_cache_stats(uint64_t* hits, uint64_t* misses) { tmap_cache_stats(hits, misses); }
 
 // ------------------------------------------------------------------------------------------------
 // Minimal DLPack (dlpack.h v0.8) structures: enough to borrow a tensor.

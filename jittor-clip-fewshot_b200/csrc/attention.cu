@@ -24,7 +24,7 @@ namespace {
 constexpr int HD = 64;       // head dim
 constexpr int LDS = HD + 8;  // smem row stride (bf16): 144 B, conflict-free for ldmatrix
 
-template <int HEADS_PER_CTA, int MT, int TP, bool CAUSAL>
+template <int HEADS_PER_CTA, int MT, int TP, bool CAUSAL, bool F16>
 __global__ void __launch_bounds__(HEADS_PER_CTA * (TP / 16 / MT) * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_bfloat16* __restrict__ out) {
   constexpr int WPH = TP / 16 / MT;  // warps per head
@@ -89,8 +89,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       ldmatrix_x4(b, sK + (krow * LDS + col) * 2);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        mma_bf16_16816(s[mt][2 * np], a[mt], b[0], b[1]);
-        mma_bf16_16816(s[mt][2 * np + 1], a[mt], b[2], b[3]);
+        if (F16) {
+          mma_f16_16816(s[mt][2 * np], a[mt], b[0], b[1]);
+          mma_f16_16816(s[mt][2 * np + 1], a[mt], b[2], b[3]);
+        } else {
+          mma_bf16_16816(s[mt][2 * np], a[mt], b[0], b[1]);
+          mma_bf16_16816(s[mt][2 * np + 1], a[mt], b[2], b[3]);
+        }
       }
     }
   }
@@ -128,8 +133,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       const float p3 = exp2f((s[mt][nt][3] - mx[1]) * scale_log2);
       sum[0] += p0 + p1;
       sum[1] += p2 + p3;
-      pfrag[mt][nt][0] = pack_bf16x2(p0, p1);
-      pfrag[mt][nt][1] = pack_bf16x2(p2, p3);
+      pfrag[mt][nt][0] = pack_h2<F16>(p0, p1);
+      pfrag[mt][nt][1] = pack_h2<F16>(p2, p3);
     }
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -165,8 +170,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
       ldmatrix_x4_trans(b, sV + (krow * LDS + col) * 2);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        mma_bf16_16816(o[mt][2 * dp], a[mt], b[0], b[1]);
-        mma_bf16_16816(o[mt][2 * dp + 1], a[mt], b[2], b[3]);
+        if (F16) {
+          mma_f16_16816(o[mt][2 * dp], a[mt], b[0], b[1]);
+          mma_f16_16816(o[mt][2 * dp + 1], a[mt], b[2], b[3]);
+        } else {
+          mma_bf16_16816(o[mt][2 * dp], a[mt], b[0], b[1]);
+          mma_bf16_16816(o[mt][2 * dp + 1], a[mt], b[2], b[3]);
+        }
       }
     }
   }
@@ -181,9 +191,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
     for (int dt = 0; dt < 8; ++dt) {
       const int col = dt * 8 + 2 * (lane & 3);
       *reinterpret_cast<uint32_t*>(stage + row * LDS + col) =
-          pack_bf16x2(o[mt][dt][0] * inv_sum[mt][0], o[mt][dt][1] * inv_sum[mt][0]);
+          pack_h2<F16>(o[mt][dt][0] * inv_sum[mt][0], o[mt][dt][1] * inv_sum[mt][0]);
       *reinterpret_cast<uint32_t*>(stage + (row + 8) * LDS + col) =
-          pack_bf16x2(o[mt][dt][2] * inv_sum[mt][1], o[mt][dt][3] * inv_sum[mt][1]);
+          pack_h2<F16>(o[mt][dt][2] * inv_sum[mt][1], o[mt][dt][3] * inv_sum[mt][1]);
     }
   }
   __syncthreads();
@@ -201,6 +211,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, int T, int heads, __nv_b
 // (jclip/model.py:121-124), so in the LAST block nothing but the class-token row of the attention output reaches
 // the result.  One warp per (sequence, head): lane j scores keys j and j + 32 (a K row is 128 contiguous bytes),
 // P is rounded to bf16 before P V exactly as in the full kernels, lanes own two output columns each.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 attention_cls_kernel(const __nv_bfloat16* __restrict__ qkv, long long n_items, int T, int heads,
                      __nv_bfloat16* __restrict__ out) {
@@ -217,9 +228,9 @@ attention_cls_kernel(const __nv_bfloat16* __restrict__ qkv, long long n_items, i
 #pragma unroll
     for (int c = 0; c < HD / 8; ++c) {
       const uint4 v = __ldg(qp + c);
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const uint32_t* hh = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 t = __bfloat1622float2(hh[e]); q[8 * c + 2 * e] = t.x; q[8 * c + 2 * e + 1] = t.y; }
+      for (int e = 0; e < 4; ++e) { const float2 t = unpack_h2<F16>(hh[e]); q[8 * c + 2 * e] = t.x; q[8 * c + 2 * e + 1] = t.y; }
     }
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;
@@ -233,10 +244,10 @@ attention_cls_kernel(const __nv_bfloat16* __restrict__ qkv, long long n_items, i
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {
         const uint4 v = __ldg(kp + c);
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const uint32_t* hh = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 t = __bfloat1622float2(hh[e]);
+          const float2 t = unpack_h2<F16>(hh[e]);
           acc = fmaf(q[8 * c + 2 * e], t.x, acc);
           acc = fmaf(q[8 * c + 2 * e + 1], t.y, acc);
         }
@@ -249,71 +260,72 @@ attention_cls_kernel(const __nv_bfloat16* __restrict__ qkv, long long n_items, i
   pr[0] = exp2f(sc[0] - mx);
   pr[1] = exp2f(sc[1] - mx);
   const float inv = 1.0f / warp_sum(pr[0] + pr[1]);
-  pr[0] = __bfloat162float(__float2bfloat16_rn(pr[0]));   // P enters P V as bf16 (as in the tensor-core kernels)
-  pr[1] = __bfloat162float(__float2bfloat16_rn(pr[1]));
+  pr[0] = from_h<F16>(to_h<F16>(pr[0]));   // P enters P V as a 16-bit operand (as in the tensor-core kernels)
+  pr[1] = from_h<F16>(to_h<F16>(pr[1]));
   float o0 = 0.f, o1 = 0.f;
   const __nv_bfloat16* vbase = base + 2 * W + 2 * lane;
   for (int j = 0; j < T; ++j) {
     const float pj = __shfl_sync(0xffffffffu, pr[j >> 5], j & 31);
-    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vbase + static_cast<long long>(j) * (3 * W)));
+    const float2 v = unpack_h2<F16>(*reinterpret_cast<const uint32_t*>(vbase + static_cast<long long>(j) * (3 * W)));
     o0 = fmaf(pj, v.x, o0);
     o1 = fmaf(pj, v.y, o1);
   }
-  *reinterpret_cast<uint32_t*>(out + seq * W + h * HD + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+  *reinterpret_cast<uint32_t*>(out + seq * W + h * HD + 2 * lane) = pack_h2<F16>(o0 * inv, o1 * inv);
 }
 
-template <int HPC, int MT, int TP, bool CAUSAL>
+template <int TP, bool CAUSAL, bool F16>
 cudaError_t launch_attention_cfg(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
                                  cudaStream_t stream) {
-  constexpr int SMEM = HPC * 3 * TP * LDS * 2;
-  constexpr int THREADS = HPC * (TP / 16 / MT) * 32;
+  // one head per CTA, one 16-row query tile per warp: the fastest of the configurations tried in round 1 (4.4 TB/s;
+  // 4 heads per CTA and 2 tiles per warp: 2.5 TB/s)
+  constexpr int SMEM = 3 * TP * LDS * 2;
+  constexpr int THREADS = (TP / 16) * 32;
   {
-    cudaError_t e = ensure_dynamic_smem(attention_kernel<HPC, MT, TP, CAUSAL>, SMEM);
+    cudaError_t e = ensure_dynamic_smem(attention_kernel<1, 1, TP, CAUSAL, F16>, SMEM);
     if (e != cudaSuccess) return e;
   }
-  const long long grid = n_views * (heads / HPC);
-  attention_kernel<HPC, MT, TP, CAUSAL><<<static_cast<unsigned>(grid), THREADS, SMEM, stream>>>(qkv, T, heads, out);
+  const long long grid = n_views * heads;
+  attention_kernel<1, 1, TP, CAUSAL, F16><<<static_cast<unsigned>(grid), THREADS, SMEM, stream>>>(qkv, T, heads, out);
   return cudaGetLastError();
+}
+
+template <bool F16>
+cudaError_t launch_attention_mma(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
+                                 cudaStream_t stream, int causal) {
+  if (causal) return launch_attention_cfg<80, true, F16>(qkv, n_views, T, heads, out, stream);
+  if (T > 64) return launch_attention_cfg<80, false, F16>(qkv, n_views, T, heads, out, stream);
+  return launch_attention_cfg<64, false, F16>(qkv, n_views, T, heads, out, stream);
 }
 
 }  // namespace
 
 cudaError_t launch_attention_cls(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, int f16) {
   if (T < 1 || T > 64 || heads < 1) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
   const long long items = n_views * heads;
-  attention_cls_kernel<<<static_cast<unsigned>((items + 7) / 8), 256, 0, stream>>>(qkv, items, T, heads, out);
+  const unsigned grid = static_cast<unsigned>((items + 7) / 8);
+  if (f16) attention_cls_kernel<true><<<grid, 256, 0, stream>>>(qkv, items, T, heads, out);
+  else attention_cls_kernel<false><<<grid, 256, 0, stream>>>(qkv, items, T, heads, out);
   return cudaGetLastError();
 }
 
+// Default: the tcgen05 / TMEM kernel (attention_tc.cu) for every shape it supports (T <= 128: both towers).  The
+// mma.sync kernel above remains as the A/B baseline (JCB_ATT_IMPL=mma; T <= 80) it was in round 1.
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream, int causal, int* dev_status, int num_sms) {
-  if (T < 1 || T > 80 || heads < 1) return cudaErrorInvalidValue;
+                             cudaStream_t stream, int causal, int* dev_status, int num_sms, int f16) {
+  if (T < 1 || T > 128 || heads < 1) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
-  static int impl = -1;  // 1: tcgen05 kernel where the shape allows it (default), 0: mma.sync kernel everywhere
+  static int impl = -1;  // 1: tcgen05 kernel (default), 0: mma.sync kernel
   if (impl < 0) {
     const char* env = getenv("JCB_ATT_IMPL");
     impl = (env && env[0] == 'm') ? 0 : 1;
   }
   if (impl == 1 && dev_status != nullptr && num_sms > 0 && attention_tc_supported(T, heads, causal))
-    return launch_attention_tc(qkv, n_views, T, heads, out, stream, dev_status, num_sms);
-  if (causal) return launch_attention_cfg<1, 1, 80, true>(qkv, n_views, T, heads, out, stream);  // text tower
-  if (T > 64) return launch_attention_cfg<1, 1, 80, false>(qkv, n_views, T, heads, out, stream);
-  static int cfg = 0;  // heads per CTA * 10 + query tiles per warp
-  if (cfg == 0) {
-    const char* env = getenv("JCB_ATT_CFG");
-    cfg = env ? atoi(env) : 11;
-  }
-  const int use = (heads % 4 != 0 && cfg > 20) ? 11 : cfg;
-  switch (use) {
-    case 12: return launch_attention_cfg<1, 2, 64, false>(qkv, n_views, T, heads, out, stream);
-    case 21: return launch_attention_cfg<2, 1, 64, false>(qkv, n_views, T, heads, out, stream);
-    case 22: return launch_attention_cfg<2, 2, 64, false>(qkv, n_views, T, heads, out, stream);
-    case 41: return launch_attention_cfg<4, 1, 64, false>(qkv, n_views, T, heads, out, stream);
-    case 42: return launch_attention_cfg<4, 2, 64, false>(qkv, n_views, T, heads, out, stream);
-    default: return launch_attention_cfg<1, 1, 64, false>(qkv, n_views, T, heads, out, stream);
-  }
+    return launch_attention_tc(qkv, n_views, T, heads, out, stream, dev_status, num_sms, f16, causal);
+  if (T > 80) return cudaErrorInvalidValue;
+  return f16 ? launch_attention_mma<true>(qkv, n_views, T, heads, out, stream, causal)
+             : launch_attention_mma<false>(qkv, n_views, T, heads, out, stream, causal);
 }
 
 }  // namespace jcb

@@ -1,7 +1,8 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:   C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)
+// Persistent, warp-specialised 16-bit-operand (bf16 | fp16) GEMM for sm_100a:   C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue)
 //
 //   warp 0      TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a STAGES-deep smem ring
-//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (bf16 -> fp32) accumulating in TMEM;
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (kind::f16: bf16 or fp16 operands -> fp32)
+//                                accumulating in TMEM;
 //                                tcgen05.commit releases smem slots / publishes accumulator stages
 //   warps 2..5  epilogue       : tcgen05.ld TMEM -> registers, bias / QuickGELU / residual / pos-embed,
 //                                vectorised global stores; TMEM accumulators are double buffered so the
@@ -23,6 +24,8 @@
 // positional-embedding add (jclip/model.py:114) are fused into the epilogues.
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <cudaTypedefs.h>
 
@@ -104,6 +107,14 @@ struct GemmDev {
   float* stats;          // LNFOLD: in / LNPREP: out, [M, stats_slots, 2]
   int stats_slots;
   const float* colsum;   // LNFOLD
+  // LNPREP: the bf16 / fp16 copy of the updated residual row is written CENTRED, x - shift[row], where shift is the
+  // row's mean as of the previous LayerNorm point (previous shift + previous mean of the centred copy): the 16-bit
+  // rounding then acts on |x - mean| instead of |x|, and the one-pass variance E[x'^2] - E[x']^2 has nothing to cancel.
+  const float* stats_in;     // [M_in, stats_slots, 2] partial sums of the previous centred copy (nullptr: shift 0)
+  const float* shift_in;     // [M_in] previous shift
+  float* shift_out;          // [M] new shift (written by the n_blk == 0 tiles)
+  long long stats_in_stride; // row r of this GEMM = row r * stride of stats_in / shift_in (class-token-only last block)
+  uint32_t idesc;            // tcgen05 instruction descriptor (operand formats, M, N)
   int arrive_release;    // A/B: 1 = the old `.release.cluster` accumulator hand-back
   long long* trace;      // debug (JCB_GEMM_TRACE=file): clock64 stamps of CTA 0's roles, [TRACE_TILES][8]
 };
@@ -113,7 +124,7 @@ constexpr int TRACE_TILES = 96;
     if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_TILES) p.trace[it * 8 + (slot)] = clock64(); \
   } while (0)
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, bool F16>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                                           const CUtensorMap& tmOut2, const GemmDev& p) {
   using Cfg = TileCfg<BN, CTAS, EPI>;
@@ -221,7 +232,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   } else if (warp_idx == 1) {
     // ===================================================================== MMA issuer (leader CTA only)
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, BN);
+      const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -284,7 +295,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       }
       __syncwarp();
       const int row0e = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;   // this warp's 32 rows
+      float shift = 0.f;   // LNPREP: what this thread's row is centred by (see GemmDev)
       if (is_lnprep(EPI)) {
+        if (p.shift_in != nullptr && row0e + lane < p.M) {
+          const long long r = static_cast<long long>(row0e + lane) * p.stats_in_stride;
+          const float2* st = reinterpret_cast<const float2*>(p.stats_in) + r * p.stats_slots;
+          float su = 0.f;
+          for (int i = 0; i < p.stats_slots; ++i) su += __ldg(st + i).x;
+          shift = __ldg(p.shift_in + r) + su / static_cast<float>(p.N);
+        }
         // the old residual of the first D chunks is requested BEFORE waiting for the accumulator: its latency hides
         // behind the main loop.  Every earlier store of this warp must have released the staging buffers.
         if (lane == 0) {
@@ -372,10 +391,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
               f[4 * h + 0] = o.x; f[4 * h + 1] = o.y; f[4 * h + 2] = o.z; f[4 * h + 3] = o.w;
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { rs += f[e]; rq = fmaf(f[e], f[e], rq); }
+            for (int e = 0; e < 8; ++e) { f[e] -= shift; rs += f[e]; rq = fmaf(f[e], f[e], rq); }
             uint4 hb;
-            hb.x = pack_bf16x2(f[0], f[1]); hb.y = pack_bf16x2(f[2], f[3]);
-            hb.z = pack_bf16x2(f[4], f[5]); hb.w = pack_bf16x2(f[6], f[7]);
+            hb.x = pack_h2<F16>(f[0], f[1]); hb.y = pack_h2<F16>(f[2], f[3]);
+            hb.z = pack_h2<F16>(f[4], f[5]); hb.w = pack_h2<F16>(f[6], f[7]);
             const int hp = (c & 1) * 4 + jj;   // piece of the 128-byte bf16 row (64 columns = two fp32 chunks)
             *reinterpret_cast<uint4*>(halfp + ((hp ^ (lane & 7)) << 4)) = hb;
           }
@@ -388,9 +407,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           }
         }
         ok = __all_sync(0xffffffffu, ok);
-        if (row0 + lane < p.M)
+        if (row0 + lane < p.M) {
           *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(row0 + lane) * p.stats_slots + n_blk) * 2) =
               make_float2(rs, rq);
+          if (n_blk == 0 && p.shift_out != nullptr) p.shift_out[row0 + lane] = shift;
+        }
       } else {
         // TMEM -> registers -> (+bias, activation, rounding) -> 128B-swizzled smem chunk of 32 rows x 128 B ->
         // one TMA store (or fp32 reduce-add for the residual epilogues) per chunk: fully coalesced, asynchronous,
@@ -485,8 +506,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                 }
                 f2_unpack(x2, f[2 * e], f[2 * e + 1]);
               }
-              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+              o.x = pack_h2<F16>(f[0], f[1]); o.y = pack_h2<F16>(f[2], f[3]);
+              o.z = pack_h2<F16>(f[4], f[5]); o.w = pack_h2<F16>(f[6], f[7]);
             } else {
               float f0, f1, f2, f3;
               f2_unpack(f2_add(f2_pack(__uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1])), bb2[2 * j]), f0, f1);
@@ -526,57 +547,97 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   }
 }
 
-template <int BN, int EPI>
+// F16 selects the element type of 16-bit OUTPUTS (the conversion instruction of the epilogue); the operand formats
+// the tensor core assumes travel in p.idesc, so the fp32-output epilogues need no second instantiation.
+template <int BN, int EPI, bool F16>
 __global__ void __launch_bounds__(64 + 32 * epi_warps_of(EPI), 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                         const GemmDev p) {
-  gemm_body<BN, EPI, 1>(tmA, tmB, tmOut, tmOut2, p);
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                    const GemmDev p) {
+  gemm_body<BN, EPI, 1, F16>(tmA, tmB, tmOut, tmOut2, p);
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * epi_warps_of(EPI), 1)
-gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-                              const GemmDev p) {
-  gemm_body<BN, EPI, 2>(tmA, tmB, tmOut, tmOut2, p);
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                         const GemmDev p) {
+  gemm_body<BN, EPI, 2, F16>(tmA, tmB, tmOut, tmOut2, p);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
 char g_driver_err[256] = {0};
 int g_ctas = 0;  // 0 = not decided yet
 
+// Encoded tensor maps are pure functions of (base, shape, strides, box, type): the towers launch the same few
+// hundred (pointer, shape) combinations every pass, so they are encoded once and looked up afterwards
+// (cuTensorMapEncodeTiled costs ~1 us of host time each; 4 per GEMM launch matters for the reference's own call
+// pattern of 1 image x 65 views per call, test.py:1692-1705).
+struct TmapKey {
+  const void* base; uint64_t rows, cols, ld; uint32_t box_rows, box_cols; int dtype;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && dtype == o.dtype;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 1315423911ull + k.ld * 2654435761ull + (h << 6) + (h >> 2));
+    h ^= (static_cast<uint64_t>(k.box_rows) << 40) ^ (static_cast<uint64_t>(k.box_cols) << 20) ^ static_cast<uint64_t>(k.dtype);
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+uint64_t g_tmap_hits = 0, g_tmap_misses = 0;
+
 // 2-D row-major tensor [rows, cols] with leading dimension ld_elems, 128B-swizzled boxes of box_rows x box_cols
-bool make_tmap_2d(CUtensorMap* tm, bool bf16, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+bool make_tmap_2d(CUtensorMap* tm, int dtype, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                   uint32_t box_rows, uint32_t box_cols) {
-  const uint64_t esz = bf16 ? 2 : 4;
+  const TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols, dtype};
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *tm = it->second; ++g_tmap_hits; return true; }
+  }
+  const uint64_t esz = dtype == TM_F32 ? 4 : 2;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld_elems * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                              const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUtensorMapDataType dt = dtype == TM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == TM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = g_encode_tiled(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();   // workspaces were re-allocated many times: start over
+  g_tmap_cache.emplace(key, *tm);
+  ++g_tmap_misses;
+  return true;
 }
 
-template <int BN, int EPI, int CTAS>
+template <int BN, int EPI, int CTAS, bool F16>
 cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStream_t stream) {
   using Cfg = TileCfg<BN, CTAS, EPI>;
+  const int op_dt = a.f16 ? TM_F16 : TM_BF16;
   CUtensorMap tmA, tmB, tmOut;
-  if (!make_tmap_2d(&tmA, true, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K)) return cudaErrorInvalidValue;
-  if (!make_tmap_2d(&tmB, true, a.B, a.N, a.K, a.ldb, Cfg::B_ROWS, BLOCK_K)) return cudaErrorInvalidValue;
+  if (!make_tmap_2d(&tmA, op_dt, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K)) return cudaErrorInvalidValue;
+  if (!make_tmap_2d(&tmB, op_dt, a.B, a.N, a.K, a.ldb, Cfg::B_ROWS, BLOCK_K)) return cudaErrorInvalidValue;
   constexpr bool OUT_BF16 = out_is_bf16(EPI);
   CUtensorMap tmOut2;
-  if (!make_tmap_2d(&tmOut, OUT_BF16, a.out, a.M, a.N, a.ldo, 32, OUT_BF16 ? 64 : 32)) return cudaErrorInvalidValue;
+  if (!make_tmap_2d(&tmOut, OUT_BF16 ? op_dt : TM_F32, a.out, a.M, a.N, a.ldo, 32, OUT_BF16 ? 64 : 32)) return cudaErrorInvalidValue;
   tmOut2 = tmOut;
   if (is_lnprep(EPI)) {
     if (!a.out2 || !a.stats || a.stats_slots < a.N / BN) return cudaErrorInvalidValue;
-    if (!make_tmap_2d(&tmOut2, true, a.out2, a.M, a.N, a.ldo2, 32, 64)) return cudaErrorInvalidValue;
+    if ((a.shift_in != nullptr) != (a.stats_in != nullptr) || a.stats_in == a.stats) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmOut2, op_dt, a.out2, a.M, a.N, a.ldo2, 32, 64)) return cudaErrorInvalidValue;
   }
   if (is_lnfold(EPI) && (!a.stats || !a.colsum || a.stats_slots < 1)) return cudaErrorInvalidValue;
-  auto kern = CTAS == 2 ? gemm_bf16_tcgen05_2cta_kernel<BN, EPI> : gemm_bf16_tcgen05_kernel<BN, EPI>;
+  auto kern = CTAS == 2 ? gemm_tcgen05_2cta_kernel<BN, EPI, F16> : gemm_tcgen05_kernel<BN, EPI, F16>;
   {
     cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -585,6 +646,9 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.status = dev_status;
   p.stats = a.stats; p.stats_slots = a.stats_slots; p.colsum = a.colsum;
+  p.stats_in = a.stats_in; p.shift_in = a.shift_in; p.shift_out = a.shift_out;
+  p.stats_in_stride = a.stats_in_row_stride > 0 ? a.stats_in_row_stride : 1;
+  p.idesc = umma_idesc_f32acc(a.f16 != 0, BLOCK_M * CTAS, BN);
   static int arrive_release = -1;
   if (arrive_release < 0) {
     const char* env = getenv("JCB_GEMM_ARRIVE_RELEASE");
@@ -626,22 +690,31 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
 
 template <int BN, int CTAS>
 cudaError_t launch_bn(const GemmArgs& a, int* st, int sms, cudaStream_t s) {
+#define JCB_CASE16(E) \
+  case E: return a.f16 ? launch_cfg<BN, E, CTAS, true>(a, st, sms, s) : launch_cfg<BN, E, CTAS, false>(a, st, sms, s)
   switch (a.epilogue) {
-    case EPI_BIAS_BF16: return launch_cfg<BN, EPI_BIAS_BF16, CTAS>(a, st, sms, s);
-    case EPI_BIAS_GELU_BF16: return launch_cfg<BN, EPI_BIAS_GELU_BF16, CTAS>(a, st, sms, s);
-    case EPI_BIAS_RESID_F32: return launch_cfg<BN, EPI_BIAS_RESID_F32, CTAS>(a, st, sms, s);
-    case EPI_F32: return launch_cfg<BN, EPI_F32, CTAS>(a, st, sms, s);
-    case EPI_LNFOLD_BF16: return launch_cfg<BN, EPI_LNFOLD_BF16, CTAS>(a, st, sms, s);
-    case EPI_LNFOLD_GELU_BF16: return launch_cfg<BN, EPI_LNFOLD_GELU_BF16, CTAS>(a, st, sms, s);
-    case EPI_RESID_LNPREP_SHORT: return launch_cfg<BN, EPI_RESID_LNPREP_SHORT, CTAS>(a, st, sms, s);
-    case EPI_RESID_LNPREP_LONG: return launch_cfg<BN, EPI_RESID_LNPREP_LONG, CTAS>(a, st, sms, s);
+    JCB_CASE16(EPI_BIAS_BF16);
+    JCB_CASE16(EPI_BIAS_GELU_BF16);
+    JCB_CASE16(EPI_LNFOLD_BF16);
+    JCB_CASE16(EPI_LNFOLD_GELU_BF16);
+    JCB_CASE16(EPI_RESID_LNPREP_SHORT);
+    JCB_CASE16(EPI_RESID_LNPREP_LONG);
+    case EPI_BIAS_RESID_F32: return launch_cfg<BN, EPI_BIAS_RESID_F32, CTAS, false>(a, st, sms, s);
+    case EPI_F32: return launch_cfg<BN, EPI_F32, CTAS, false>(a, st, sms, s);
     default: return cudaErrorInvalidValue;
   }
+#undef JCB_CASE16
 }
 
 }  // namespace
 
 void* gemm_encode_tiled_fn() { return reinterpret_cast<void*>(g_encode_tiled); }
+
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  if (hits) *hits = g_tmap_hits;
+  if (misses) *misses = g_tmap_misses;
+}
 
 const char* gemm_init_driver_api() {
   if (g_encode_tiled) return nullptr;

@@ -8,6 +8,11 @@
 
 namespace jcb {
 
+// 16-bit operand storage.  Every 16-bit tensor of a tower (weights, raw residual copy, q|k|v, attention output, MLP
+// hidden) holds bf16 OR fp16 bits, fixed per tower when it is packed (jcb_ctx_set_operand_type); the pointers are
+// typed __nv_bfloat16* for historical reasons and the launchers take `f16` (0 = bf16, 1 = fp16) next to them.
+enum TmapDtype : int { TM_F32 = 0, TM_BF16 = 1, TM_F16 = 2 };
+
 // ---- GEMM epilogues (fused into the tcgen05 kernel) -------------------------------------------
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,       // out_bf16[m,n]  = acc + bias[n]                       (QKV projection)
@@ -38,8 +43,15 @@ struct GemmArgs {
   float* stats = nullptr;            // LNFOLD: in, LNPREP: out.  [M, stats_slots, 2] fp32 partial (sum, sum of squares)
   int stats_slots = 0;               // partial slots per row (= N / 256 of the producer; the consumer adds them up)
   const float* colsum = nullptr;     // LNFOLD: S[N]
-  void* out2 = nullptr;              // LNPREP: bf16 copy of the updated residual [M, N]
+  void* out2 = nullptr;              // LNPREP: 16-bit copy of the updated residual [M, N], centred by `shift`
   int64_t ldo2 = 0;
+  int f16 = 0;                       // element type of A, B and of 16-bit outputs: 0 = bf16, 1 = fp16
+  // LNPREP: out2 = x - shift[row] and stats = partial sums of the centred copy, shift[row] = the row's mean at the
+  // previous LayerNorm point = shift_in[row] + sum(stats_in[row, :].sum) / N.  nullptr: shift 0.
+  const float* stats_in = nullptr;   // [M * stats_in_row_stride, stats_slots, 2], must not alias `stats`
+  const float* shift_in = nullptr;   // [M * stats_in_row_stride]
+  float* shift_out = nullptr;        // [M]
+  int64_t stats_in_row_stride = 1;
 };
 
 // Persistent TMA + tcgen05 GEMM.  Requires N % 128 == 0 and K % 64 == 0 (every GEMM of the ViT-B/32
@@ -53,19 +65,21 @@ const char* gemm_init_driver_api();
 // apply_norm: fuse tfm_clip (x - mean_c) / std_c ; u8 input is scaled by 1/255 first.
 enum ImageDtype : int { IMG_F32 = 0, IMG_BF16 = 1, IMG_U8 = 2 };
 cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
-                          int apply_norm, __nv_bfloat16* patches, cudaStream_t stream);
+                          int apply_norm, __nv_bfloat16* patches, cudaStream_t stream, int f16 = 0);
 // tokens [B*T, W] fp32: row t==0 of each view := cls + pos[0]; rows 1..T-1-n_vpt already hold patch+pos;
 // the last n_vpt rows := vpt[0..n_vpt) (IVLP / VPT prompt tokens, no positional embedding);
 // then x := ln_pre(x) written back in place (the residual stream), and y := ln_1(x) as bf16.
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
                             const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
                             const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats = nullptr,
-                            int stats_slots = 0,    // stats != nullptr: y = bf16(x) raw + (sum, sumsq) for EPI_LNFOLD_*
-                            const float* patch_out = nullptr);   // dense conv1 output [n_views * (T-1-n_vpt), W] (no pos) instead
+                            int stats_slots = 0,    // stats != nullptr: y = 16-bit (x - mean) + (sum, sumsq) of it for EPI_LNFOLD_*
+                            const float* patch_out = nullptr,    // dense conv1 output [n_views * (T-1-n_vpt), W] (no pos) instead
                                                                  // of patch rows already scattered into `tokens`
+                            float* shift = nullptr,              // with stats: the row mean the copy was centred by
+                            int f16 = 0);
 // y_bf16[r,:] = LayerNorm(x_f32[r,:]) * g + b   (eps 1e-5, biased variance), W == 768 or any W % 128 == 0 <= 1024
 cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
-                             __nv_bfloat16* y, cudaStream_t stream);
+                             __nv_bfloat16* y, cudaStream_t stream, int f16 = 0);
 // out[v,:] = (ln_post(tokens[v*T + row_idx[v], :]) @ proj[W,E]) ; optionally / ||.||_2.  row_idx == nullptr: row 0
 // (the class token); the text tower passes the EOT position of each sequence.
 cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, const float* g, const float* b,
@@ -75,30 +89,33 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
 // stream), y = ln_1(x) as bf16, and eot[s] = argmax_t ids[s, t] (first maximum; model.py:213-214)
 cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
                                  const float* pos, const float* g1, const float* b1, float* tokens, __nv_bfloat16* y,
-                                 int* eot, cudaStream_t stream, float* stats = nullptr, int stats_slots = 0);
+                                 int* eot, cudaStream_t stream, float* stats = nullptr, int stats_slots = 0,
+                                 float* shift = nullptr, int f16 = 0);
 // qkv [B*T, 3W] bf16 (q | k | v, heads = 64-wide column blocks) -> out [B*T, W] bf16
 // causal != 0: key j is visible to query i only if j <= i (text tower); T <= 80
 // dev_status + num_sms given: the tcgen05 / TMEM kernel (attention_tc.cu) runs when the shape allows it (no mask,
 // T <= 64, even head count; JCB_ATT_IMPL=mma forces the mma.sync kernel); otherwise the mma.sync kernel (attention.cu)
 cudaError_t launch_attention(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                             cudaStream_t stream, int causal = 0, int* dev_status = nullptr, int num_sms = 0);
+                             cudaStream_t stream, int causal = 0, int* dev_status = nullptr, int num_sms = 0, int f16 = 0);
 // query row 0 only (no mask, T <= 64): out [n_views, W] bf16, dense
 cudaError_t launch_attention_cls(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, int f16 = 0);
 bool attention_tc_supported(int T, int heads, int causal);
 cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, int64_t n_views, int T, int heads, __nv_bfloat16* out,
-                                cudaStream_t stream, int* dev_status, int num_sms);
+                                cudaStream_t stream, int* dev_status, int num_sms, int f16 = 0, int causal = 0);
+// hits / misses of the encoded-tensor-map cache (gemm.cu)
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 // fp32 -> bf16 cast (weight packing)
-cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
+cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream, int f16 = 0);
 // W'[rows, cols] (bf16) = W (fp32) + scaling * B[rows, r] @ A[r, cols]   for a row range of a packed weight
 cudaError_t launch_merge_lora_cast(const float* W, const float* A, const float* B, int rows, int cols, int r,
-                                   float scaling, __nv_bfloat16* dst, cudaStream_t stream);
+                                   float scaling, __nv_bfloat16* dst, cudaStream_t stream, int f16 = 0);
 
 // in place W (fp32) += scaling * B A; and the LayerNorm fold of a weight (see EPI_LNFOLD_* above)
 cudaError_t launch_merge_lora_f32(float* W, const float* A, const float* B, int rows, int cols, int r, float scaling,
                                   cudaStream_t stream);
 cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
-                           __nv_bfloat16* Wf, float* S, float* c, cudaStream_t stream);
+                           __nv_bfloat16* Wf, float* S, float* c, cudaStream_t stream, int f16 = 0);
 
 // ---- MTA + head --------------------------------------------------------------------------------
 struct MtaParams {

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace jcb {
@@ -176,6 +177,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+// The same with the 16-bit operand type chosen by the caller: kind::f16 multiplies fp16 (format 0) and bf16 (format 1)
+// operands at the same rate, so the operand type is a property of the data, not of the kernel.
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(bool f16, int m, int n, bool b_mn_major = false) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (b_mn_major ? (1u << 16) : 0u) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread for the whole CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -380,6 +387,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void cp_async_16(uint32_t saddr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
@@ -390,6 +404,33 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// ---------------------------------------------------------------- 16-bit operand type (bf16 | fp16)
+// Every 16-bit tensor of a tower (weights, the raw residual copy, q|k|v, P, attention output, MLP hidden) has ONE
+// element type, fixed when the tower is packed: bf16 (the north star's wording) or fp16 (3 more mantissa bits at the
+// same tensor-core rate: 8x less operand rounding, which is what puts the x100 logits within 1e-2 of the fp32
+// reference).  fp16 conversions SATURATE (+-65504) instead of producing inf.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  if (F16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t to_h(float x) {
+  return static_cast<uint16_t>(pack_h2<F16>(x, 0.f) & 0xFFFFu);
+}
+template <bool F16>
+__device__ __forceinline__ float from_h(uint16_t v) {
+  return unpack_h2<F16>(static_cast<uint32_t>(v)).x;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -32,7 +32,7 @@ __constant__ float c_clip_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 // 1.7 TB/s; this one is a plain streaming kernel.
 constexpr int IM2COL_UNROLL = 4;
 
-template <int DT>
+template <int DT, bool F16>
 __global__ void __launch_bounds__(384)
 im2col_kernel(const void* __restrict__ images, unsigned n_patches, int R, int P, int G, int apply_norm,
               __nv_bfloat16* __restrict__ patches) {
@@ -90,8 +90,8 @@ im2col_kernel(const void* __restrict__ images, unsigned n_patches, int R, int P,
 #pragma unroll
     for (int h = 0; h < EPT / 8; ++h) {
       uint4 o;
-      o.x = pack_bf16x2(f[8 * h + 0], f[8 * h + 1]); o.y = pack_bf16x2(f[8 * h + 2], f[8 * h + 3]);
-      o.z = pack_bf16x2(f[8 * h + 4], f[8 * h + 5]); o.w = pack_bf16x2(f[8 * h + 6], f[8 * h + 7]);
+      o.x = pack_h2<F16>(f[8 * h + 0], f[8 * h + 1]); o.y = pack_h2<F16>(f[8 * h + 2], f[8 * h + 3]);
+      o.z = pack_h2<F16>(f[8 * h + 4], f[8 * h + 5]); o.w = pack_h2<F16>(f[8 * h + 6], f[8 * h + 7]);
       dst[h] = o;
     }
   };
@@ -143,13 +143,13 @@ __device__ __forceinline__ void normalize_row(float4 (&v)[NV], float mean, float
   }
 }
 
-template <int NV>
-__device__ __forceinline__ void store_row_bf16(const float4 (&v)[NV], __nv_bfloat16* __restrict__ y, int lane) {
+template <int NV, bool F16>
+__device__ __forceinline__ void store_row_h(const float4 (&v)[NV], __nv_bfloat16* __restrict__ y, int lane) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     uint2 o;
-    o.x = pack_bf16x2(v[i].x, v[i].y);
-    o.y = pack_bf16x2(v[i].z, v[i].w);
+    o.x = pack_h2<F16>(v[i].x, v[i].y);
+    o.y = pack_h2<F16>(v[i].z, v[i].w);
     reinterpret_cast<uint2*>(y)[lane + 32 * i] = o;
   }
 }
@@ -157,23 +157,34 @@ __device__ __forceinline__ void store_row_bf16(const float4 (&v)[NV], __nv_bfloa
 constexpr int LN_WARPS = 8;
 
 // what a residual GEMM epilogue with EPI_RESID_LNPREP_* leaves behind, for the first block of a tower:
-// y = bf16(x) and stats[0] = (sum x, sum x^2), stats[1..slots) = 0
-template <int NV>
-__device__ __forceinline__ void emit_raw_and_stats(const float4 (&v)[NV], __nv_bfloat16* __restrict__ y,
-                                                   float* __restrict__ st, int slots, int lane) {
+// y = 16-bit (x - shift), stats[0] = (sum, sum of squares) of the centred copy, stats[1..slots) = 0, and
+// shift = the row mean (exact here: the whole row is in registers).  shift == nullptr: uncentred copy (shift 0).
+template <int NV, bool F16>
+__device__ __forceinline__ void emit_raw_and_stats(float4 (&v)[NV], __nv_bfloat16* __restrict__ y,
+                                                   float* __restrict__ st, int slots, float* __restrict__ shift,
+                                                   int lane) {
+  float mean = 0.f;
+  if (shift != nullptr) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) t += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(t) / static_cast<float>(NV * 128);
+  }
   float s = 0.f, q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
   }
   s = warp_sum(s);
   q = warp_sum(q);
-  store_row_bf16<NV>(v, y, lane);
+  store_row_h<NV, F16>(v, y, lane);
   if (lane < 2 * slots) st[lane] = lane == 0 ? s : (lane == 1 ? q : 0.f);
+  if (shift != nullptr && lane == 0) *shift = mean;
 }
 
-template <int NV>
+template <int NV, bool F16>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_kernel(const float* __restrict__ x, long long rows, const float* __restrict__ g,
                  const float* __restrict__ b, __nv_bfloat16* __restrict__ y) {
@@ -188,16 +199,17 @@ layernorm_kernel(const float* __restrict__ x, long long rows, const float* __res
   float mean, rstd;
   row_stats<NV>(v, W, mean, rstd);
   normalize_row<NV>(v, mean, rstd, g, b, lane);
-  store_row_bf16<NV>(v, y + row * W, lane);
+  store_row_h<NV, F16>(v, y + row * W, lane);
 }
 
-template <int NV>
+template <int NV, bool F16>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* __restrict__ cls,
                 const float* __restrict__ pos, const float* __restrict__ vpt, int n_vpt,
                 const float* __restrict__ g_pre, const float* __restrict__ b_pre,
                 const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y,
-                float* __restrict__ stats, int stats_slots, const float* __restrict__ patch_out) {
+                float* __restrict__ stats, int stats_slots, const float* __restrict__ patch_out,
+                float* __restrict__ shift) {
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -238,22 +250,23 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
   normalize_row<NV>(v, mean, rstd, g_pre, b_pre, lane);  // ln_pre -> residual stream
 #pragma unroll
   for (int i = 0; i < NV; ++i) xr[lane + 32 * i] = v[i];
-  if (stats != nullptr) {   // LayerNorm folded into the consuming GEMM: raw bf16 copy + (sum, sum of squares)
-    emit_raw_and_stats<NV>(v, y + row * W, stats + row * stats_slots * 2, stats_slots, lane);
+  if (stats != nullptr) {   // LayerNorm folded into the consuming GEMM: centred 16-bit copy + (sum, sum of squares)
+    emit_raw_and_stats<NV, F16>(v, y + row * W, stats + row * stats_slots * 2, stats_slots,
+                                shift ? shift + row : nullptr, lane);
     return;
   }
   row_stats<NV>(v, W, mean, rstd);
   normalize_row<NV>(v, mean, rstd, g1, b1, lane);        // layer 0's ln_1
-  store_row_bf16<NV>(v, y + row * W, lane);
+  store_row_h<NV, F16>(v, y + row * W, lane);
 }
 
 // ------------------------------------------------------------------------------------------ text front end
-template <int NV>
+template <int NV, bool F16>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, int vocab,
                      const float* __restrict__ tok_emb, const float* __restrict__ pos, const float* __restrict__ g1,
                      const float* __restrict__ b1, float* __restrict__ tokens, __nv_bfloat16* __restrict__ y,
-                     int* __restrict__ eot, float* __restrict__ stats, int stats_slots) {
+                     int* __restrict__ eot, float* __restrict__ stats, int stats_slots, float* __restrict__ shift) {
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -272,12 +285,13 @@ text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, i
 #pragma unroll
   for (int i = 0; i < NV; ++i) xr[lane + 32 * i] = v[i];
   if (stats != nullptr) {
-    emit_raw_and_stats<NV>(v, y + row * W, stats + row * stats_slots * 2, stats_slots, lane);
+    emit_raw_and_stats<NV, F16>(v, y + row * W, stats + row * stats_slots * 2, stats_slots,
+                                shift ? shift + row : nullptr, lane);
   } else {
     float mean, rstd;
     row_stats<NV>(v, W, mean, rstd);
     normalize_row<NV>(v, mean, rstd, g1, b1, lane);
-    store_row_bf16<NV>(v, y + row * W, lane);
+    store_row_h<NV, F16>(v, y + row * W, lane);
   }
   if (t == 0) {  // the warp of a sequence's first token also finds its EOT position: first maximum of the ids
     long long best = -1;
@@ -382,22 +396,24 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
 }
 
 // ------------------------------------------------------------------------------------------ packing
-__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+template <bool F16>
+__global__ void cast_h_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+  if (i < n) dst[i] = to_h<F16>(src[i]);
 }
 
 // dst = bf16(W + scaling * B @ A), fp32 accumulation: the merge the reference's eval path is
 // mathematically equal to (test.py:388-398 applies W x + s x (BA)^T un-merged).
+template <bool F16>
 __global__ void merge_lora_cast_kernel(const float* __restrict__ W, const float* __restrict__ A,
                                        const float* __restrict__ B, int rows, int cols, int r, float scaling,
-                                       __nv_bfloat16* __restrict__ dst) {
+                                       uint16_t* __restrict__ dst) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(rows) * cols) return;
   const int o = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
   float d = 0.f;
   for (int k = 0; k < r; ++k) d = fmaf(B[o * r + k], A[k * cols + c], d);
-  dst[i] = __float2bfloat16_rn(W[i] + scaling * d);
+  dst[i] = to_h<F16>(W[i] + scaling * d);
 }
 
 // in place: W[rows, cols] (fp32) += scaling * B[rows, r] @ A[r, cols]
@@ -414,9 +430,10 @@ __global__ void merge_lora_f32_kernel(float* __restrict__ W, const float* __rest
 // LayerNorm folded into the consuming GEMM (kernels.h EPI_LNFOLD_*): one warp per output row n of W [N, K]
 //   Wf[n, k] = bf16(gamma[k] * W[n, k]);  S[n] = sum_k float(Wf[n, k]);  c[n] = sum_k beta[k] * W[n, k] + bias[n]
 // S is the sum of the ROUNDED folded weights, i.e. exactly what the tensor core will multiply the row mean by.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
-               const float* __restrict__ bias, int N, int K, __nv_bfloat16* __restrict__ Wf, float* __restrict__ S,
+               const float* __restrict__ bias, int N, int K, uint16_t* __restrict__ Wf, float* __restrict__ S,
                float* __restrict__ c) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -424,9 +441,9 @@ fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma, con
   float s = 0.f, cc = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float w = W[static_cast<long long>(n) * K + k];
-    const __nv_bfloat16 wf = __float2bfloat16_rn(gamma[k] * w);
+    const uint16_t wf = to_h<F16>(gamma[k] * w);
     Wf[static_cast<long long>(n) * K + k] = wf;
-    s += __bfloat162float(wf);
+    s += from_h<F16>(wf);
     cc = fmaf(beta[k], w, cc);
   }
   s = warp_sum(s);
@@ -445,14 +462,16 @@ cudaError_t launch_merge_lora_f32(float* W, const float* A, const float* B, int 
 }
 
 cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
-                           __nv_bfloat16* Wf, float* S, float* c, cudaStream_t stream) {
+                           __nv_bfloat16* Wf, float* S, float* c, cudaStream_t stream, int f16) {
   if (N == 0) return cudaSuccess;
-  fold_ln_kernel<<<static_cast<unsigned>((N + 7) / 8), 256, 0, stream>>>(W, gamma, beta, bias, N, K, Wf, S, c);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(Wf);
+  if (f16) fold_ln_kernel<true><<<static_cast<unsigned>((N + 7) / 8), 256, 0, stream>>>(W, gamma, beta, bias, N, K, dst, S, c);
+  else fold_ln_kernel<false><<<static_cast<unsigned>((N + 7) / 8), 256, 0, stream>>>(W, gamma, beta, bias, N, K, dst, S, c);
   return cudaGetLastError();
 }
 
 cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, int resolution, int patch,
-                          int apply_norm, __nv_bfloat16* patches, cudaStream_t stream) {
+                          int apply_norm, __nv_bfloat16* patches, cudaStream_t stream, int f16) {
   if (resolution % patch != 0 || patch % 16 != 0) return cudaErrorInvalidValue;
   const int G = resolution / patch;
   const int ept = 8;
@@ -470,12 +489,16 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
   const int64_t want = (n_patches + IM2COL_UNROLL - 1) / IM2COL_UNROLL;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * (1536 / threads) * 2));
   const unsigned np = static_cast<unsigned>(n_patches);
+#define JCB_IM2COL(DT)                                                                                              \
+  if (f16) im2col_kernel<DT, true><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); \
+  else im2col_kernel<DT, false><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches)
   switch (img_dtype) {
-    case IMG_F32: im2col_kernel<IMG_F32><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); break;
-    case IMG_BF16: im2col_kernel<IMG_BF16><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); break;
-    case IMG_U8: im2col_kernel<IMG_U8><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); break;
+    case IMG_F32: JCB_IM2COL(IMG_F32); break;
+    case IMG_BF16: JCB_IM2COL(IMG_BF16); break;
+    case IMG_U8: JCB_IM2COL(IMG_U8); break;
     default: return cudaErrorInvalidValue;
   }
+#undef JCB_IM2COL
   return cudaGetLastError();
 }
 
@@ -486,27 +509,31 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
     case 8: { constexpr int NV = 8; CALL; } break; \
     default: return cudaErrorInvalidValue;     \
   }
+// the same with the 16-bit output type as a second compile-time constant F16
+#define JCB_DISPATCH_NV_H(W, f16, CALL)                                  \
+  if (f16) { constexpr bool F16 = true; JCB_DISPATCH_NV(W, CALL) }       \
+  else { constexpr bool F16 = false; JCB_DISPATCH_NV(W, CALL) }
 
 cudaError_t launch_layernorm(const float* x, int64_t rows, int W, const float* g, const float* b,
-                             __nv_bfloat16* y, cudaStream_t stream) {
+                             __nv_bfloat16* y, cudaStream_t stream, int f16) {
   if (W % 128 != 0) return cudaErrorInvalidValue;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
-  JCB_DISPATCH_NV(W, (layernorm_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(x, rows, g, b, y)));
+  JCB_DISPATCH_NV_H(W, f16, (layernorm_kernel<NV, F16><<<grid, LN_WARPS * 32, 0, stream>>>(x, rows, g, b, y)));
   return cudaGetLastError();
 }
 
 cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const float* cls, const float* pos,
                             const float* vpt, int n_vpt, const float* g_pre, const float* b_pre, const float* g1,
                             const float* b1, __nv_bfloat16* y, cudaStream_t stream, float* stats, int stats_slots,
-                            const float* patch_out) {
+                            const float* patch_out, float* shift, int f16) {
   if (W % 128 != 0) return cudaErrorInvalidValue;
   const long long rows = n_views * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
-  JCB_DISPATCH_NV(W, (embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(tokens, rows, T, cls, pos, vpt,
-                                                                           n_vpt, g_pre, b_pre, g1, b1, y, stats,
-                                                                           stats_slots, patch_out)));
+  JCB_DISPATCH_NV_H(W, f16, (embed_ln_kernel<NV, F16><<<grid, LN_WARPS * 32, 0, stream>>>(
+                                tokens, rows, T, cls, pos, vpt, n_vpt, g_pre, b_pre, g1, b1, y, stats, stats_slots,
+                                patch_out, shift)));
   return cudaGetLastError();
 }
 
@@ -528,28 +555,32 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
 
 cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
                                  const float* pos, const float* g1, const float* b1, float* tokens, __nv_bfloat16* y,
-                                 int* eot, cudaStream_t stream, float* stats, int stats_slots) {
+                                 int* eot, cudaStream_t stream, float* stats, int stats_slots, float* shift, int f16) {
   if (W % 128 != 0 || T < 1 || vocab < 1) return cudaErrorInvalidValue;
   const long long rows = n_seq * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
-  JCB_DISPATCH_NV(W, (text_embed_ln_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(ids, rows, T, vocab, tok_emb, pos,
-                                                                                g1, b1, tokens, y, eot, stats, stats_slots)));
+  JCB_DISPATCH_NV_H(W, f16, (text_embed_ln_kernel<NV, F16><<<grid, LN_WARPS * 32, 0, stream>>>(
+                                ids, rows, T, vocab, tok_emb, pos, g1, b1, tokens, y, eot, stats, stats_slots, shift)));
   return cudaGetLastError();
 }
 
-cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream) {
+cudaError_t launch_cast_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream, int f16) {
   if (n == 0) return cudaSuccess;
-  cast_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+  uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+  if (f16) cast_h_kernel<true><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, d, n);
+  else cast_h_kernel<false><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, d, n);
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_lora_cast(const float* W, const float* A, const float* B, int rows, int cols, int r,
-                                   float scaling, __nv_bfloat16* dst, cudaStream_t stream) {
+                                   float scaling, __nv_bfloat16* dst, cudaStream_t stream, int f16) {
   const long long n = static_cast<long long>(rows) * cols;
   if (n == 0) return cudaSuccess;
-  merge_lora_cast_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(W, A, B, rows, cols, r,
-                                                                                    scaling, dst);
+  uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (f16) merge_lora_cast_kernel<true><<<grid, 256, 0, stream>>>(W, A, B, rows, cols, r, scaling, d);
+  else merge_lora_cast_kernel<false><<<grid, 256, 0, stream>>>(W, A, B, rows, cols, r, scaling, d);
   return cudaGetLastError();
 }
 

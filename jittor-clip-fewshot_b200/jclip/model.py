@@ -7,10 +7,8 @@ unchanged -- but the objects are thin parameter containers: `encode_image` hands
 to the sm_100a library through the C-ABI (include/jclip_b200.h), with no per-op Python.
 
 `encode_text` (it runs once per run to produce the cached text embeddings,
-`clip_classifier`, reference test.py:920-940) runs on the same library with a causal attention mask;
-`encode_text_torch` is a plain-torch cross-check for tests.
+`clip_classifier`, reference test.py:920-940) runs on the same library with a causal attention mask.
 """
-import math
 import pickle
 from typing import Dict
 
@@ -233,6 +231,8 @@ class VisionTransformer(Module):
             h = c_void_p()
             check(ctx.lib.jcb_vit_create(ctx.handle, byref(cfg), byref(h)), ctx.handle)
             self._vit, self._ctx, self._dirty = h, ctx, True
+        if not self._dirty and ctx.lib.jcb_vit_operand_type(self._vit) != ctx.lib.jcb_ctx_get_operand_type(ctx.handle):
+            self._dirty = True      # the context's operand type changed since the weights were packed
         if self._dirty:
             lib = ctx.lib
             for name, p in self.named_parameters("visual."):
@@ -370,6 +370,8 @@ class CLIP(Module):
             h = c_void_p()
             check(lib.jcb_text_create(ctx.handle, byref(cfg), byref(h)), ctx.handle)
             self._text, self._text_ctx, self._text_dirty = h, ctx, True
+        if not self._text_dirty and lib.jcb_text_operand_type(self._text) != lib.jcb_ctx_get_operand_type(ctx.handle):
+            self._text_dirty = True
         if self._text_dirty:
             named = [("token_embedding.weight", self.token_embedding.weight), ("positional_embedding", self.positional_embedding),
                      ("ln_final.weight", self.ln_final.weight), ("ln_final.bias", self.ln_final.bias),
@@ -425,8 +427,7 @@ class CLIP(Module):
             raise ValueError(f"expected tokens of shape [n, {self.context_length}], got {tuple(tok.shape)}")
         if not tok.is_cuda:
             if not torch.cuda.is_available():
-                raise RuntimeError("encode_text runs on a B200 GPU only; there is no CPU fallback "
-                                   "(encode_text_torch is the plain-torch cross-check)")
+                raise RuntimeError("encode_text runs on a B200 GPU only; there is no CPU fallback")
             tok = tok.cuda()
         tok = tok.to(torch.int64).contiguous()
         with torch.cuda.device(tok.device):
@@ -435,23 +436,6 @@ class CLIP(Module):
             out = torch.empty((tok.shape[0], self.text_projection.shape[1]), dtype=torch.float32, device=tok.device)
             check(ctx.lib.jcb_encode_text(handle, ptr(tok), tok.shape[0], int(normalize), ptr(out)), ctx.handle)
         return out
-
-    # ---- plain torch fp32 text tower: a cross-check for tests, never called by the product path ---------
-    @torch.no_grad()
-    def encode_text_torch(self, text):
-        # jclip/model.py:202-215
-        text = as_torch(text).long()
-        dev = text.device
-        x = self.token_embedding.weight.torch(dev)[text] + self.positional_embedding.torch(dev)
-        mask = self.build_attention_mask().to(dev)
-        for block in self.transformer.resblocks:
-            x = x + _text_attention(block.attn, _ln(x, block.ln_1, dev), mask, dev)
-            h = _ln(x, block.ln_2, dev) @ block.mlp.c_fc.weight.torch(dev).t() + block.mlp.c_fc.bias.torch(dev)
-            h = h * torch.sigmoid(1.702 * h)
-            x = x + h @ block.mlp.c_proj.weight.torch(dev).t() + block.mlp.c_proj.bias.torch(dev)
-        x = _ln(x, self.ln_final, dev)
-        eot = text.argmax(dim=-1)                                  # highest token id = EOT
-        return x[torch.arange(x.shape[0], device=dev), eot] @ self.text_projection.torch(dev)
 
     def execute(self, image, text):
         # jclip/model.py:217-232
@@ -480,32 +464,6 @@ class CLIP(Module):
     def load(self, path):
         with open(path, "rb") as f:
             self.load_parameters(pickle.load(f))
-
-
-def _ln(x, ln, dev):
-    return torch.nn.functional.layer_norm(x, (x.shape[-1],), ln.weight.torch(dev), ln.bias.torch(dev), 1e-5)
-
-
-def _text_attention(attn, x, mask, dev):
-    """Packed or LoRA-wrapped attention on [B,S,W] in torch (text tower only)."""
-    W, H = attn.embed_dim, attn.num_heads
-    w_in, b_in = attn.in_proj_weight.torch(dev), attn.in_proj_bias.torch(dev)
-    qkv = []
-    for j, name in enumerate(("q_proj", "k_proj", "v_proj")):
-        y = x @ w_in[j * W:(j + 1) * W].t() + b_in[j * W:(j + 1) * W]
-        lin = getattr(attn, name, None)
-        if lin is not None and getattr(lin, "lora_enabled", False):      # reference test.py:388-398
-            y = y + (x @ (lin.w_lora_B.torch(dev) @ lin.w_lora_A.torch(dev)).t()) * lin.scaling
-        qkv.append(y)
-    B, S, _ = x.shape
-    q, k, v = (t.view(B, S, H, W // H).transpose(1, 2) for t in qkv)
-    a = (q @ k.transpose(-2, -1)) / math.sqrt(W // H) + mask[:S, :S]
-    o = (torch.softmax(a, dim=-1) @ v).transpose(1, 2).reshape(B, S, W)
-    y = o @ attn.out_proj.weight.torch(dev).t() + attn.out_proj.bias.torch(dev)
-    lin = getattr(attn, "proj", None)
-    if lin is not None and getattr(lin, "lora_enabled", False):
-        y = y + (o @ (lin.w_lora_B.torch(dev) @ lin.w_lora_A.torch(dev)).t()) * lin.scaling
-    return y
 
 
 def build_model(state_dict: Dict[str, np.ndarray], design_details=None):

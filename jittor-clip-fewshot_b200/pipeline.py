@@ -42,8 +42,13 @@ class _Ticket:
 class HotPath:
     """encode_image -> L2 normalise -> solve_mta x3 -> Channel_LP / logit_normalize / fusion -> top-k."""
 
-    def __init__(self, clip_model, text_bank, channel_lp, clip_model_zs=None, rank_by="cs5", k=5,
+    def __init__(self, clip_model, text_bank, channel_lp, clip_model_zs=None, rank_by="cs1", k=5,
                  apply_clip_norm=True):
+        """rank_by: the score whose top-k is returned.  Default "cs1" = cosine_similarity1, what the reference's
+        evaluate_base writes to its result file (test.py:1738); "cs5" is the LP++ fusion the reference computes beside it
+        (test.py:1735) and BASELINE.json's headline config names -- bench.py and the parity tests pass it explicitly."""
+        if rank_by not in _capi.SCORE_INDEX:
+            raise ValueError(f"rank_by must be one of {sorted(_capi.SCORE_INDEX)}, got {rank_by!r}")
         self.model, self.model_zs = clip_model, clip_model_zs
         self.text, self.lp = text_bank, channel_lp
         self.rank_by, self.k, self.apply_clip_norm = rank_by, k, apply_clip_norm
@@ -203,3 +208,41 @@ def write_ood_split(base_path, new_path, impaths, is_base):
     with open(base_path, "w") as fb, open(new_path, "w") as fn:
         for p, b in zip(impaths, is_base):
             (fb if b else fn).write(f"{p}\n")
+
+
+def read_results(path):
+    """A result file as {first field: [remaining fields]} in file order; a repeated key keeps its first position and
+    its last values (reference load_txt_to_dict, test.py:1650-1658: whitespace-split lines into a dict).  A blank line
+    raises, as it does in the reference (`parts[0]` of an empty split)."""
+    out = {}
+    with open(path, "r") as f:
+        for line in f:
+            fields = line.split()
+            if not fields:
+                raise IndexError(f"{path}: blank line in a result file")
+            out[fields[0]] = fields[1:]
+    return out
+
+
+def save_results(entries, path):
+    """reference save_dict_to_txt (test.py:1660-1664): "<key> <v1> <v2> ...\n" per entry, single spaces."""
+    with open(path, "w") as f:
+        for key, values in entries.items():
+            f.write(f"{key} {' '.join(values)}\n")
+
+
+def merge_results(base_txt, update_txt):
+    """The merger that ends run_test1 (reference update_txt_file, test.py:1666-1674, called at :1837-1840): the base
+    list written by evaluate_base is overwritten, entry by entry, by the list evaluate_new wrote for the images the
+    OOD router sent to the zero-shot tower; files only in the update list are appended.  Rewrites `base_txt` in place."""
+    merged = read_results(base_txt)
+    merged.update(read_results(update_txt))
+    save_results(merged, base_txt)
+    return merged
+
+
+def clean_results(input_txt, output_txt):
+    """test.py:1843-1849: every line through process_line ("['dir/file.jpg']" -> "file.jpg") into result.txt."""
+    with open(input_txt, "r") as fi, open(output_txt, "w") as fo:
+        for line in fi:
+            fo.write(process_line(line))

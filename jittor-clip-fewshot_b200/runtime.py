@@ -45,6 +45,23 @@ class Context:
         """Opt-in: last block of the image tower on the class-token rows only (include/jclip_b200.h)."""
         check(self.lib.jcb_ctx_set_cls_only_last_block(self.handle, int(bool(on))), self.handle)
 
+    def set_operand_type(self, name):
+        """16-bit operand type of the towers packed from now on: "f16" (default; logits within 1e-2 of the fp32
+        reference end to end) or "bf16" (include/jclip_b200.h jcb_ctx_set_operand_type).  Models re-pack lazily."""
+        try:
+            code = _capi.OPERAND_NAMES[str(name).lower()]
+        except KeyError:
+            raise ValueError(f"operand type must be 'f16' or 'bf16', got {name!r}") from None
+        check(self.lib.jcb_ctx_set_operand_type(self.handle, code), self.handle)
+
+    @property
+    def operand_type(self):
+        return "f16" if self.lib.jcb_ctx_get_operand_type(self.handle) == _capi.OPERAND_F16 else "bf16"
+
+    @property
+    def operand_torch_dtype(self):
+        return torch.float16 if self.operand_type == "f16" else torch.bfloat16
+
     def sync(self):
         check(self.lib.jcb_sync(self.handle), self.handle)
 

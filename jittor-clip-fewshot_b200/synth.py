@@ -16,7 +16,7 @@ EMBED_DIM = 512
 
 
 def make_vit_state_dict(seed=0, layers=12, width=768, patch=32, resolution=224, embed_dim=EMBED_DIM,
-                        with_text_stub=True, text_layers=1, vpt_tokens=0):
+                        with_text_stub=True, text_layers=1, vpt_tokens=0, trained_like=False):
     """Random-init CLIP state dict (numpy fp32) with the reference's key names (vision tower + the
     few text-side keys `build_model` reads shapes from)."""
     rng = np.random.default_rng(seed)
@@ -39,6 +39,20 @@ def make_vit_state_dict(seed=0, layers=12, width=768, patch=32, resolution=224, 
     }
     if vpt_tokens:
         sd["visual.VPT"] = n((vpt_tokens, width), 0.02)      # reference jclip/model1.py:161-164
+    if trained_like:
+        # Activation statistics of TRAINED CLIP towers that random init never produces: "offset" = every residual row
+        # carries a common offset (|row mean| = 20 x the spread of its channels); "outliers" = three "massive
+        # activation" channels 100 x above the rest; True / "both" = both.  They enter through ln_pre's bias, i.e.
+        # straight into the residual stream, and stay there through all blocks (LayerNorm removes them from what the
+        # blocks compute, the residual adds keep them).
+        kind = "both" if trained_like is True else str(trained_like)
+        if kind not in ("offset", "outliers", "both"):
+            raise ValueError(f"trained_like must be 'offset', 'outliers' or 'both', got {trained_like!r}")
+        if kind in ("offset", "both"):
+            sd["visual.ln_pre.bias"] = sd["visual.ln_pre.bias"] + f32(20.0)
+        if kind in ("outliers", "both"):
+            for ch, sign in ((7, 1.0), (300, -1.0), (511, 1.0)):
+                sd["visual.ln_pre.bias"][ch] += f32(sign * 100.0)
     for i in range(layers):
         p = f"visual.transformer.resblocks.{i}."
         sd[p + "attn.in_proj_weight"] = n((3 * width, width), attn_std)
@@ -144,6 +158,42 @@ def make_text_features(seed=1, num_classes=NUM_CLASSES, dim=EMBED_DIM, project_o
         t = t - (t @ u)[:, None] * u[None, :]
     t /= np.linalg.norm(t, axis=1, keepdims=True)
     return t.astype(np.float32)
+
+
+def make_structured_text_banks(centre_feats, seed=10, num_classes=NUM_CLASSES, per_image=6, n_banks=3):
+    """Three text banks [C, dim] (prompt-tuned / hand / zero-shot variants of the SAME classes) whose class scores
+    are separated the way trained CLIP text features separate them, built from the images' own centre-view
+    embeddings `centre_feats` [I, dim] (unit rows, e.g. from the fp32 oracle tower).
+
+    A random-init tower maps every image next to one common direction m, so against independent random unit rows all
+    403 scores of an image sit within a few logits and neighbouring scores at rank 5 are ~0.2 apart: any 0.05 logit
+    perturbation flips a label there, which says nothing about the path under test.  Here image i owns `per_image`
+    classes c = per_image * i + k whose text rows point along the image-specific part d_i = f_i - m with decreasing
+    weight a_k = 1, 0.8, 0.64, ... (plus per-bank noise), so its top scores are whole logits apart -- as they are for a
+    trained model and its class prompts; the remaining classes are random rows orthogonal to m."""
+    f = np.asarray(centre_feats, np.float32)
+    I, dim = f.shape
+    if per_image * I > num_classes:
+        raise ValueError(f"{I} images x {per_image} classes do not fit {num_classes} classes")
+    rng = np.random.default_rng(seed)
+    m = f.mean(0)
+    m /= np.linalg.norm(m)
+    d = f - (f @ m)[:, None] * m[None, :]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    base = make_text_features(seed + 100, num_classes, dim, project_out=m)
+    banks = []
+    for b in range(n_banks):
+        t = base + 0.05 * rng.standard_normal(base.shape).astype(np.float32)
+        for i in range(I):
+            for k in range(per_image):
+                noise = rng.standard_normal(dim).astype(np.float32)
+                noise -= (noise @ d[i]) * d[i]
+                noise /= np.linalg.norm(noise)
+                a = 0.8 ** k
+                t[per_image * i + k] = a * d[i] + np.sqrt(max(1.0 - a * a, 0.0)) * noise
+        t /= np.linalg.norm(t, axis=1, keepdims=True)
+        banks.append(t.astype(np.float32))
+    return banks
 
 
 def make_head(seed=2, text_zs=None, num_classes=NUM_CLASSES, dim=EMBED_DIM):

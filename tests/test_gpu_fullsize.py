@@ -88,62 +88,102 @@ def test_pipeline_sweep_sizes(jb, cuda_dev, lora_model, n_crops, n_images):
         assert set(t5.tolist()) == set(topk[i].cpu().tolist())
 
 
+# End-to-end acceptance (BASELINE.json north star): embedding cosine >= 0.999, logits within 1e-2 absolute, >= 99.5 %
+# top-5 label agreement against the fp32 reference on identical synthetic inputs (random unit text
+# rows).  Asserted per 16-bit operand type:
+#   f16  (default)  the north-star numbers themselves
+#   bf16            within 1.2 x of what 8-bit significands measure (profiles/r01y_e2e_agreement_*.json and
+#                   profiles/r02_error_attribution_*.json: the same deviations reproduced on the CPU by rounding the
+#                   fp32 oracle's operands -- half of it is weight rounding, identical for every view, which MTA's
+#                   averaging over views cannot remove)
+# "structured" text banks (synth.make_structured_text_banks) point the class rows along the image-specific directions
+# of the embeddings -- the worst case for the logit deviation (|dlogit| <= 100 |df|) and the case where the top scores are
+# whole logits apart; there the gate is the top-5 agreement, and the logit bound is the measured one x 1.2.
+E2E_BOUNDS = {
+    ("f16", "random"): {"dlogit": 1e-2, "cs1": 0.995, "cs5": 0.995},
+    ("bf16", "random"): {"dlogit": 0.08, "cs1": 0.995, "cs5": 0.97},
+    ("f16", "structured"): {"dlogit": 0.35, "cs1": 0.995, "cs5": 0.995},
+    ("bf16", "structured"): {"dlogit": 0.80, "cs1": 0.985, "cs5": 0.985},
+}
+_oracle_feats_cache = {}
+
+
+def _oracle_feats(jb, sd, lora, I, V):
+    """fp32 oracle tower on the test's views, once per (I, V): [I, V, 512] unit rows (CPU, all host cores)."""
+    import os
+    from oracle import vit_encode_image
+    key = (I, V)
+    if key not in _oracle_feats_cache:
+        torch.set_num_threads(os.cpu_count() or 1)
+        imgs = jb.synth.make_views(21, I, V)                       # float32 [I, V, 3, 224, 224] in [0, 1]
+        sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+        feats = torch.stack([vit_encode_image(sd_t, imgs[i], lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+                             for i in range(I)])
+        _oracle_feats_cache[key] = (imgs, feats)
+    return _oracle_feats_cache[key]
+
+
+@pytest.mark.parametrize("text", ["random", "structured"])
+@pytest.mark.parametrize("op", ["f16", "bf16"])
 @pytest.mark.parametrize("I,V", [(64, 9), (24, 65)])
-def test_end_to_end_agreement_with_fp32_oracle(jb, cuda_dev, lora_model, I, V):
+def test_end_to_end_agreement_with_fp32_oracle(jb, cuda_dev, lora_model, I, V, op, text):
     """The whole path against the fp32 oracle END TO END (oracle tower -> oracle MTA x3 -> oracle head), full
-    12-layer LoRA tower, 64 images x 9 views and 24 images x 65 views (the headline N = 64): embedding cosine >= 0.999 (north star), top-5 label agreement, and
-    the logit deviation.  The other parity tests hold MTA / head to 1e-2 and 99.5 % GIVEN THE SAME embeddings; here
-    the x100 logits also carry the bf16 tower's embedding error (cosine 0.999997 -> 0.02-0.07 logits), and a top-5
-    set can only differ where the oracle's 5th and 6th scores are closer than twice that error -- asserted per image.  The
-    measured numbers are written to gpurun_out/e2e_agreement_<I>x<V>.json (copies under profiles/)."""
+    12-layer LoRA tower, 64 images x 9 views and 24 images x 65 views (the headline N = 64).  A top-5 set can only differ
+    where the oracle's 5th and 6th scores are closer than twice the logit deviation -- asserted per image.  The measured
+    numbers are written to gpurun_out/e2e_agreement_<I>x<V>_<op>_<text>.json (copies under profiles/)."""
     import json
     import os
-    from oracle import pipeline_image, vit_encode_image
+    from oracle import pipeline_image
     sd, lora, model = lora_model
-    imgs = jb.synth.make_views(21, I, V)                       # float32 [I, V, 3, 224, 224] in [0, 1]
-    Ts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
+    imgs, ref_feats = _oracle_feats(jb, sd, lora, I, V)
+    if text == "structured":
+        Ts = [torch.from_numpy(t) for t in jb.synth.make_structured_text_banks(ref_feats[:, 0].numpy(), seed=10)]
+    else:
+        Ts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
     lp_np = jb.synth.make_head(2, Ts[2].numpy())
     lp_t = tuple(torch.from_numpy(a) for a in lp_np)
     lp = jb.Channel_LP()
     lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = lp_np
-    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
-    torch.set_num_threads(os.cpu_count() or 1)
+    ctx = jb.get_context(cuda_dev)
+    prev = ctx.operand_type
     res = {}
-    for rank_by in ("cs5", "cs1"):
-        hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by=rank_by)
-        topk, feats, scores = hp.evaluate_base(torch.from_numpy(imgs).to(cuda_dev), return_feats=True, return_scores=True)
-        topk, feats, scores = topk.cpu(), feats.cpu(), scores.cpu()
-        agree, same_set, cos_min, dlogit, gap_at_flips = 0, 0, 1.0, 0.0, 0.0
-        for i in range(I):
-            f = vit_encode_image(sd_t, imgs[i], lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
-            cos_min = min(cos_min, float(_cos(feats[i], f).min()))
-            t5, sc, _ = pipeline_image(f, f, Ts[0], Ts[1], Ts[2], lp_t, score=rank_by)
-            ref_scores = sc[rank_by][0]
-            d_i = float((scores[i] - ref_scores).abs().max())
-            dlogit = max(dlogit, d_i)
-            n = len(set(t5.tolist()) & set(topk[i].tolist()))
-            agree += n
-            same_set += n == 5
-            if n < 5:
-                # a different top-5 set is only possible at a near-tie: the oracle's own 5th and 6th scores are closer
-                # than twice the logit deviation of this image
-                srt = ref_scores.sort(descending=True).values
-                gap = float(srt[4] - srt[5])
-                assert gap <= 2.0 * d_i + 1e-6, (i, gap, d_i)
-                assert n == 4, (i, n)                         # and then exactly one label is exchanged
-                gap_at_flips = max(gap_at_flips, gap)
-        res[rank_by] = {"images": I, "views": V, "top5_label_agreement": agree / (5 * I), "identical_top5_sets": same_set / I,
-                        "min_embedding_cosine": cos_min, "max_abs_logit_diff": dlogit,
-                        "largest_oracle_5th_6th_gap_where_sets_differ": gap_at_flips}
+    try:
+        ctx.set_operand_type(op)
+        for rank_by in ("cs5", "cs1"):
+            hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by=rank_by)
+            topk, feats, scores = hp.evaluate_base(torch.from_numpy(imgs).to(cuda_dev), return_feats=True, return_scores=True)
+            topk, feats, scores = topk.cpu(), feats.cpu(), scores.cpu()
+            agree, same_set, cos_min, dlogit, gap_at_flips = 0, 0, 1.0, 0.0, 0.0
+            for i in range(I):
+                f = ref_feats[i]
+                cos_min = min(cos_min, float(_cos(feats[i], f).min()))
+                t5, sc, _ = pipeline_image(f, f, Ts[0], Ts[1], Ts[2], lp_t, score=rank_by)
+                ref_scores = sc[rank_by][0]
+                d_i = float((scores[i] - ref_scores).abs().max())
+                dlogit = max(dlogit, d_i)
+                n = len(set(t5.tolist()) & set(topk[i].tolist()))
+                agree += n
+                same_set += n == 5
+                if n < 5:
+                    # a different top-5 set is only possible at a near-tie: the oracle's own 5th and 6th scores are closer
+                    # than twice the logit deviation of this image
+                    srt = ref_scores.sort(descending=True).values
+                    gap = float(srt[4] - srt[5])
+                    assert gap <= 2.0 * d_i + 1e-6, (i, gap, d_i)
+                    assert n == 4, (i, n)                         # and then exactly one label is exchanged
+                    gap_at_flips = max(gap_at_flips, gap)
+            res[rank_by] = {"images": I, "views": V, "operands": op, "text": text,
+                            "top5_label_agreement": agree / (5 * I), "identical_top5_sets": same_set / I,
+                            "min_embedding_cosine": cos_min, "max_abs_logit_diff": dlogit,
+                            "largest_oracle_5th_6th_gap_where_sets_differ": gap_at_flips}
+    finally:
+        ctx.set_operand_type(prev)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/e2e_agreement_{I}x{V}.json", "w") as fh:
+    with open(f"gpurun_out/e2e_agreement_{I}x{V}_{op}_{text}.json", "w") as fh:
         json.dump(res, fh, indent=1)
     print(res)
-    # measured (profiles/r01y_e2e_agreement_*.json): cs1 (the score test.py ranks by) 99.7 % / 100 %, cs5 99.1 % / 97.5 %
-    # label agreement at 64x9 / 24x65; logits within 0.07.  Every differing set is a one-label exchange at a 5th/6th gap
-    # below 0.1 logits -- the three averaged random text banks put neighbouring cs5 scores ~0.2 apart at rank 5.
-    assert res["cs1"]["top5_label_agreement"] >= 0.985 and res["cs5"]["top5_label_agreement"] >= 0.95, res
-    for r in res.values():
-        assert r["min_embedding_cosine"] >= 0.999
-        assert r["max_abs_logit_diff"] <= 0.15, res
-        assert r["largest_oracle_5th_6th_gap_where_sets_differ"] <= 0.15, res
+    b = E2E_BOUNDS[(op, text)]
+    for rank_by, r in res.items():
+        assert r["min_embedding_cosine"] >= 0.999, res
+        assert r["max_abs_logit_diff"] <= b["dlogit"], res
+        assert r["top5_label_agreement"] >= b[rank_by], res

@@ -139,13 +139,14 @@ def test_encode_text_runs_with_lora(jb):
     tok = torch.randint(1, 60, (3, 77), generator=torch.Generator().manual_seed(0))
     tok[:, 9] = 63
     from oracle import text_encode
-    a = m.encode_text_torch(tok)
+    from _torch_text import encode_text_torch
+    a = encode_text_torch(m, tok)
     assert (a - text_encode(sd, tok)).abs().max() < 1e-4
     layers = jb.apply_lora(_args(encoder="text"), m)
     assert m._text_dirty
-    assert torch.allclose(a, m.encode_text_torch(tok))              # B = 0: adapters are a no-op
+    assert torch.allclose(a, encode_text_torch(m, tok))              # B = 0: adapters are a no-op
     layers[0].q_proj.w_lora_B.data = np.ones((512, 4), np.float32) * 0.05
-    assert not torch.allclose(a, m.encode_text_torch(tok), atol=1e-4)
+    assert not torch.allclose(a, encode_text_torch(m, tok), atol=1e-4)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             m.encode_text(tok)
@@ -234,3 +235,36 @@ def test_alias_package_has_single_module_copies():
     assert get_context is real.runtime.get_context
     import jclip_b200.build as b
     assert b is importlib.import_module("jittor-clip-fewshot_b200.build")
+
+
+def test_result_merger_matches_reference_strings(jb, tmp_path):
+    """merge_results / clean_results against what the reference's own update_txt_file + process_line loop produced
+    (test.py:1650-1674, :1837-1849; fixtures generated by oracle/make_golden_results.py): string-exact."""
+    import json
+    import os
+    from jclip_b200 import pipeline as P
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "result_files.json")))
+    assert len(golden) >= 6
+    for name, g in golden.items():
+        b, u, r = (tmp_path / f"{name}_{n}.txt" for n in ("base", "update", "result"))
+        b.write_text(g["base"])
+        u.write_text(g["update"])
+        merged = P.merge_results(str(b), str(u))
+        assert b.read_text() == g["merged"], name
+        assert list(merged) == [ln.split()[0] for ln in g["merged"].splitlines()], name
+        P.clean_results(str(b), str(r))
+        assert r.read_text() == g["result"], name
+    # a blank line is an error in the reference (IndexError on parts[0]); same here
+    bad = tmp_path / "bad.txt"
+    bad.write_text("a 1 2\n\nb 3 4\n")
+    with pytest.raises(IndexError):
+        P.read_results(str(bad))
+
+
+def test_hotpath_default_rank_is_what_test_py_writes(jb):
+    """evaluate_base writes topk(cosine_similarity1) (test.py:1738) = "cs1"; unknown scores are refused."""
+    import inspect
+    from jclip_b200.pipeline import HotPath
+    assert inspect.signature(HotPath.__init__).parameters["rank_by"].default == "cs1"
+    with pytest.raises(ValueError):
+        HotPath(None, None, None, rank_by="cs9")

@@ -13,6 +13,7 @@ import jclip_b200 as jb  # noqa: E402
 
 what = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+OP = torch.float16 if os.environ.get("JCB_OPERANDS", "f16").lower().startswith("f") else torch.bfloat16
 dev = torch.device("cuda", 0)
 ctx = jb.get_context(dev)
 ctx.bind_current_stream()
@@ -35,16 +36,16 @@ def timeit(fn, iters=10, warm=3):
 
 if what == "attention":
     T, H = 50, 12
-    qkv = torch.randn(n * T, 3 * 768, device=dev).to(torch.bfloat16)
-    out = torch.empty(n * T, 768, dtype=torch.bfloat16, device=dev)
-    ms = timeit(lambda: jb._capi.check(lib.jcb_attention_bf16(h, P(qkv), n, T, H, P(out)), h))
+    qkv = torch.randn(n * T, 3 * 768, device=dev).to(OP)
+    out = torch.empty(n * T, 768, dtype=OP, device=dev)
+    ms = timeit(lambda: jb.blocks.attention(qkv, n, T, H, out, sync=False))
     gb = n * T * 768 * 8 / 1e9
     print(f"attention cfg={os.environ.get('JCB_ATT_CFG', 'default')} n={n}: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
 elif what == "layernorm":
     x = torch.randn(n * 50, 768, device=dev)
     g, b = torch.ones(768, device=dev), torch.zeros(768, device=dev)
-    y = torch.empty(n * 50, 768, dtype=torch.bfloat16, device=dev)
-    ms = timeit(lambda: jb._capi.check(lib.jcb_layernorm_bf16(h, P(x), n * 50, 768, P(g), P(b), P(y)), h))
+    y = torch.empty(n * 50, 768, dtype=OP, device=dev)
+    ms = timeit(lambda: jb.blocks.layernorm(x, g, b, y))
     print(f"layernorm n={n}: {ms:.3f} ms  {n * 50 * 768 * 6 / 1e9 / ms * 1e3:.0f} GB/s")
 elif what == "mta":
     I, V = n, 65
@@ -56,11 +57,11 @@ elif what == "gemm":
     shapes = {"qkv": (2304, 768, 0), "out": (768, 768, 2), "fc1": (3072, 768, 1), "fc2": (768, 3072, 2)}
     M = n * 50
     for name, (N, K, epi) in shapes.items():
-        A = torch.randn(M, K, device=dev).to(torch.bfloat16)
-        B = (torch.randn(N, K, device=dev) * K ** -0.5).to(torch.bfloat16)
+        A = torch.randn(M, K, device=dev).to(OP)
+        B = (torch.randn(N, K, device=dev) * K ** -0.5).to(OP)
         bias = torch.randn(N, device=dev)
-        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 2 else torch.bfloat16)
-        ms = timeit(lambda: jb._capi.check(lib.jcb_gemm_bf16(h, P(A), P(B), M, N, K, P(bias), epi, P(out), N), h))
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 2 else OP)
+        ms = timeit(lambda: jb.blocks.gemm(A, B, out, epi, bias=bias, sync=False))
         print(f"gemm {name} M={M} N={N} K={K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
 elif what == "tta":
     import numpy as np
