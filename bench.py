@@ -415,17 +415,15 @@ def main():
     if not args.no_e2e:
         rng = np.random.default_rng(2000 + rank)
         src = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I_r)]
-        gen = jb.TTAViews(n_crops=args.crops, scale=(0.5, 1.0), seed=rank)
+        gen = jb.TTAViews(n_crops=args.crops, scale=(0.5, 1.0), seed=rank, emit="patches")
 
         def run_images(steps):
-            # software pipeline: while the GPU works on batch k, the host draws the boxes of batch k+1, packs its
-            # images into the other pinned buffer and enqueues upload + view generation behind the running step
-            views = gen(src)
-            for k in range(steps):
-                topk_dev = hp.evaluate_base(views, topk_to_host=False)
-                if k + 1 < steps:
-                    views = gen(src)
-                topk = topk_dev.cpu()          # the step's result on the host (synchronises with step k)
+            # HotPath.evaluate_image_stream: while the towers work on batch k (current stream), the host draws the boxes
+            # of batch k+1, packs its images into the other pinned buffer, and upload + view generation run on a second
+            # stream; the generator writes the conv1 patch matrix directly (emit="patches": no uint8 views, no im2col)
+            topk = None
+            for topk in hp.evaluate_image_stream((src for _ in range(steps)), gen):
+                pass
             return topk
 
         run_images(2)
@@ -437,8 +435,10 @@ def main():
         dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
         e2e_img = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
                    "h2d_bytes_per_step": int(sum(a.size for a in src)), "d2h_bytes_per_step": int(I_r * 5 * 4),
+                   "api": "HotPath.evaluate_image_stream(batches of decoded images, TTAViews(emit='patches')): two batches in flight",
                    "note": "host: 500x375 uint8 decoded images + crop-box draw; device: Pillow-exact centre view + "
-                           f"{args.crops} RandomResizedCrop(0.5-1)+flip views per image, then the hot path"}
+                           f"{args.crops} RandomResizedCrop(0.5-1)+flip views per image written straight into the conv1 patch "
+                           "matrix on a second stream while the previous batch's towers run, then the hot path"}
     # ---- informational: the same device-resident step with the OTHER 16-bit operand type (the towers are re-packed)
     other_operands = None
     if not args.no_e2e:

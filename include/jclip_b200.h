@@ -45,6 +45,10 @@ typedef struct jcb_text jcb_text;
 #define JCB_IMG_F32 0   /* float32, the reference's dtype (T.ToTensor -> float32) */
 #define JCB_IMG_BF16 1
 #define JCB_IMG_U8 2    /* uint8 0..255, scaled by 1/255 on the device */
+/* not pixels but the conv1 patch matrix [n_views * (R/P)^2, 3 * P * P] written by jcb_tta_patches (view generator fused
+ * with ToTensor / tfm_clip / im2col), device-resident, in the tower's 16-bit operand type; apply_clip_norm is ignored */
+#define JCB_IMG_PATCHES_BF16 3
+#define JCB_IMG_PATCHES_F16 4
 
 /* LoRA target projections (reference test.py:625-640 `enable_lora` items q, k, v, o) */
 #define JCB_PROJ_Q 0
@@ -225,9 +229,20 @@ typedef struct jcb_view_job {
 /* out_dev [n_jobs, 3, size, size] uint8 (planar, the layout jcb_encode_image / jcb_pipeline take with
  * JCB_IMG_U8).  images / jobs are host arrays; they are validated and copied.  When src_dev is 4-byte aligned the
  * source is read as whole aligned 32-bit words, so the buffer must be readable up to the next multiple of 4 bytes
- * past the last image (any cudaMalloc / torch allocation is); an unaligned src_dev takes a slower byte-wise path. */
-int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+ * past the last image (any cudaMalloc / torch allocation is); an unaligned src_dev takes a slower byte-wise path.
+ * cuda_stream: the stream to enqueue on (a cudaStream_t cast to void*), NULL = the context's stream.  The generator has
+ * its own scratch, so a batch may be generated on a second stream while the towers work on the previous one; the caller
+ * orders the streams (src_dev ready before, out_dev consumed after) with its own events. */
+int jcb_tta_views(jcb_ctx* ctx, void* cuda_stream, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
                   const jcb_view_job* jobs, int64_t n_jobs, int32_t size, uint8_t* out_dev);
+/* The same views, delivered as what the image tower's first GEMM reads: out_patches_dev [n_jobs * (size/patch)^2,
+ * 3 * patch^2] 16-bit of `operand_type`, row = (view, py, px), column = (c, i, j) (jclip/model.py:105-108 as im2col),
+ * value = round16(u8 / 255) or, with apply_clip_norm, round16((u8 / 255 - mean_c) / std_c) (test.py:1301) -- bit-identical
+ * to jcb_tta_views followed by jcb_im2col, without the uint8 view tensor or the im2col pass.  Feed it to
+ * jcb_encode_image / jcb_pipeline with img_dtype JCB_IMG_PATCHES_*. */
+int jcb_tta_patches(jcb_ctx* ctx, void* cuda_stream, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+                    const jcb_view_job* jobs, int64_t n_jobs, int32_t size, int32_t patch, int32_t apply_clip_norm,
+                    int32_t operand_type, void* out_patches_dev);
 
 /* ---------------------------------------------------------------- MTA ------------------------ */
 typedef struct jcb_mta_params {

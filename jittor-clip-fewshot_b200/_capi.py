@@ -17,7 +17,7 @@ JCB_OK = 0
 JCB_E_INVALID, JCB_E_CUDA, JCB_E_STATE, JCB_E_NO_DEVICE, JCB_E_KERNEL, JCB_E_NOMEM = -1, -2, -3, -4, -5, -6
 JCB_ABI_VERSION = 3
 MAX_INFLIGHT = 4   # JCB_MAX_INFLIGHT
-IMG_F32, IMG_BF16, IMG_U8 = 0, 1, 2
+IMG_F32, IMG_BF16, IMG_U8, IMG_PATCHES_BF16, IMG_PATCHES_F16 = 0, 1, 2, 3, 4
 PROJ_Q, PROJ_K, PROJ_V, PROJ_O = 0, 1, 2, 3
 SCORE_NAMES = ("logits", "cs", "cs1", "cs2", "cs3", "cs4", "cs5")
 SCORE_INDEX = {n: i for i, n in enumerate(SCORE_NAMES)}
@@ -121,8 +121,10 @@ PROTOTYPES = {
     "jcb_text_finalize": (c_int, [c_void_p]),
     "jcb_encode_text": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "jcb_class_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
-    "jcb_tta_views": (c_int, [c_void_p, c_void_p, POINTER(SrcImage), c_int32, POINTER(ViewJob), c_int64, c_int32,
+    "jcb_tta_views": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SrcImage), c_int32, POINTER(ViewJob), c_int64, c_int32,
                               c_void_p]),
+    "jcb_tta_patches": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(SrcImage), c_int32, POINTER(ViewJob), c_int64,
+                                c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "jcb_mta_default_params": (None, [POINTER(MtaParams)]),
     "jcb_mta": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, POINTER(MtaParams),
                         c_void_p, c_void_p]),

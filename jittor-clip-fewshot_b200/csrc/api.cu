@@ -55,7 +55,11 @@ struct jcb_ctx {
   cudaEvent_t ticket_done[JCB_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
   int* ticket_status = nullptr;      // pinned host, [JCB_MAX_INFLIGHT]: device status word copied behind each submission
   int64_t next_ticket = 0, waited_ticket = 0;
-  // jcb_tta_views: pinned, double-buffered staging of the per-view plan (no stream synchronisation in the call)
+  // jcb_tta_views / jcb_tta_patches: their own scratch (plan + horizontal-pass intermediate), so that a view batch can be
+  // generated on a second stream WHILE the towers use `ws` for the previous batch
+  void* tta_ws = nullptr;
+  size_t tta_ws_bytes = 0;
+  // pinned, double-buffered staging of the per-view plan (no stream synchronisation in the call)
   void* tta_plan_host[2] = {nullptr, nullptr};
   size_t tta_plan_bytes[2] = {0, 0};
   cudaEvent_t tta_plan_copied[2] = {nullptr, nullptr};
@@ -182,7 +186,8 @@ struct Bump {
   }
 };
 
-size_t img_elem_bytes(int dt) { return dt == JCB_IMG_F32 ? 4 : dt == JCB_IMG_BF16 ? 2 : 1; }
+size_t img_elem_bytes(int dt) { return dt == JCB_IMG_F32 ? 4 : dt == JCB_IMG_U8 ? 1 : 2; }
+bool is_patches(int dt) { return dt == JCB_IMG_PATCHES_BF16 || dt == JCB_IMG_PATCHES_F16; }
 
 }  // namespace
 
@@ -456,13 +461,16 @@ int tower_forward(jcb_vit* v, const void* images, int dt, int64_t n, int apply_n
   // conv1 as im2col + GEMM; epilogue scatters to token rows 1..T-1 and adds the positional embedding
   const double MW = static_cast<double>(M) * W;  // elements of one [tokens, width] tensor
   const double img_b = static_cast<double>(n) * 3 * v->cfg.resolution * v->cfg.resolution;
-  LAUNCH_P(ctx, JCB_KC_IM2COL, 0, img_b * img_elem_bytes(dt) + img_b * 2,
-           launch_im2col(images, dt, n, v->cfg.resolution, v->cfg.patch, apply_norm, w.big, s, v->f16));
+  // input already is the patch matrix (jcb_tta_patches: view generator fused with the front end): no im2col pass
+  const __nv_bfloat16* patches = is_patches(dt) ? static_cast<const __nv_bfloat16*>(images) : w.big;
+  if (!is_patches(dt))
+    LAUNCH_P(ctx, JCB_KC_IM2COL, 0, img_b * img_elem_bytes(dt) + img_b * 2,
+             launch_im2col(images, dt, n, v->cfg.resolution, v->cfg.patch, apply_norm, w.big, s, v->f16));
   // conv1 output as a dense [n * GG, W] fp32 matrix through the TMA-store epilogue, parked in the (not yet used)
   // QKV buffer; the embed kernel moves each row to its token slot while adding the positional embedding.  The
   // scatter epilogue (EPI_PATCH_F32: direct stores, one row per thread) ran the GEMM at 0.81-1.0 of the others' rate.
   float* patch_out = reinterpret_cast<float*>(w.qkv);
-  int rc = run_gemm(ctx, JCB_KC_GEMM_PATCH, v->f16, w.big, v->conv_w, static_cast<int>(n * GG), W, KP, nullptr, EPI_F32, patch_out, W);
+  int rc = run_gemm(ctx, JCB_KC_GEMM_PATCH, v->f16, patches, v->conv_w, static_cast<int>(n * GG), W, KP, nullptr, EPI_F32, patch_out, W);
   if (rc) return rc;
   // class token + positional embedding + ln_pre (residual stream) + layer 0's ln_1
   LAUNCH_P(ctx, JCB_KC_EMBED_LN, 0, MW * (4 + 4 + 2), launch_embed_ln(w.tokens, n, T, W, v->cls, v->pos, v->vpt, v->cfg.vpt_tokens, v->ln_pre_g, v->ln_pre_b, v->layers[0].ln1_g,
@@ -495,7 +503,13 @@ int check_vit(jcb_vit* v) {
 int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n, int apply_norm, int normalize,
                  float* out_dev, size_t ws_extra) {
   jcb_ctx* ctx = v->ctx;
-  if (dt < 0 || dt > 2) return fail(ctx, JCB_E_INVALID, "unknown image dtype %d", dt);
+  if (dt < 0 || dt > JCB_IMG_PATCHES_F16) return fail(ctx, JCB_E_INVALID, "unknown image dtype %d", dt);
+  if (is_patches(dt)) {
+    if (on_host) return fail(ctx, JCB_E_INVALID, "patch-matrix input must be device-resident");
+    if ((dt == JCB_IMG_PATCHES_F16) != (v->f16 != 0))
+      return fail(ctx, JCB_E_INVALID, "patch matrix is %s but the tower was packed with %s operands",
+                  dt == JCB_IMG_PATCHES_F16 ? "fp16" : "bf16", v->f16 ? "fp16" : "bf16");
+  }
   if (n < 0) return fail(ctx, JCB_E_INVALID, "negative view count");
   if (n == 0) return JCB_OK;
   if (!images || !out_dev) return fail(ctx, JCB_E_INVALID, "null image / output pointer");
@@ -506,6 +520,7 @@ int encode_views(jcb_vit* v, const void* images, int dt, bool on_host, int64_t n
   if (rc) return rc;
   Bump b(static_cast<uint8_t*>(ctx->ws) + ws_extra);
   TowerWs w = tower_ws_carve(v, chunk, b);
+  // bytes of one view: [3, R, R] pixels, or its G^2 rows of the patch matrix (the same 3 R^2 elements, 16-bit)
   const size_t view_bytes = static_cast<size_t>(3) * v->cfg.resolution * v->cfg.resolution * img_elem_bytes(dt);
   if (on_host && (rc = stage_reserve(ctx, chunk * view_bytes))) return rc;
   // Host input: the upload of pass i+1 overlaps the compute of pass i, but nothing hides the FIRST upload, so
@@ -610,6 +625,7 @@ int jcb_ctx_destroy(jcb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->tta_ws) cudaFree(ctx->tta_ws);
   for (int i = 0; i < 2; ++i) {
     if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
@@ -1139,28 +1155,55 @@ int jcb_vit_debug_tokens(jcb_vit* v, const void* images_dev, int img_dtype, int6
 }
 
 // ------------------------------------------------------------------------------------------------
-int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
-                  const jcb_view_job* jobs, int64_t n_jobs, int32_t size, uint8_t* out_dev) {
-  if (!ctx) return JCB_E_INVALID;
-  if (n_jobs < 0 || n_images < 0 || size < 8 || size > 1024) return fail(ctx, JCB_E_INVALID, "jcb_tta_views: bad sizes");
+namespace {
+// Grow-only scratch of the view generator.  Growth waits for the whole device (a view batch may be in flight on a
+// stream this context does not know); steady state never does.
+int tta_ws_reserve(jcb_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->tta_ws_bytes) return JCB_OK;
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  if (ctx->tta_ws) cudaFree(ctx->tta_ws);
+  ctx->tta_ws = nullptr;
+  ctx->tta_ws_bytes = 0;
+  cudaError_t e = cudaMalloc(&ctx->tta_ws, bytes);
+  if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for the view generator failed: %s", bytes, cudaGetErrorString(e));
+  ctx->tta_ws_bytes = bytes;
+  return JCB_OK;
+}
+
+int tta_run(jcb_ctx* ctx, cudaStream_t stream, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+            const jcb_view_job* jobs, int64_t n_jobs, int32_t size, int out_mode, int patch, int apply_norm, void* out_dev) {
+  if (n_jobs < 0 || n_images < 0 || size < 8 || size > 1024) return fail(ctx, JCB_E_INVALID, "jcb_tta: bad sizes");
   if (n_jobs == 0) return JCB_OK;
-  if (!src_dev || !images || !jobs || !out_dev) return fail(ctx, JCB_E_INVALID, "jcb_tta_views: null pointer");
+  if (!src_dev || !images || !jobs || !out_dev) return fail(ctx, JCB_E_INVALID, "jcb_tta: null pointer");
   static_assert(sizeof(jcb_src_image) == sizeof(TtaImage) && sizeof(jcb_view_job) == sizeof(TtaJob), "ABI structs");
   DeviceGuard g(ctx->device);
   const int64_t BATCH = 16384;   // views per launch pair (grid.y limit; bounds the intermediate scratch)
+  const size_t out_view_bytes = static_cast<size_t>(3) * size * size * (out_mode == 0 ? 1 : 2);
+  // one reservation for the whole call: a later batch must not move the scratch an earlier batch's kernels still use
+  std::vector<std::vector<uint8_t>> plans;
+  struct Meta { int kh, kv, mr; size_t tmp_bytes; };
+  std::vector<Meta> metas;
+  size_t need = 0;
   for (int64_t j0 = 0; j0 < n_jobs; j0 += BATCH) {
     const int64_t nj = std::min(BATCH, n_jobs - j0);
-    std::vector<uint8_t> plan;
-    int kh = 0, kv = 0, mr = 0;
+    plans.emplace_back();
+    Meta m{};
     const char* err = nullptr;
-    const size_t tmp_bytes = tta_plan(reinterpret_cast<const TtaImage*>(images), n_images,
-                                      reinterpret_cast<const TtaJob*>(jobs + j0), nj, size, &plan, &kh, &kv, &mr, &err);
-    if (tmp_bytes == SIZE_MAX) return fail(ctx, JCB_E_INVALID, "jcb_tta_views: %s", err ? err : "invalid job");
-    const size_t plan_b = align_up(plan.size());
-    int rc = ws_reserve(ctx, plan_b + tmp_bytes);
-    if (rc) return rc;
-    uint8_t* plan_dev = static_cast<uint8_t*>(ctx->ws);
-    uint8_t* tmp = plan_dev + plan_b;
+    m.tmp_bytes = tta_plan(reinterpret_cast<const TtaImage*>(images), n_images, reinterpret_cast<const TtaJob*>(jobs + j0), nj,
+                           size, &plans.back(), &m.kh, &m.kv, &m.mr, &err);
+    if (m.tmp_bytes == SIZE_MAX) return fail(ctx, JCB_E_INVALID, "jcb_tta: %s", err ? err : "invalid job");
+    need = std::max(need, align_up(plans.back().size()) + m.tmp_bytes);
+    metas.push_back(m);
+  }
+  int rc = tta_ws_reserve(ctx, need);
+  if (rc) return rc;
+  size_t bi = 0;
+  for (int64_t j0 = 0; j0 < n_jobs; j0 += BATCH, ++bi) {
+    const int64_t nj = std::min(BATCH, n_jobs - j0);
+    const std::vector<uint8_t>& plan = plans[bi];
+    const Meta& m = metas[bi];
+    uint8_t* plan_dev = static_cast<uint8_t*>(ctx->tta_ws);
+    uint8_t* tmp = plan_dev + align_up(plan.size());
     // the plan goes through one of two pinned buffers, so the call never waits for the stream: a buffer is reused only
     // after the upload that last read it has completed (its event; two calls back, normally long done)
     const int t = ctx->tta_turn;
@@ -1175,16 +1218,36 @@ int jcb_tta_views(jcb_ctx* ctx, const uint8_t* src_dev, const jcb_src_image* ima
       ctx->tta_plan_bytes[t] = plan.size();
     }
     memcpy(ctx->tta_plan_host[t], plan.data(), plan.size());
-    CUDA_TRY(ctx, cudaMemcpyAsync(plan_dev, ctx->tta_plan_host[t], plan.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaEventRecord(ctx->tta_plan_copied[t], ctx->stream));
-    double macs = 0;
-    for (int64_t i = 0; i < nj; ++i) macs += 3.0 * size * (jobs[j0 + i].crop_h + size);
-    LAUNCH_P(ctx, JCB_KC_TTA, 0, static_cast<double>(nj) * 3 * size * size,
-             launch_tta(src_dev, plan_dev, nj, size, kh, kv, mr, tmp, out_dev + j0 * 3LL * size * size, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(plan_dev, ctx->tta_plan_host[t], plan.size(), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->tta_plan_copied[t], stream));
+    void* out = static_cast<uint8_t*>(out_dev) + j0 * out_view_bytes;
+    if (stream == ctx->stream) {
+      LAUNCH_P(ctx, JCB_KC_TTA, 0, static_cast<double>(nj) * out_view_bytes,
+               launch_tta(src_dev, plan_dev, nj, size, m.kh, m.kv, m.mr, tmp, out, stream, out_mode, patch, apply_norm));
+    } else {   // a caller-chosen stream: the per-class event profile belongs to the context's stream
+      LAUNCH(ctx, launch_tta(src_dev, plan_dev, nj, size, m.kh, m.kv, m.mr, tmp, out, stream, out_mode, patch, apply_norm));
+    }
     ++ctx->launches;  // two kernels per call
-    (void)macs;
   }
   return JCB_OK;
+}
+}  // namespace
+
+int jcb_tta_views(jcb_ctx* ctx, void* cuda_stream, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+                  const jcb_view_job* jobs, int64_t n_jobs, int32_t size, uint8_t* out_dev) {
+  if (!ctx) return JCB_E_INVALID;
+  return tta_run(ctx, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream, src_dev, images, n_images, jobs,
+                 n_jobs, size, 0, 0, 0, out_dev);
+}
+
+int jcb_tta_patches(jcb_ctx* ctx, void* cuda_stream, const uint8_t* src_dev, const jcb_src_image* images, int32_t n_images,
+                    const jcb_view_job* jobs, int64_t n_jobs, int32_t size, int32_t patch, int32_t apply_clip_norm,
+                    int32_t operand_type, void* out_patches_dev) {
+  if (!ctx) return JCB_E_INVALID;
+  if (operand_type != JCB_OPERAND_BF16 && operand_type != JCB_OPERAND_F16) return fail(ctx, JCB_E_INVALID, "jcb_tta_patches: bad operand_type");
+  if (patch < 4 || patch % 4 != 0 || size % patch != 0) return fail(ctx, JCB_E_INVALID, "jcb_tta_patches: patch=%d must divide size=%d and be a multiple of 4", patch, size);
+  return tta_run(ctx, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream, src_dev, images, n_images, jobs,
+                 n_jobs, size, operand_type == JCB_OPERAND_F16 ? 2 : 1, patch, apply_clip_norm, out_patches_dev);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -185,7 +185,11 @@ struct TtaJob {              // == jcb_view_job
 // intermediate scratch the two passes need, or SIZE_MAX with *err set.
 size_t tta_plan(const TtaImage* images, int n_images, const TtaJob* jobs, int64_t n_jobs, int S,
                 std::vector<uint8_t>* plan_bytes, int* kmax_h, int* kmax_v, int* max_rows, const char** err);
+// out_mode 0: out = uint8 [n_jobs, 3, S, S] planar views.  out_mode 1 (bf16) / 2 (fp16): out = the views' rows of the
+// conv1 patch matrix [n_jobs * (S / patch)^2, 3 * patch^2] with ToTensor's 1/255 and (apply_norm) tfm_clip applied --
+// bit-identical to launch_im2col over the uint8 views.
 cudaError_t launch_tta(const uint8_t* src, const void* plan_dev, int64_t n_jobs, int S, int kmax_h, int kmax_v,
-                       int max_rows, uint8_t* tmp, uint8_t* out, cudaStream_t stream);
+                       int max_rows, uint8_t* tmp, void* out, cudaStream_t stream, int out_mode = 0, int patch = 0,
+                       int apply_norm = 0);
 
 }  // namespace jcb

@@ -14,7 +14,10 @@
 //   resample_h_kernel   one CTA = 128 intermediate rows x S columns of one view; weights for the S columns are
 //                       computed once per CTA in fp64 (explicitly rounded ops: no FMA contraction) into smem
 //   resample_v_kernel   one CTA = all S output rows x S columns of one view; reads the planar uint8 intermediate
-//                       coalesced, writes the planar [3, S, S] uint8 view (mirrored if asked)
+//                       coalesced, writes the planar [3, S, S] uint8 view (mirrored if asked) -- or, fused with the
+//                       tower's front end (OUT_PATCH_*), the view's rows of the conv1 patch matrix directly: ToTensor's
+//                       1/255, tfm_clip's (x - mean) / std (test.py:1301) and the im2col of jclip/model.py:105-108 applied
+//                       to the finished uint8 pixel, so the uint8 view tensor and the im2col pass over it disappear
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -82,6 +85,13 @@ __device__ __forceinline__ void axis_coeffs(const AxisDev& a, int kind, int X, i
   xmin = lo;
   n = cnt;
 }
+
+// where the vertical pass leaves a view
+enum TtaOut : int { OUT_U8 = 0, OUT_PATCH_BF16 = 1, OUT_PATCH_F16 = 2 };
+struct PatchEmit {        // OUT_PATCH_*: patch geometry and the per-channel affine map of the pixel (rowwise.cu im2col_kernel)
+  int P, Gp;              // patch edge, patches per row (S / P)
+  float a[3], b[3];       // pixel -> a[c] * u8 + b[c]
+};
 
 __device__ __forceinline__ uint32_t clip8(int v) {
   v >>= PREC;
@@ -204,10 +214,10 @@ resample_h_kernel(const uint8_t* __restrict__ src, const ViewDev* __restrict__ v
 // One thread = four adjacent output pixels of one channel: every tap is one aligned 32-bit load of the planar
 // intermediate (a warp reads 128 contiguous bytes), the four results leave as one 32-bit store (byte-reversed and
 // mirrored in x for a flipped view).  Needs S % 4 == 0 and 4-byte aligned buffers; otherwise the byte version runs.
-template <int KW>
+template <int KW, int OUT>
 __device__ __forceinline__ void v_rows_fast(const uint8_t* __restrict__ t, long long plane, const int* __restrict__ kk,
                                             int kmax, const int* __restrict__ ymin, const int* __restrict__ cnt, int S,
-                                            int y_begin, int rows, int flip, uint8_t* __restrict__ o) {
+                                            int y_begin, int rows, int flip, uint8_t* __restrict__ o, const PatchEmit& pe) {
   const int G = S >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const long long plane_w = plane >> 2;          // plane = n_rows * S, a multiple of 4
@@ -239,14 +249,29 @@ __device__ __forceinline__ void v_rows_fast(const uint8_t* __restrict__ t, long 
         r4 = __byte_perm(r4, 0u, 0x0123);
         go = G - 1 - g;
       }
-      reinterpret_cast<uint32_t*>(o + (static_cast<long long>(c) * S + y_begin + yy) * S)[go] = r4;
+      if (OUT == OUT_U8) {
+        reinterpret_cast<uint32_t*>(o + (static_cast<long long>(c) * S + y_begin + yy) * S)[go] = r4;
+      } else {
+        // the four pixels (x = 4 go .. 4 go + 3 of row y) are four consecutive columns of one patch row: one 8-byte store
+        const int y = y_begin + yy, x0 = 4 * go;
+        const long long prow = static_cast<long long>(y / pe.P) * pe.Gp + x0 / pe.P;
+        const int col = (c * pe.P + y % pe.P) * pe.P + x0 % pe.P;
+        const float pa = pe.a[c], pb = pe.b[c];
+        const float f0 = fmaf(static_cast<float>(r4 & 0xFFu), pa, pb), f1 = fmaf(static_cast<float>((r4 >> 8) & 0xFFu), pa, pb);
+        const float f2 = fmaf(static_cast<float>((r4 >> 16) & 0xFFu), pa, pb), f3 = fmaf(static_cast<float>(r4 >> 24), pa, pb);
+        uint2 h;
+        h.x = pack_h2<OUT == OUT_PATCH_F16>(f0, f1);
+        h.y = pack_h2<OUT == OUT_PATCH_F16>(f2, f3);
+        *reinterpret_cast<uint2*>(o + (prow * (3LL * pe.P * pe.P) + col) * 2) = h;
+      }
     }
   }
 }
 
+template <int OUT>
 __device__ __forceinline__ void v_rows_generic(const uint8_t* __restrict__ t, long long plane, const int* __restrict__ kk,
                                                int kmax, const int* __restrict__ ymin, const int* __restrict__ cnt, int S,
-                                               int y_begin, int rows, int flip, uint8_t* __restrict__ o) {
+                                               int y_begin, int rows, int flip, uint8_t* __restrict__ o, const PatchEmit& pe) {
   for (int p = threadIdx.x; p < rows * S; p += blockDim.x) {
     const int yy = p / S, xx = p % S;
     const int* k = kk + yy * kmax;
@@ -260,16 +285,27 @@ __device__ __forceinline__ void v_rows_generic(const uint8_t* __restrict__ t, lo
       a2 += static_cast<int>(s[2 * plane + static_cast<long long>(y) * S]) * w;
     }
     const int xo = flip ? S - 1 - xx : xx;
-    uint8_t* d = o + static_cast<long long>(y_begin + yy) * S + xo;
-    d[0] = static_cast<uint8_t>(clip8(a0));
-    d[static_cast<long long>(S) * S] = static_cast<uint8_t>(clip8(a1));
-    d[2LL * S * S] = static_cast<uint8_t>(clip8(a2));
+    if (OUT == OUT_U8) {
+      uint8_t* d = o + static_cast<long long>(y_begin + yy) * S + xo;
+      d[0] = static_cast<uint8_t>(clip8(a0));
+      d[static_cast<long long>(S) * S] = static_cast<uint8_t>(clip8(a1));
+      d[2LL * S * S] = static_cast<uint8_t>(clip8(a2));
+    } else {
+      const int y = y_begin + yy;
+      const long long prow = static_cast<long long>(y / pe.P) * pe.Gp + xo / pe.P;
+      uint16_t* d = reinterpret_cast<uint16_t*>(o) + prow * (3LL * pe.P * pe.P) + (y % pe.P) * pe.P + xo % pe.P;
+      const int acc[3] = {a0, a1, a2};
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        d[c * pe.P * pe.P] = to_h<OUT == OUT_PATCH_F16>(fmaf(static_cast<float>(clip8(acc[c])), pe.a[c], pe.b[c]));
+    }
   }
 }
 
+template <int OUT>
 __global__ void __launch_bounds__(256)
 resample_v_kernel(const uint8_t* __restrict__ tmp, const ViewDev* __restrict__ views, int S, int kmax,
-                  uint8_t* __restrict__ out, int words_ok) {
+                  uint8_t* __restrict__ out, int words_ok, const PatchEmit pe) {
   extern __shared__ __align__(16) int rs_smem[];
   const ViewDev v = views[blockIdx.y];
   const int y_begin = blockIdx.x * RBV;
@@ -287,14 +323,15 @@ resample_v_kernel(const uint8_t* __restrict__ tmp, const ViewDev* __restrict__ v
   __syncthreads();
   const long long plane = static_cast<long long>(v.n_rows) * S;
   const uint8_t* t = tmp + v.tmp_off;
-  uint8_t* o = out + static_cast<long long>(blockIdx.y) * 3 * S * S;
+  // a view = 3 S^2 bytes of planar uint8, or its Gp^2 rows of 3 P^2 16-bit patch columns (the same 3 S^2 elements)
+  uint8_t* o = out + static_cast<long long>(blockIdx.y) * 3 * S * S * (OUT == OUT_U8 ? 1 : 2);
   const int ks = words_ok ? v.v.ksize : 0;
   switch (ks) {
-    case 3: v_rows_fast<3>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
-    case 5: v_rows_fast<5>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
-    case 7: v_rows_fast<7>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
-    case 9: v_rows_fast<9>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o); break;
-    default: v_rows_generic(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o);
+    case 3: v_rows_fast<3, OUT>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o, pe); break;
+    case 5: v_rows_fast<5, OUT>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o, pe); break;
+    case 7: v_rows_fast<7, OUT>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o, pe); break;
+    case 9: v_rows_fast<9, OUT>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o, pe); break;
+    default: v_rows_generic<OUT>(t, plane, kk, kmax, ymin, cnt, S, y_begin, rows, v.flip, o, pe);
   }
 }
 
@@ -364,14 +401,30 @@ size_t tta_plan(const TtaImage* images, int n_images, const TtaJob* jobs, int64_
 }
 
 cudaError_t launch_tta(const uint8_t* src, const void* views_dev, int64_t n_jobs, int S, int kmax_h, int kmax_v,
-                       int max_rows, uint8_t* tmp, uint8_t* out, cudaStream_t stream) {
+                       int max_rows, uint8_t* tmp, void* out, cudaStream_t stream, int out_mode, int patch,
+                       int apply_norm) {
   if (n_jobs == 0) return cudaSuccess;
   const size_t smem_h = static_cast<size_t>(S) * (kmax_h + 2) * sizeof(int);
   const size_t smem_v = static_cast<size_t>(RBV) * (kmax_v + 2) * sizeof(int);
   if (smem_h > 200 * 1024 || smem_v > 200 * 1024 || n_jobs > 65535) return cudaErrorInvalidValue;
+  if (out_mode < OUT_U8 || out_mode > OUT_PATCH_F16) return cudaErrorInvalidValue;
+  PatchEmit pe{};
+  if (out_mode != OUT_U8) {
+    if (patch < 4 || patch % 4 != 0 || S % patch != 0) return cudaErrorInvalidValue;
+    pe.P = patch;
+    pe.Gp = S / patch;
+    // the same expressions as rowwise.cu im2col_kernel evaluates for uint8 input: bit-identical patches
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f}, std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    for (int c = 0; c < 3; ++c) {
+      pe.a[c] = apply_norm ? 1.0f / (255.0f * std[c]) : 1.0f / 255.0f;
+      pe.b[c] = apply_norm ? -mean[c] / std[c] : 0.0f;
+    }
+  }
   {
     cudaError_t e = ensure_dynamic_smem(resample_h_kernel, smem_h);
-    if (e == cudaSuccess) e = ensure_dynamic_smem(resample_v_kernel, smem_v);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(resample_v_kernel<OUT_U8>, smem_v);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(resample_v_kernel<OUT_PATCH_BF16>, smem_v);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(resample_v_kernel<OUT_PATCH_F16>, smem_v);
     if (e != cudaSuccess) return e;
   }
   const ViewDev* views = static_cast<const ViewDev*>(views_dev);
@@ -384,8 +437,11 @@ cudaError_t launch_tta(const uint8_t* src, const void* views_dev, int64_t n_jobs
   if (e != cudaSuccess) return e;
   dim3 gv(static_cast<unsigned>((S + RBV - 1) / RBV), static_cast<unsigned>(n_jobs));
   // word-wide vertical pass: rows of the intermediate start on 4-byte boundaries (tmp_off is 256-byte aligned)
-  const int words_ok = S % 4 == 0 && (reinterpret_cast<uintptr_t>(tmp) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
-  resample_v_kernel<<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, out, words_ok);
+  const int words_ok = S % 4 == 0 && (reinterpret_cast<uintptr_t>(tmp) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+  uint8_t* o = static_cast<uint8_t*>(out);
+  if (out_mode == OUT_U8) resample_v_kernel<OUT_U8><<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, o, words_ok, pe);
+  else if (out_mode == OUT_PATCH_BF16) resample_v_kernel<OUT_PATCH_BF16><<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, o, words_ok, pe);
+  else resample_v_kernel<OUT_PATCH_F16><<<gv, 256, smem_v, stream>>>(tmp, views, S, kmax_v, o, words_ok, pe);
   return cudaGetLastError();
 }
 

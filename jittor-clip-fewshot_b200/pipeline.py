@@ -53,6 +53,16 @@ class HotPath:
         self.text, self.lp = text_bank, channel_lp
         self.rank_by, self.k, self.apply_clip_norm = rank_by, k, apply_clip_norm
 
+    @staticmethod
+    def _check_input(images):
+        """[I, V, 3, R, R] pixels (float32 / bfloat16 / uint8, device or pinned host) or the device-resident patch matrix
+        [I, V, patches, 3 * P * P] of TTAViews(emit="patches")."""
+        t = as_torch(images)
+        is_patches = t.dim() == 4 and t.dtype in (torch.float16, torch.bfloat16) and t.is_cuda
+        if t.dim() != 5 and not is_patches:
+            raise ValueError(f"expected images [I, V, 3, R, R] (or a device patch matrix [I, V, patches, 3 P P]), got {tuple(t.shape)}")
+        return t.contiguous()
+
     def _args(self, images, I, V, on_host, out_topk, out_feats, out_scores, device):
         a = _capi.PipelineArgs()
         a.images = images.data_ptr()
@@ -77,10 +87,7 @@ class HotPath:
         """images [I, V, 3, R, R] (V = N+1 views, view 0 un-augmented; reference test.py:1700), float32 /
         bfloat16 / uint8, on the device or in (pinned) host memory.  Returns int32 top-k [I, k] -- on the
         host when the images were on the host (the end-to-end call), else on the device."""
-        t = as_torch(images)
-        if t.dim() != 5:
-            raise ValueError(f"expected images [I, V, 3, R, R], got {tuple(t.shape)}")
-        t = t.contiguous()
+        t = self._check_input(images)
         I, V = t.shape[0], t.shape[1]
         on_host = not t.is_cuda
         device = self.text.device
@@ -109,10 +116,7 @@ class HotPath:
         """Enqueue evaluate_base(images) without waiting and return a ticket for `collect`.  `images` as in
         evaluate_base; host images must be page-locked (pin_memory) for the copies to overlap compute and
         must not be modified until `collect` returns."""
-        t = as_torch(images)
-        if t.dim() != 5:
-            raise ValueError(f"expected images [I, V, 3, R, R], got {tuple(t.shape)}")
-        t = t.contiguous()
+        t = self._check_input(images)
         I, V = t.shape[0], t.shape[1]
         device = self.text.device
         with torch.cuda.device(device):
@@ -143,6 +147,43 @@ class HotPath:
                 yield self.collect(pending.pop(0))
         while pending:
             yield self.collect(pending.pop(0))
+
+    def evaluate_image_stream(self, image_batches, tta):
+        """The reference's test loop from DECODED images (`for images in loader`, test.py:1692, with JtDataset building the
+        1 + N views per image, :1547-1560): `image_batches` yields lists of [H, W, 3] uint8 arrays, `tta` is a TTAViews.
+        Yields the host top-k of each batch in order.  Software pipeline, two batches in flight: while the towers work on
+        batch k on the current stream, batch k + 1 is packed on the host, uploaded and turned into views (or patches) on a
+        second stream -- the generator has its own scratch in the library, and its integer work shares the SMs with the
+        tensor-core kernels (a GEMM CTA leaves ~27 KB of shared memory and most issue slots free)."""
+        device = self.text.device
+        with torch.cuda.device(device):
+            ctx, _ = self.model.visual._engine(device)
+            main = torch.cuda.current_stream(device)
+            side = getattr(self, "_tta_stream", None)
+            if side is None:
+                side = self._tta_stream = torch.cuda.Stream(device)
+            bufs, produced, consumed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+            pending = None
+            for k, imgs in enumerate(image_batches):
+                b = k & 1
+                shape, dtype = tta.out_shape_dtype(len(imgs), ctx)
+                n = 1
+                for d in shape:
+                    n *= d
+                if bufs[b] is None or bufs[b].numel() < n or bufs[b].dtype != dtype:
+                    bufs[b] = torch.empty(n, dtype=dtype, device=device)
+                if consumed[b] is not None:
+                    side.wait_event(consumed[b])            # the towers have read what this buffer held two batches ago
+                views = tta(imgs, out=bufs[b][:n], stream=side)
+                produced[b].record(side)
+                if pending is not None:
+                    yield self.collect(pending)             # host waits for batch k - 1 while batch k's views are generated
+                main.wait_event(produced[b])
+                pending = self.submit(views.view(shape))
+                consumed[b] = torch.cuda.Event()
+                consumed[b].record(main)
+            if pending is not None:
+                yield self.collect(pending)
 
     def evaluate_new(self, images, text_zs=None):
         """evaluate_new (test.py:1759-1779): zero-shot tower -> solve_mta -> 100 f T^T -> top-5."""

@@ -118,6 +118,10 @@ _IMG_DTYPES = {torch.float32: _capi.IMG_F32, torch.bfloat16: _capi.IMG_BF16, tor
 
 
 def img_dtype_code(t):
+    """JCB_IMG_* of an image tensor [..., 3, R, R] -- or, for a 16-bit tensor whose last two dims are NOT a square image
+    ([..., patches, 3 * P * P]: the patch matrix TTAViews(emit="patches") writes), JCB_IMG_PATCHES_*."""
+    if t.dim() >= 3 and t.shape[-1] != t.shape[-2] and t.dtype in (torch.float16, torch.bfloat16):
+        return _capi.IMG_PATCHES_F16 if t.dtype == torch.float16 else _capi.IMG_PATCHES_BF16
     try:
         return _IMG_DTYPES[t.dtype]
     except KeyError:

@@ -96,10 +96,18 @@ def random_resized_crop_params_batch(rng, W, H, n, scale=(0.5, 1.0), ratio=(3.0 
 
 class TTAViews:
     """images (list of [H, W, 3] uint8 arrays, any sizes) -> torch.uint8 [I, 1 + n_crops, 3, size, size] on the GPU;
-    view 0 is the centre view (reference test.py:1700 concatenates it first)."""
+    view 0 is the centre view (reference test.py:1700 concatenates it first).
+
+    emit="patches": the same views delivered as the conv1 patch matrix [I, 1 + n_crops, (size/patch)^2, 3 * patch^2] in
+    the context's 16-bit operand type (jcb_tta_patches: ToTensor, tfm_clip and the im2col of jclip/model.py:105-108
+    fused into the resampler's last pass; bit-identical to the views + the tower's own front end).  `HotPath.evaluate_base`
+    takes either form."""
 
     def __init__(self, n_crops=64, scale=(0.5, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), size=224, resize=256, flip_p=0.5,
-                 seed=0, device=None):
+                 seed=0, device=None, emit="views", patch=32, apply_clip_norm=True):
+        if emit not in ("views", "patches"):
+            raise ValueError(f"emit must be 'views' or 'patches', got {emit!r}")
+        self.emit, self.patch, self.apply_clip_norm = emit, patch, apply_clip_norm
         self.n_crops, self.scale, self.ratio = n_crops, scale, ratio
         self.size, self.resize, self.flip_p = size, resize, flip_p
         self.rng = np.random.default_rng(seed)
@@ -152,7 +160,16 @@ class TTAViews:
                 c["flip"] = self.rng.random(self.n_crops) < self.flip_p
         return jobs
 
-    def __call__(self, images, jobs=None):
+    def out_shape_dtype(self, n_images, ctx):
+        V, S = 1 + self.n_crops, self.size
+        if self.emit == "patches":
+            return (n_images, V, (S // self.patch) ** 2, 3 * self.patch * self.patch), ctx.operand_torch_dtype
+        return (n_images, V, 3, S, S), torch.uint8
+
+    def __call__(self, images, jobs=None, out=None, stream=None):
+        """out: an existing device tensor of out_shape_dtype() to write into (double buffering by the caller);
+        stream: a torch.cuda.Stream to upload and generate on instead of the current one (the caller orders it against
+        the consumer with events; HotPath.evaluate_image_stream does)."""
         imgs = [np.ascontiguousarray(np.asarray(im), dtype=np.uint8) for im in images]
         for im in imgs:
             if im.ndim != 3 or im.shape[2] != 3:
@@ -189,17 +206,33 @@ class TTAViews:
         hv = host.numpy()
         for d, im in zip(descs, imgs):
             hv[d.offset:d.offset + im.size] = im.reshape(-1)
-        with torch.cuda.device(dev):
-            ctx.bind_current_stream()
+        S = self.size
+        patches = self.emit == "patches"
+        per_view = ((S // self.patch) ** 2, 3 * self.patch * self.patch) if patches else (3, S, S)
+        with torch.cuda.device(dev), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(dev)):
+            cur = torch.cuda.current_stream(dev)
+            if stream is None:
+                ctx.bind_current_stream()
             src = host.to(dev, non_blocking=True)
             self._copied[t] = torch.cuda.Event()
-            self._copied[t].record()
-            out = torch.empty((n_jobs, 3, self.size, self.size), dtype=torch.uint8, device=dev)
-            check(ctx.lib.jcb_tta_views(ctx.handle, ptr(src), descs, len(imgs), jobs_ptr, n_jobs, self.size, ptr(out)),
-                  ctx.handle)
+            self._copied[t].record(cur)
+            dtype = ctx.operand_torch_dtype if patches else torch.uint8
+            want = n_jobs * int(np.prod(per_view))
+            if out is None:
+                out = torch.empty((n_jobs,) + per_view, dtype=dtype, device=dev)
+            elif out.numel() != want or out.dtype != dtype or not out.is_cuda or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous {dtype} device tensor of {want} elements ({n_jobs} views of {per_view})")
+            sp = ctypes.c_void_p(cur.cuda_stream)
+            if patches:
+                check(ctx.lib.jcb_tta_patches(ctx.handle, sp, ptr(src), descs, len(imgs), jobs_ptr, n_jobs, S, self.patch,
+                                              int(self.apply_clip_norm),
+                                              _capi.OPERAND_F16 if dtype == torch.float16 else _capi.OPERAND_BF16, ptr(out)),
+                      ctx.handle)
+            else:
+                check(ctx.lib.jcb_tta_views(ctx.handle, sp, ptr(src), descs, len(imgs), jobs_ptr, n_jobs, S, ptr(out)), ctx.handle)
         if len(imgs) and n_jobs % len(imgs) == 0:
-            return out.view(len(imgs), n_jobs // len(imgs), 3, self.size, self.size)
-        return out
+            return out.view((len(imgs), n_jobs // len(imgs)) + per_view)
+        return out.view((n_jobs,) + per_view)
 
 
 def jobs_to_tuples(jobs):

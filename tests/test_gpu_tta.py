@@ -1,6 +1,8 @@
 """GPU parity of the TTA view generator (jcb_tta_views) against Pillow itself, BIT FOR BIT on uint8:
 centre view = Resize(256, BICUBIC) + CenterCrop(224) (jclip/clip.py:130-135), crops = RandomResizedCrop
 (BILINEAR) + RandomHorizontalFlip (test.py:1898-1903)."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -90,7 +92,7 @@ def test_byte_paths_unaligned_source_and_odd_size(jb, cuda_dev):
         out = torch.empty((len(boxes), 3, size, size), dtype=torch.uint8, device=cuda_dev)
         with torch.cuda.device(cuda_dev):
             ctx.bind_current_stream()
-            check(ctx.lib.jcb_tta_views(ctx.handle, ctypes.c_void_p(buf.data_ptr() + shift), desc, 1, jobs, len(boxes), size,
+            check(ctx.lib.jcb_tta_views(ctx.handle, None, ctypes.c_void_p(buf.data_ptr() + shift), desc, 1, jobs, len(boxes), size,
                                         ctypes.c_void_p(out.data_ptr())), ctx.handle)
         got = out.cpu().numpy()
         for k, (t, l, h, w, f) in enumerate(boxes):
@@ -127,3 +129,76 @@ def test_views_feed_the_hot_path(jb, cuda_dev):
     a = hp.evaluate_base(views)
     b = hp.evaluate_base(torch.from_numpy(ref.astype(np.float32) / 255.0).to(cuda_dev))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("op", ["f16", "bf16"])
+@pytest.mark.parametrize("norm", [True, False])
+def test_fused_patches_equal_views_plus_im2col(jb, cuda_dev, op, norm):
+    """jcb_tta_patches (resampler's last pass writes the conv1 patch matrix: ToTensor, tfm_clip, im2col fused) is
+    bit-identical to jcb_tta_views (Pillow-exact uint8) followed by jcb_im2col -- word-wide and byte-wise bodies,
+    bicubic centre view, flipped and unflipped bilinear crops, image sizes that are not multiples of four."""
+    rng = np.random.default_rng(11)
+    imgs = [_img(rng, 300, 400), _img(rng, 421, 383), _img(rng, 257, 999)]
+    ctx = jb.get_context(cuda_dev)
+    prev = ctx.operand_type
+    try:
+        ctx.set_operand_type(op)
+        dt = ctx.operand_torch_dtype
+        gv = jb.TTAViews(n_crops=9, seed=5)
+        jobs = gv.draw_jobs_fast([im.shape[:2] for im in imgs])
+        views = gv(imgs, jobs=jobs)                                            # [3, 10, 3, 224, 224] uint8
+        want = torch.empty(30 * 49, 3072, dtype=dt, device=cuda_dev)
+        jb.blocks.im2col(views.view(30, 3, 224, 224), 224, 32, norm, want)
+        gp = jb.TTAViews(n_crops=9, seed=5, emit="patches", apply_clip_norm=norm)
+        got = gp(imgs, jobs=jobs)
+        assert got.shape == (3, 10, 49, 3072) and got.dtype == dt
+        assert torch.equal(got.view(30 * 49, 3072), want)
+        # the byte-wise bodies: an unaligned source buffer
+        from jclip_b200._capi import check
+        im = imgs[1]
+        buf = torch.zeros(im.size + 64, dtype=torch.uint8, device=cuda_dev)
+        buf[1:1 + im.size] = torch.from_numpy(im.reshape(-1)).to(cuda_dev)
+        desc = (jb._capi.SrcImage * 1)()
+        desc[0].offset, desc[0].height, desc[0].width = 0, im.shape[0], im.shape[1]
+        j1 = np.ascontiguousarray(jobs[10:20].copy())
+        j1["image"] = 0
+        out_b = torch.empty(10 * 49, 3072, dtype=dt, device=cuda_dev)
+        check(ctx.lib.jcb_tta_patches(ctx.handle, None, ctypes.c_void_p(buf.data_ptr() + 1), desc, 1,
+                                      j1.ctypes.data_as(ctypes.POINTER(jb._capi.ViewJob)), 10, 224, 32, int(norm),
+                                      jb._capi.OPERAND_NAMES[op], ctypes.c_void_p(out_b.data_ptr())), ctx.handle)
+        ctx.sync()
+        assert torch.equal(out_b, want[10 * 49:20 * 49])
+    finally:
+        ctx.set_operand_type(prev)
+
+
+def test_patches_feed_the_hot_path_and_image_stream(jb, cuda_dev):
+    """HotPath.evaluate_base(patches) == evaluate_base(views), bit for bit, and HotPath.evaluate_image_stream (views or
+    patches generated on a second stream while the towers run the previous batch) returns the same top-k per batch."""
+    rng = np.random.default_rng(4)
+    batches = [[_img(rng, 300 + 7 * i, 400 - 5 * i) for i in range(n)] for n in (3, 2, 4, 1, 3)]
+    sd = jb.synth.make_vit_state_dict(seed=4, layers=2)
+    model = jb.jclip.build_model(sd)
+    Ts = [torch.from_numpy(jb.synth.make_text_features(seed=10 + i)) for i in range(3)]
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = jb.synth.make_head(2, Ts[2].numpy())
+    hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by="cs5")
+    want = []
+    for emit in ("views", "patches"):
+        gen = jb.TTAViews(n_crops=6, seed=2, emit=emit)
+        got = [hp.evaluate_base(gen(b)).cpu() for b in batches]
+        if not want:
+            want = got
+        assert all(torch.equal(g, w) for g, w in zip(got, want)), emit
+        gen = jb.TTAViews(n_crops=6, seed=2, emit=emit)                  # same seed -> same boxes
+        streamed = list(hp.evaluate_image_stream(iter(batches), gen))
+        assert len(streamed) == len(want)
+        assert all(torch.equal(g, w) for g, w in zip(streamed, want)), emit
+    # a patch matrix of the wrong operand type is refused
+    ctx = jb.get_context(cuda_dev)
+    other = "bf16" if ctx.operand_type == "f16" else "f16"
+    p = jb.TTAViews(n_crops=1, seed=0, emit="patches")(batches[0])
+    wrong = p.to(torch.bfloat16 if p.dtype == torch.float16 else torch.float16)
+    with pytest.raises(jb.JcbError):
+        hp.evaluate_base(wrong)
+    assert other
