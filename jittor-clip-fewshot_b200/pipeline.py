@@ -176,12 +176,13 @@ class HotPath:
                     side.wait_event(consumed[b])            # the towers have read what this buffer held two batches ago
                 views = tta(imgs, out=bufs[b][:n], stream=side)
                 produced[b].record(side)
-                if pending is not None:
-                    yield self.collect(pending)             # host waits for batch k - 1 while batch k's views are generated
                 main.wait_event(produced[b])
-                pending = self.submit(views.view(shape))
+                ticket = self.submit(views.view(shape))     # queued BEHIND batch k - 1: the current stream never drains
                 consumed[b] = torch.cuda.Event()
                 consumed[b].record(main)
+                if pending is not None:
+                    yield self.collect(pending)             # returns when batch k - 1 is done, i.e. as batch k starts: the
+                pending = ticket                            # host then packs batch k + 1 while the GPU runs batch k
             if pending is not None:
                 yield self.collect(pending)
 
