@@ -417,15 +417,22 @@ def main():
         src = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I_r)]
         gen = jb.TTAViews(n_crops=args.crops, scale=(0.5, 1.0), seed=rank, emit="patches")
 
-        def run_images(steps):
-            # HotPath.evaluate_image_stream: while the towers work on batch k (current stream), the host draws the boxes
-            # of batch k+1, packs its images into the other pinned buffer, and upload + view generation run on a second
-            # stream; the generator writes the conv1 patch matrix directly (emit="patches": no uint8 views, no im2col)
+        def run_images(steps, overlap=True):
+            # HotPath.evaluate_image_stream: while the towers work on batch k, the host draws the boxes of batch k+1, packs
+            # its images into the other pinned buffer, and upload + view generation are enqueued (overlap: on a second,
+            # low-priority stream); the generator writes the conv1 patch matrix directly (no uint8 views, no im2col)
             topk = None
-            for topk in hp.evaluate_image_stream((src for _ in range(steps)), gen):
+            for topk in hp.evaluate_image_stream((src for _ in range(steps)), gen, overlap=overlap):
                 pass
             return topk
 
+        run_images(2, overlap=False)
+        jb.dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_images(K, overlap=False)
+        torch.cuda.synchronize()
+        dt_serial = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
         run_images(2)
         jb.dist.barrier()
         torch.cuda.synchronize()
@@ -436,6 +443,8 @@ def main():
         e2e_img = {"value": n_total * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K,
                    "h2d_bytes_per_step": int(sum(a.size for a in src)), "d2h_bytes_per_step": int(I_r * 5 * 4),
                    "api": "HotPath.evaluate_image_stream(batches of decoded images, TTAViews(emit='patches')): two batches in flight",
+                   "in_stream_order": {"value": n_total * K / dt_serial, "ms_per_step": 1e3 * dt_serial / K,
+                                       "api": "the same with overlap=False: view generation in stream order in front of the towers"},
                    "note": "host: 500x375 uint8 decoded images + crop-box draw; device: Pillow-exact centre view + "
                            f"{args.crops} RandomResizedCrop(0.5-1)+flip views per image written straight into the conv1 patch "
                            "matrix on a second stream while the previous batch's towers run, then the hot path"}

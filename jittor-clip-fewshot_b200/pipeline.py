@@ -148,20 +148,27 @@ class HotPath:
         while pending:
             yield self.collect(pending.pop(0))
 
-    def evaluate_image_stream(self, image_batches, tta):
+    def evaluate_image_stream(self, image_batches, tta, overlap=True):
         """The reference's test loop from DECODED images (`for images in loader`, test.py:1692, with JtDataset building the
         1 + N views per image, :1547-1560): `image_batches` yields lists of [H, W, 3] uint8 arrays, `tta` is a TTAViews.
         Yields the host top-k of each batch in order.  Software pipeline, two batches in flight: while the towers work on
-        batch k on the current stream, batch k + 1 is packed on the host, uploaded and turned into views (or patches) on a
-        second stream -- the generator has its own scratch in the library, and its integer work shares the SMs with the
-        tensor-core kernels (a GEMM CTA leaves ~27 KB of shared memory and most issue slots free)."""
+        batch k, the host packs batch k + 1 and enqueues its upload and view generation.
+
+        overlap=True: the generator runs on a second, LOW-priority stream and the towers on a high-priority one, so its
+        integer work fills the issue slots the tensor-core kernels leave free (the generator has its own scratch in the
+        library) without delaying the persistent GEMM grids at kernel boundaries.  overlap=False: everything in stream
+        order on the current stream."""
         device = self.text.device
         with torch.cuda.device(device):
             ctx, _ = self.model.visual._engine(device)
-            main = torch.cuda.current_stream(device)
-            side = getattr(self, "_tta_stream", None)
-            if side is None:
-                side = self._tta_stream = torch.cuda.Stream(device)
+            if overlap:
+                if getattr(self, "_streams", None) is None:
+                    lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+                    self._streams = (torch.cuda.Stream(device, priority=hi), torch.cuda.Stream(device, priority=lo))
+                main, side = self._streams
+                main.wait_stream(torch.cuda.current_stream(device))   # weights / text banks prepared by the caller's stream
+            else:
+                main = side = torch.cuda.current_stream(device)
             bufs, produced, consumed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
             pending = None
             for k, imgs in enumerate(image_batches):
@@ -172,14 +179,18 @@ class HotPath:
                     n *= d
                 if bufs[b] is None or bufs[b].numel() < n or bufs[b].dtype != dtype:
                     bufs[b] = torch.empty(n, dtype=dtype, device=device)
-                if consumed[b] is not None:
+                    main.wait_stream(torch.cuda.current_stream(device))
+                if overlap and consumed[b] is not None:
                     side.wait_event(consumed[b])            # the towers have read what this buffer held two batches ago
-                views = tta(imgs, out=bufs[b][:n], stream=side)
-                produced[b].record(side)
-                main.wait_event(produced[b])
-                ticket = self.submit(views.view(shape))     # queued BEHIND batch k - 1: the current stream never drains
-                consumed[b] = torch.cuda.Event()
-                consumed[b].record(main)
+                views = tta(imgs, out=bufs[b][:n], stream=side if overlap else None)
+                with torch.cuda.stream(main):
+                    if overlap:
+                        produced[b].record(side)
+                        main.wait_event(produced[b])
+                    ticket = self.submit(views.view(shape))     # queued BEHIND batch k - 1: the tower stream never drains
+                    if overlap:
+                        consumed[b] = torch.cuda.Event()
+                        consumed[b].record(main)
                 if pending is not None:
                     yield self.collect(pending)             # returns when batch k - 1 is done, i.e. as batch k starts: the
                 pending = ticket                            # host then packs batch k + 1 while the GPU runs batch k
