@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--host-chunk-views", type=int, default=0, help="views per pass when the input is in host memory")
     ap.add_argument("--no-balance", action="store_true",
                     help="N > 1: keep equal shards instead of sizing them by each rank's measured speed")
+    ap.add_argument("--rebalance-every", type=int, default=5,
+                    help="N > 1: every R timed steps the ranks exchange their step times and re-split the NEXT steps' global "
+                         "batch by measured speed (no image moves); 0 = keep the calibrated split")
     ap.add_argument("--gather-every", type=int, default=0,
                     help="N > 1: all-gather the top-5 every G steps (1 = every step); 0 = once, at the end of the timed steps")
     ap.add_argument("--operands", default="f16", choices=["f16", "bf16"],
@@ -207,6 +210,7 @@ def main():
         raise SystemExit("bench.py needs a B200 GPU: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = jb.dist.bind_to_gpu_numa(local)     # before any pinned allocation
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     peaks = measured_peaks()
@@ -237,7 +241,11 @@ def main():
 
     n_total = I * world                      # the step's global batch: fixed, I images per GPU on average
     sizes = [I] * world
-    images = make_images(I)
+    # N > 1: every rank keeps a pool of I_max images and works on a prefix of it, so that the split of the global batch
+    # can follow the ranks' speeds without generating or moving an image
+    I_max = I if world == 1 else int(I * 1.15) + 2
+    pool = make_images(I_max)
+    images = pool[:I]
     balance = None
     if world > 1 and not args.no_balance:
         # The GPUs of one box differ by a few per cent under the power cap, and every step ends in an all-gather: with
@@ -260,9 +268,9 @@ def main():
             ms_all = jb.dist.all_gather_floats(c0.elapsed_time(c1) / 5, dev)
             rounds.append({"shard_images": list(sizes), "ms_per_step_by_rank": [round(m, 2) for m in ms_all]})
             new_sizes = jb.dist.balanced_shard_sizes(n_total, [m / max(n, 1) for m, n in zip(ms_all, sizes)])
-            if new_sizes[rank] != sizes[rank]:
-                images = make_images(new_sizes[rank])
-            sizes = new_sizes
+            if max(new_sizes) <= I_max:
+                sizes = new_sizes
+                images = pool[:sizes[rank]]
         balance = {"calibration": rounds, "shard_images": sizes}
     I_r = sizes[rank]
     lo_r = sum(sizes[:rank])
@@ -274,15 +282,16 @@ def main():
     # in lockstep, and the timed region ends only when every gather has completed.
     G = max(args.gather_every, 0)
     gather = jb.dist.AsyncTopkGather(n_total, 5, dev, sizes=sizes, depth=4)
-    gather_all = jb.dist.AsyncTopkGather(n_total * K, 5, dev, sizes=[x * K for x in sizes], depth=1) if G != 1 else None
-    kept = torch.empty((K, I_r, 5), dtype=torch.int32, device=dev)
+    # every rank's [K, I_max, 5] block (rows beyond a step's shard size are padding), gathered as one tensor
+    gather_all = jb.dist.AsyncTopkGather(world * K * I_max, 5, dev, sizes=[K * I_max] * world, depth=1) if G != 1 else None
+    kept = torch.zeros((K, I_max, 5), dtype=torch.int32, device=dev)
     step_no = [0]
 
     def step_device():
         topk = hp.evaluate_base(images, topk_to_host=False)
         if G == 1:
             return gather.submit(topk)
-        kept[step_no[0] % K].copy_(topk, non_blocking=True)
+        kept[step_no[0] % K, :topk.shape[0]].copy_(topk, non_blocking=True)
         step_no[0] += 1
         return topk
 
@@ -290,8 +299,41 @@ def main():
         """Inside the timed region, after the K steps: every rank's predictions of all K steps on every rank."""
         if G == 1:
             gather.drain()
-        else:
-            gather_all.result(gather_all.submit(kept.view(K * I_r, 5)))
+            return None
+        return gather_all.result(gather_all.submit(kept.view(K * I_max, 5)))
+
+    # The main timed region with shards that FOLLOW the ranks' speeds (N > 1, --rebalance-every R > 0): the calibrated split
+    # is static, but a GPU under the power cap drifts by a few per cent within seconds.  Every R steps each rank measures its
+    # last R steps with CUDA events, the per-image times are exchanged (one all-gather of a float) and the NEXT steps' global
+    # batch is re-split in proportion to speed (exponentially smoothed).  No image moves: a rank just evaluates a longer
+    # or shorter prefix of its pool.  The step's global batch (n_total images) never changes.
+    R = max(args.rebalance_every, 0) if (world > 1 and G != 1 and not args.no_balance) else 0
+    split_history = []
+
+    def timed_steps():
+        cur = list(sizes)
+        t_img = None
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        done_in_window = 0
+        for k in range(K):
+            if R and k > 0 and k % R == 0:
+                w1.record()
+                w1.synchronize()
+                mine = w0.elapsed_time(w1) / max(done_in_window, 1)
+                per = jb.dist.all_gather_floats(mine, dev)
+                t_img = per if t_img is None else [0.5 * a + 0.5 * b for a, b in zip(t_img, per)]
+                new = jb.dist.balanced_shard_sizes(n_total, t_img)
+                if max(new) <= I_max:
+                    cur = new
+                w0.record()
+                done_in_window = 0
+            n = cur[rank]
+            topk = hp.evaluate_base(pool[:n], topk_to_host=False)
+            kept[k, :n].copy_(topk, non_blocking=True)
+            done_in_window += n
+            split_history.append(list(cur))
+        return finish_steps()
 
     for _ in range(max(W, 1)):
         r = step_device()
@@ -304,9 +346,9 @@ def main():
     if world > 1:
         other = (rank + 1) % world
         lo_o = sum(sizes[:other])
-        im_o = jb.synth.make_views_torch(1000 + other, sizes[other], V, dev)
+        im_o = jb.synth.make_views_torch(1000 + other, I_max, V, dev)[:sizes[other]]       # that rank's pool prefix
         im_o = (im_o * 255.0).round_().to(torch.uint8) if args.img_dtype == "u8" else im_o
-        mine = hp.evaluate_base(im_o, topk_to_host=False)
+        mine = hp.evaluate_base(im_o.contiguous(), topk_to_host=False)
         same = bool(torch.equal(mine, out[lo_o:lo_o + sizes[other]]))
         del im_o
         oks = jb.dist.all_gather_floats(1.0 if same else 0.0, dev)
@@ -323,13 +365,27 @@ def main():
     ctx.profile_start()
     ev0.record()
     step_no[0] = 0
-    for _ in range(K):
-        step_device()
-    finish_steps()
+    if R:
+        all_kept = timed_steps()
+    else:
+        for _ in range(K):
+            step_device()
+        all_kept = finish_steps()
     ev1.record()
     torch.cuda.synchronize()
     jb.dist.barrier()
     prof = ctx.profile_stop()
+    if R and all_kept is not None:
+        # the gathered block of rank r, step k holds that step's shard of rank r in rows [0, split[k][r]): every step's
+        # predictions cover the whole global batch exactly once
+        blk = all_kept.view(world, K, I_max, 5)
+        for k in (0, K - 1):
+            rows = torch.cat([blk[r, k, :split_history[k][r]] for r in range(world)])
+            assert rows.shape == (n_total, 5) and sum(split_history[k]) == n_total
+        # step 0 used the calibrated split: its rows equal the warm-up step's gathered predictions
+        assert torch.equal(torch.cat([blk[r, 0, :split_history[0][r]] for r in range(world)]), out)
+        balance["rebalance"] = {"every_steps": R, "splits": [split_history[k] for k in range(0, K, R)],
+                                "note": "per-image times exchanged every R steps (CUDA events), next steps' split by smoothed speed"}
     launches = ctx.launch_count - n0
     ms_total = jb.dist.max_over_ranks(ev0.elapsed_time(ev1), dev)
     ms_step = ms_total / K
@@ -381,7 +437,7 @@ def main():
             if G == 1:
                 gather.submit(tk.to(dev))
             else:
-                kept[k].copy_(tk, non_blocking=True)
+                kept[k, :I_r].copy_(tk, non_blocking=True)
         finish_steps()
         torch.cuda.synchronize()
         dt_block = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
@@ -398,7 +454,7 @@ def main():
             if G == 1:
                 gather.submit(tk2.to(dev, non_blocking=True))
             else:
-                kept[k].copy_(tk2, non_blocking=True)
+                kept[k, :I_r].copy_(tk2, non_blocking=True)
         finish_steps()
         torch.cuda.synchronize()
         dt = jb.dist.max_over_ranks(time.perf_counter() - t0, dev)
@@ -448,6 +504,21 @@ def main():
                    "note": "host: 500x375 uint8 decoded images + crop-box draw; device: Pillow-exact centre view + "
                            f"{args.crops} RandomResizedCrop(0.5-1)+flip views per image written straight into the conv1 patch "
                            "matrix on a second stream while the previous batch's towers run, then the hot path"}
+    # ---- informational: the reference's own call pattern, one image x (N+1) views per call (test.py:1692-1742), blocking,
+    #      host top-5 out: launch-latency-bound (~200 launches per call; encoded TMA descriptors are cached per shape)
+    single = None
+    if not args.no_e2e:
+        one = images[:1].contiguous()
+        for _ in range(5):
+            hp.evaluate_base(one, topk_to_host=True)
+        torch.cuda.synchronize()
+        n_calls = 50
+        t0 = time.perf_counter()
+        for _ in range(n_calls):
+            hp.evaluate_base(one, topk_to_host=True)
+        dt1 = (time.perf_counter() - t0) / n_calls
+        single = {"ms_per_call": 1e3 * dt1, "images_per_s": 1.0 / dt1, "views_per_call": V,
+                  "api": "HotPath.evaluate_base(1 image x views, device-resident), host top-5 back, one blocking call per image"}
     # ---- informational: the same device-resident step with the OTHER 16-bit operand type (the towers are re-packed)
     other_operands = None
     if not args.no_e2e:
@@ -591,7 +662,7 @@ def main():
                        **({"shard_check": shard_check} if shard_check else {}),
                        **({"topk_all_gather": "every step, asynchronous (dist.AsyncTopkGather)" if G == 1 else
                            f"once per {K} timed steps, inside the timed region"} if world > 1 else {})),
-        "e2e": e2e, "e2e_from_images": e2e_img, "cls_only_last_block": cls_only, "other_operand_type": other_operands, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "e2e_from_images": e2e_img, "cls_only_last_block": cls_only, "other_operand_type": other_operands, "single_image_call": single, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
     return 0

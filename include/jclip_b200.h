@@ -100,6 +100,9 @@ int jcb_ctx_set_cls_only_last_block(jcb_ctx* ctx, int on);
 #define JCB_OPERAND_F16 1
 int jcb_ctx_set_operand_type(jcb_ctx* ctx, int operand_type);
 int jcb_ctx_get_operand_type(const jcb_ctx* ctx);
+/* Give the grow-only scratch of the context (tower pass buffers, view-generator scratch, host-input staging) back to
+ * the device allocator; it is re-reserved on demand.  Waits for the device.  JCB_E_STATE while submissions are in flight. */
+int jcb_ctx_trim(jcb_ctx* ctx);
 /* Wait for the context's stream and report any device-side kernel status. */
 int jcb_sync(jcb_ctx* ctx);
 const char* jcb_last_error(const jcb_ctx* ctx);

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "jcb_ctx_get_operand_type": (c_int, [c_void_p]),
     "jcb_vit_operand_type": (c_int, [c_void_p]),
     "jcb_text_operand_type": (c_int, [c_void_p]),
+    "jcb_ctx_trim": (c_int, [c_void_p]),
     "jcb_sync": (c_int, [c_void_p]),
     "jcb_last_error": (c_char_p, [c_void_p]),
     "jcb_ctx_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),

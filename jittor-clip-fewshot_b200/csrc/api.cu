@@ -691,6 +691,26 @@ int jcb_vit_operand_type(const jcb_vit* v) { return v ? (v->f16 ? JCB_OPERAND_F1
 
 int jcb_text_operand_type(const jcb_text* t) { return t ? (t->f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
 
+int jcb_ctx_trim(jcb_ctx* ctx) {
+  if (!ctx) return JCB_E_INVALID;
+  DeviceGuard g(ctx->device);
+  if (ctx->next_ticket > ctx->waited_ticket) return fail(ctx, JCB_E_STATE, "jcb_ctx_trim: submissions are still in flight");
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  if (ctx->tta_ws) cudaFree(ctx->tta_ws);
+  ctx->tta_ws = nullptr;
+  ctx->tta_ws_bytes = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    ctx->stage[i] = nullptr;
+  }
+  ctx->stage_bytes = 0;
+  ctx->stage_recorded[0] = ctx->stage_recorded[1] = false;
+  return JCB_OK;
+}
+
 int jcb_sync(jcb_ctx* ctx) {
   if (!ctx) return JCB_E_INVALID;
   DeviceGuard g(ctx->device);

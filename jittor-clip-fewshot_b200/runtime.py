@@ -65,6 +65,10 @@ class Context:
     def sync(self):
         check(self.lib.jcb_sync(self.handle), self.handle)
 
+    def trim(self):
+        """Release the context's grow-only scratch (re-reserved on demand)."""
+        check(self.lib.jcb_ctx_trim(self.handle), self.handle)
+
     @property
     def launch_count(self):
         return int(self.lib.jcb_ctx_launch_count(self.handle))

@@ -218,3 +218,39 @@ def test_evaluate_new_and_ood_split(jb, cuda_dev):
     pred, is_base = jb.split_ood_batch(model, imgs, Tz, apply_clip_norm=True)
     assert pred.cpu().tolist() == top5[:, 0].tolist()
     assert is_base.cpu().tolist() == [p <= 372 for p in pred.cpu().tolist()]
+
+
+@pytest.mark.parametrize("order", ["small_then_large", "large_then_small"])
+def test_two_towers_of_different_size_share_the_workspace(jb, cuda_dev, order):
+    """jcb_pipeline with a second (zero-shot) tower that needs MORE workspace than the first (50-token plain tower first,
+    54-token IVLP / VPT tower second) or less: the embeddings of the first tower, the modes and the MTA scratch are carved
+    from the same workspace as the towers' pass buffers and must survive the second tower's reservation (round-1 bug:
+    the second reservation re-allocated the buffer).  Checked against per-tower encode_image calls + the oracle pipeline
+    on those embeddings.  Reference: test.py:1705-1713 (two towers feeding the three solve_mta calls)."""
+    from oracle import pipeline_image
+    sd_a = jb.synth.make_vit_state_dict(seed=4, layers=2)
+    sd_b = jb.synth.make_vit_state_dict(seed=5, layers=2, vpt_tokens=4)
+    m_a, m_b = jb.jclip.build_model(sd_a), jb.jclip.build_model(sd_b, design_details=dict(jb.clip.IVLP_DESIGN))
+    main, zs = (m_a, m_b) if order == "small_then_large" else (m_b, m_a)
+    Ts = _texts(jb, 3)
+    lp_np = jb.synth.make_head(2, Ts[2].numpy())
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = lp_np
+    lp_t = tuple(torch.from_numpy(a) for a in lp_np)
+    I, V = 6, 7
+    imgs = torch.from_numpy(jb.synth.make_views(31, I, V)).to(cuda_dev)
+    ctx = jb.get_context(cuda_dev)
+    ctx.trim()       # the workspace is grow-only: start from nothing so that the reservations below are the ones under test
+    hp = jb.HotPath(main, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, clip_model_zs=zs, rank_by="cs5")
+    big = torch.from_numpy(jb.synth.make_views(32, 40, V)).to(cuda_dev)
+    topk, feats, scores = hp.evaluate_base(imgs, return_feats=True, return_scores=True)
+    topk_big = hp.evaluate_base(big)                                          # forces a larger reservation for both towers
+    assert topk_big.shape == (40, 5)
+    f_main = main.visual(imgs.view(I * V, 3, 224, 224), apply_clip_norm=True, normalize=True).view(I, V, -1)
+    f_zs = zs.visual(imgs.view(I * V, 3, 224, 224), apply_clip_norm=True, normalize=True).view(I, V, -1)
+    assert torch.equal(feats, f_main)
+    for i in range(I):
+        t5, sc, _ = pipeline_image(f_main[i].cpu(), f_zs[i].cpu(), Ts[0], Ts[1], Ts[2], lp_t, score="cs5")
+        assert (scores[i].cpu() - sc["cs5"][0]).abs().max() <= 1e-2
+        assert set(t5.tolist()) == set(topk[i].cpu().tolist())
+    assert torch.equal(hp.evaluate_base(imgs), topk)

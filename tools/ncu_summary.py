@@ -62,7 +62,9 @@ def full(path):
                 print(f"- {k} [{u[k]}] = {d[k]}")
         rd, wr = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
         if rd and wr:
-            print(f"- traffic (dram read + write) [{u['dram__bytes_read.sum']}] = {float(rd) + float(wr):.3f}")
+            scale = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0, "Tbyte": 1e3}
+            gb = float(rd) * scale[u["dram__bytes_read.sum"]] + float(wr) * scale[u["dram__bytes_write.sum"]]
+            print(f"- traffic (dram read + write) [Gbyte] = {gb:.3f}")
         print()
 
 
