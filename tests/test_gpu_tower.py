@@ -181,7 +181,7 @@ def test_empty_and_bad_inputs(jb, cuda_dev, tower):
         model.encode_image(torch.zeros(2, 3, 224, 224, dtype=torch.int32, device=cuda_dev))
 
 
-def test_real_lora_pickle_if_present(jb, cuda_dev, tmp_path):
+def test_lora_pickle_round_trip(jb, cuda_dev, tmp_path):
     """The LoRA pickle layout: round-trip through save_lora / load_lora with
     encoder='both' (text layers first, vision layers 12..23), then encode."""
     sd = jb.synth.make_vit_state_dict(seed=2, text_layers=12)
@@ -235,3 +235,71 @@ def test_cls_only_last_block_matches_full_schedule(jb, cuda_dev, vpt):
     assert _cos(fast, full).min() >= 0.99999 and (fast - full).abs().max() <= 2e-3
     assert _cos(fast_big, full_big).min() >= 0.99999 and (fast_big - full_big).abs().max() <= 2e-3
     assert torch.equal(model.visual(x, apply_clip_norm=True, normalize=True).cpu(), full)     # switched off again
+
+
+def _shipped_lora_pickle(tmp_path):
+    """The reference's trained adapters (lora_weights1/lora_weights.pkl) rebuilt in the reference's pickle layout
+    (save_lora, test.py:642-684) from the numeric fixture tests/golden/lora_weights1_arrays.npz
+    (oracle/make_golden_lora.py)."""
+    import json
+    import os
+    import pickle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lora_weights1_arrays.npz"))
+    meta = json.loads(bytes(z["metadata_json"]).decode())
+    weights = {}
+    for key in z.files:
+        if key == "metadata_json":
+            continue
+        layer, proj, name = key.split("/")
+        weights.setdefault(layer, {}).setdefault(proj, {})[name] = z[key]
+    path = tmp_path / "lora_weights.pkl"
+    with open(path, "wb") as f:
+        pickle.dump({"weights": weights, "metadata": meta}, f)
+    return str(path), meta, weights
+
+
+@pytest.mark.parametrize("op", ["f16", "bf16"])
+def test_shipped_trained_lora_through_load_lora(jb, cuda_dev, tmp_path, op):
+    """The only real weight artefact of the reference: trained rank-4 adapters on q, k, v of all 24 blocks
+    (encoder='both': layer_0..11 = text tower, layer_12..23 = vision tower), loaded through
+    `load_lora` exactly as test.py:1800-1803 does and run through BOTH towers against the fp32 oracle, which applies
+    them un-merged (test.py:388-398)."""
+    from oracle import text_encode, vit_encode_image
+    path, meta, weights = _shipped_lora_pickle(tmp_path)
+    assert meta == {"r": 4, "alpha": 1, "encoder": "both", "params": ["q", "k", "v"], "position": "all"}
+    sd = jb.synth.make_vit_state_dict(seed=2, text_layers=12)
+    model = jb.jclip.build_model(sd)
+    args = _args(encoder="both")
+    layers = jb.apply_lora(args, model)
+    assert len(layers) == 24
+    jb.load_lora(args, layers, path)
+    assert np.array_equal(layers[12].q_proj.w_lora_A.data, weights["layer_12"]["q_proj"]["w_lora_A"])
+    assert layers[0].q_proj.w_lora_B.data.shape == (512, 4) and layers[23].v_proj.w_lora_B.data.shape == (768, 4)
+    # a mismatching metadata field is refused as in the reference (test.py:702-717)
+    with pytest.raises(ValueError):
+        jb.load_lora(_args(params=("q", "v"), encoder="both"), layers, path)
+    lora_v = {i: {p: (weights[f"layer_{12 + i}"][p]["w_lora_A"], weights[f"layer_{12 + i}"][p]["w_lora_B"])
+                  for p in ("q_proj", "k_proj", "v_proj")} for i in range(12)}
+    lora_t = {i: {p: (weights[f"layer_{i}"][p]["w_lora_A"], weights[f"layer_{i}"][p]["w_lora_B"])
+                  for p in ("q_proj", "k_proj", "v_proj")} for i in range(12)}
+    imgs = jb.synth.make_views(12, 1, 6).reshape(6, 3, 224, 224)
+    tok = jb.synth.make_tokens(9, 7, vocab=64)
+    ref = vit_encode_image(sd, imgs, lora=lora_v, scaling=0.5, apply_clip_norm=True, normalize=True)
+    ref0 = vit_encode_image(sd, imgs, lora=None, apply_clip_norm=True, normalize=True)
+    reft = text_encode(sd, tok, lora=lora_t, scaling=0.5, normalize=True)
+    ctx = jb.get_context(cuda_dev)
+    prev = ctx.operand_type
+    try:
+        ctx.set_operand_type(op)
+        out = model.visual(torch.from_numpy(imgs).to(cuda_dev), apply_clip_norm=True, normalize=True).cpu()
+        outt = model.encode_text(torch.from_numpy(tok).to(cuda_dev), normalize=True).cpu()
+    finally:
+        ctx.set_operand_type(prev)
+    floor = 0.9995 if op == "bf16" else 0.99999
+    assert _cos(out, ref).min() >= floor, _cos(out, ref).min()
+    assert _cos(outt, reft).min() >= floor, _cos(outt, reft).min()
+    # What the adapters do at their trained magnitudes (on these random-init base weights): 1 - cos = 1.7e-6 between the
+    # embeddings with and without them.  fp16 operands resolve that ten times over (1 - cos = 4e-8 vs the oracle); bf16
+    # operands (3e-6) do not -- their rounding is larger than the whole LoRA effect.
+    if op == "f16":
+        assert (1 - _cos(ref0, ref)).min() > 10 * (1 - _cos(out, ref)).max()
