@@ -329,6 +329,14 @@ typedef struct jcb_pipeline_args {
  * (test.py:1711-1713). */
 int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* args);
 
+/* Small calls (n_images * n_views <= max_views, default 1024; device work only; no out_feats / out_scores) are served
+ * from CUDA graphs: the second jcb_pipeline call with the same towers, shapes and operand pointers is captured, later ones
+ * replay it with a single launch (the reference's own loop calls the path once per image, test.py:1692-1742: ~210
+ * launches for ~0.6 ms of GPU work).  Results are bit-identical to the un-captured path.  on = 0 (or env JCB_GRAPHS=0)
+ * disables and drops the captured graphs; max_views = 0 keeps the current threshold. */
+int jcb_ctx_set_graphs(jcb_ctx* ctx, int on, int64_t max_views);
+int jcb_ctx_graph_stats(const jcb_ctx* ctx, int64_t* captured, int64_t* launched);
+
 /* The same for a STREAM of batches (the reference's `for images in loader:` loop, test.py:1692): submit enqueues
  * everything jcb_pipeline does -- the host->device copies of the view chunks, the tower, MTA, head and, with
  * topk_on_host, the device->host copy of the top-k -- and returns without waiting; jcb_pipeline_wait blocks until

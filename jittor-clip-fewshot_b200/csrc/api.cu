@@ -34,6 +34,7 @@ cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
 }  // namespace jcb
 
 // ------------------------------------------------------------------------------------------------
+struct PipelineGraph;
 struct jcb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -71,6 +72,12 @@ struct jcb_ctx {
                                      // 0 none, 1 ln_1 only (c_proj -> QKV), 2 ln_1 and ln_2
   int operand_f16 = 1;               // 16-bit operand type towers are packed with: 1 = fp16 (default), 0 = bf16
   char err[512] = {0};
+  // CUDA graphs of whole small pipelines (see PipelineGraph below)
+  int graphs_on = 1;
+  int64_t graph_max_views = 1024;
+  uint64_t ws_gen = 0;               // bumped whenever `ws` is re-allocated: graphs hold pointers into it
+  std::vector<struct PipelineGraph*> graphs;
+  int64_t graph_captures = 0, graph_launches = 0;
   // per-kernel-class CUDA-event profile (jcb_ctx_profile): event pairs recorded on the launch stream
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;           // 2 * PROF_PAIRS events, created on first use
@@ -81,6 +88,8 @@ struct jcb_ctx {
   double prof_flops[JCB_KC_COUNT] = {0};
   double prof_bytes[JCB_KC_COUNT] = {0};
 };
+
+void graphs_clear_fwd(jcb_ctx* ctx);   // defined next to the pipeline graphs below
 
 namespace {
 
@@ -151,6 +160,7 @@ int ws_reserve(jcb_ctx* ctx, size_t bytes) {
   if (ctx->ws) cudaFree(ctx->ws);
   ctx->ws = nullptr;
   ctx->ws_bytes = 0;
+  ++ctx->ws_gen;
   cudaError_t e = cudaMalloc(&ctx->ws, bytes);
   if (e != cudaSuccess) return fail(ctx, JCB_E_NOMEM, "cudaMalloc(%zu) for the workspace failed: %s", bytes, cudaGetErrorString(e));
   ctx->ws_bytes = bytes;
@@ -213,6 +223,7 @@ struct LayerDev {
 struct TowerBase {
   jcb_ctx* ctx = nullptr;
   int f16 = 0;                                       // operand type the device weights were packed with (jcb_*_finalize)
+  uint64_t gen = 0;                                  // bumped by every finalize (captured graphs key on it)
   int W = 0, L = 0, heads = 0, tokens = 0;           // width, blocks, heads (W / 64), tokens per sequence
   std::string prefix;                                // state-dict prefix of the blocks
   std::map<std::string, std::vector<float>> host;   // fp32 staging by reference key name
@@ -591,6 +602,8 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
     ctx->cls_only_last = (env_cls && env_cls[0] == '1') ? 1 : 0;
     const char* env_op = getenv("JCB_OPERANDS");   // "bf16" | "f16" (default): see jcb_ctx_set_operand_type
     ctx->operand_f16 = (env_op && (env_op[0] == 'b' || env_op[0] == 'B')) ? 0 : 1;
+    const char* env_g = getenv("JCB_GRAPHS");
+    ctx->graphs_on = (env_g && env_g[0] == '0') ? 0 : 1;
     const char* env = getenv("JCB_LN_FOLD");
     ctx->ln_fold = env ? atoi(env) : 2;   // default: both LayerNorms folded (measured, same box: 75.7-76.0 vs
                                           // 77.2-78.7 ms / step for ln_1 only); see tower_blocks
@@ -624,6 +637,7 @@ int jcb_ctx_destroy(jcb_ctx* ctx) {
   DeviceGuard g(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  graphs_clear_fwd(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->tta_ws) cudaFree(ctx->tta_ws);
   for (int i = 0; i < 2; ++i) {
@@ -696,9 +710,11 @@ int jcb_ctx_trim(jcb_ctx* ctx) {
   DeviceGuard g(ctx->device);
   if (ctx->next_ticket > ctx->waited_ticket) return fail(ctx, JCB_E_STATE, "jcb_ctx_trim: submissions are still in flight");
   CUDA_TRY(ctx, cudaDeviceSynchronize());
+  graphs_clear_fwd(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   ctx->ws = nullptr;
   ctx->ws_bytes = 0;
+  ++ctx->ws_gen;
   if (ctx->tta_ws) cudaFree(ctx->tta_ws);
   ctx->tta_ws = nullptr;
   ctx->tta_ws_bytes = 0;
@@ -813,6 +829,7 @@ int jcb_vit_destroy(jcb_vit* v) {
   if (!v) return JCB_OK;
   DeviceGuard g(v->ctx->device);
   cudaStreamSynchronize(v->ctx->stream);
+  graphs_clear_fwd(v->ctx);      // captured pipelines point into this tower's weights
   if (v->arena) cudaFree(v->arena);
   delete v;
   return JCB_OK;
@@ -851,6 +868,7 @@ struct Packer {
   int begin(size_t arena_bytes, size_t max_tensor_elems) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     t->f16 = ctx->operand_f16;   // the tower keeps the operand type it was packed with until the next finalize
+    ++t->gen;
     if (!t->arena || t->arena_bytes < arena_bytes) {
       if (t->arena) cudaFree(t->arena);
       t->arena = nullptr;
@@ -1425,10 +1443,170 @@ int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) 
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// CUDA graphs for SMALL pipelines.  The reference calls the path once per image (test.py:1692-1742: 1 image x 65 views):
+// ~210 kernel launches for ~0.6 ms of GPU work, i.e. bound by launch latency on the host.  The launch sequence of
+// jcb_pipeline depends only on (towers, shapes, operand pointers), so the second call with the same key is captured
+// into a graph (input copied into a graph-owned staging buffer, top-k read from a graph-owned buffer) and later calls
+// replay it with one launch.  Only device work is captured: no allocation, no synchronisation (the first call with a
+// key ran normally and reserved the workspace).  Graphs are dropped when the workspace moves, a tower is re-packed or
+// destroyed, or a schedule option changes.  jcb_ctx_set_graphs(ctx, 0) / JCB_GRAPHS=0 turn the mechanism off.
+struct PipelineGraph {
+  // key
+  const jcb_vit *vit = nullptr, *vit_zs = nullptr;
+  uint64_t vit_gen = 0, zs_gen = 0, ws_gen = 0;
+  int64_t I = 0;
+  int V = 0, dt = 0, apply_norm = 0, C = 0, rank_by = 0, k = 0, ln_fold = 0, cls_only = 0;
+  const void* ptrs[10] = {nullptr};   // text banks (6) + head weights (4)
+  cudaStream_t stream = nullptr;
+  // state
+  int seen = 0;
+  cudaGraphExec_t exec = nullptr;
+  void* in_stage = nullptr;
+  int32_t* topk_dev = nullptr;
+  uint64_t last_use = 0;
+};
+
+namespace {
+void graph_free(PipelineGraph* g) {
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->in_stage) cudaFree(g->in_stage);
+  if (g->topk_dev) cudaFree(g->topk_dev);
+  delete g;
+}
+void graphs_clear(jcb_ctx* ctx) {
+  if (ctx->graphs.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto* g : ctx->graphs) graph_free(g);
+  ctx->graphs.clear();
+}
+bool graph_key_equal(const PipelineGraph& g, const jcb_ctx* ctx, const jcb_vit* vit, const jcb_vit* vit_zs, const jcb_pipeline_args* a) {
+  if (g.vit != vit || g.vit_zs != vit_zs || g.vit_gen != vit->gen || g.zs_gen != (vit_zs ? vit_zs->gen : 0) ||
+      g.I != a->n_images || g.V != a->n_views || g.dt != a->img_dtype ||
+      g.apply_norm != a->apply_clip_norm || g.C != a->n_classes || g.rank_by != a->rank_by || g.k != a->k ||
+      g.ln_fold != ctx->ln_fold || g.cls_only != ctx->cls_only_last || g.stream != ctx->stream)
+    return false;
+  const void* p[10] = {a->text_pt_dev, a->text_hand_dev, a->text_zs_dev, a->text_pt_t_dev, a->text_hand_t_dev, a->text_zs_t_dev,
+                       a->lp.scale1, a->lp.bias1, a->lp.fc_w, a->lp.fc_b};
+  for (int i = 0; i < 10; ++i)
+    if (g.ptrs[i] != p[i]) return false;
+  return true;
+}
+
+// returns JCB_OK with *handled = true when the call was served by a graph
+int pipeline_try_graph(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a, bool* handled) {
+  *handled = false;
+  jcb_ctx* ctx = vit->ctx;
+  if (!ctx->graphs_on || ctx->prof_on || !a || a->n_images < 1 || a->out_feats_dev || a->out_scores_dev ||
+      static_cast<int64_t>(a->n_images) * a->n_views > ctx->graph_max_views || ctx->next_ticket > ctx->waited_ticket)
+    return JCB_OK;
+  if (check_vit(vit) != JCB_OK || (vit_zs && (check_vit(vit_zs) != JCB_OK || vit_zs->ctx != ctx))) return JCB_OK;   // the normal path reports it
+  static uint64_t tick = 0;
+  PipelineGraph* g = nullptr;
+  for (size_t i = 0; i < ctx->graphs.size();) {
+    PipelineGraph* c = ctx->graphs[i];
+    if (c->ws_gen != ctx->ws_gen && c->exec) {     // the workspace moved under a captured graph: drop it
+      cudaStreamSynchronize(ctx->stream);
+      graph_free(c);
+      ctx->graphs.erase(ctx->graphs.begin() + static_cast<long>(i));
+      continue;
+    }
+    if (graph_key_equal(*c, ctx, vit, vit_zs, a)) g = c;
+    ++i;
+  }
+  if (!g) {
+    if (ctx->graphs.size() >= 16) {   // forget the least recently used shape
+      size_t lru = 0;
+      for (size_t i = 1; i < ctx->graphs.size(); ++i)
+        if (ctx->graphs[i]->last_use < ctx->graphs[lru]->last_use) lru = i;
+      cudaStreamSynchronize(ctx->stream);
+      graph_free(ctx->graphs[lru]);
+      ctx->graphs.erase(ctx->graphs.begin() + static_cast<long>(lru));
+    }
+    g = new PipelineGraph();
+    g->vit = vit; g->vit_zs = vit_zs; g->vit_gen = vit->gen; g->zs_gen = vit_zs ? vit_zs->gen : 0;
+    g->I = a->n_images; g->V = a->n_views; g->dt = a->img_dtype; g->apply_norm = a->apply_clip_norm; g->C = a->n_classes;
+    g->rank_by = a->rank_by; g->k = a->k; g->ln_fold = ctx->ln_fold; g->cls_only = ctx->cls_only_last; g->stream = ctx->stream;
+    const void* p[10] = {a->text_pt_dev, a->text_hand_dev, a->text_zs_dev, a->text_pt_t_dev, a->text_hand_t_dev, a->text_zs_t_dev,
+                         a->lp.scale1, a->lp.bias1, a->lp.fc_w, a->lp.fc_b};
+    for (int i = 0; i < 10; ++i) g->ptrs[i] = p[i];
+    ctx->graphs.push_back(g);
+  }
+  g->last_use = ++tick;
+  if (g->seen++ == 0) return JCB_OK;          // first call with this key: the normal path (reserves the workspace)
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = static_cast<size_t>(a->n_images) * a->n_views * 3 * vit->cfg.resolution * vit->cfg.resolution *
+                          img_elem_bytes(a->img_dtype);
+  const size_t topk_bytes = static_cast<size_t>(a->n_images) * a->k * sizeof(int32_t);
+  if (!g->exec) {
+    g->ws_gen = ctx->ws_gen;
+    if (!g->in_stage && cudaMalloc(&g->in_stage, in_bytes) != cudaSuccess) { cudaGetLastError(); g->seen = 0; return JCB_OK; }
+    if (!g->topk_dev && cudaMalloc(reinterpret_cast<void**>(&g->topk_dev), topk_bytes) != cudaSuccess) { cudaGetLastError(); g->seen = 0; return JCB_OK; }
+    jcb_pipeline_args inner = *a;
+    inner.images = g->in_stage;
+    inner.images_on_host = 0;
+    inner.topk_on_host = 0;
+    inner.out_topk = g->topk_dev;
+    const uint64_t ws_before = ctx->ws_gen;
+    const int64_t launches_before = ctx->launches;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g->seen = 0; return JCB_OK; }
+    const int rc = pipeline_enqueue(vit, vit_zs, &inner);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != JCB_OK || ce != cudaSuccess || graph == nullptr || ctx->ws_gen != ws_before) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      ctx->launches = launches_before;
+      g->seen = 0;                             // fall back to the normal path (and try again later)
+      return JCB_OK;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    ctx->launches = launches_before;           // captured, not launched
+    if (ie != cudaSuccess) { cudaGetLastError(); g->exec = nullptr; g->seen = 0; return JCB_OK; }
+    ++ctx->graph_captures;
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(g->in_stage, a->images, in_bytes, cudaMemcpyDefault, ctx->stream));
+  CUDA_TRY(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(a->out_topk, g->topk_dev, topk_bytes, cudaMemcpyDefault, ctx->stream));
+  ++ctx->graph_launches;
+  ++ctx->launches;
+  *handled = true;
+  return JCB_OK;
+}
+}  // namespace
+
 int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) {
+  if (vit && a) {
+    bool handled = false;
+    int rc = pipeline_try_graph(vit, vit_zs, a, &handled);
+    if (rc) return rc;
+    if (handled) return a->topk_on_host ? sync_and_check(vit->ctx) : JCB_OK;
+  }
   int rc = pipeline_enqueue(vit, vit_zs, a);
   if (rc) return rc;
   if (a->n_images > 0 && a->topk_on_host) return sync_and_check(vit->ctx);
+  return JCB_OK;
+}
+
+}  // extern "C"
+void graphs_clear_fwd(jcb_ctx* ctx) { graphs_clear(ctx); }
+extern "C" {
+
+int jcb_ctx_set_graphs(jcb_ctx* ctx, int on, int64_t max_views) {
+  if (!ctx) return JCB_E_INVALID;
+  if (max_views < 0) return fail(ctx, JCB_E_INVALID, "jcb_ctx_set_graphs: negative max_views");
+  DeviceGuard g(ctx->device);
+  ctx->graphs_on = on ? 1 : 0;
+  if (max_views > 0) ctx->graph_max_views = max_views;
+  if (!on) graphs_clear(ctx);
+  return JCB_OK;
+}
+
+int jcb_ctx_graph_stats(const jcb_ctx* ctx, int64_t* captured, int64_t* launched) {
+  if (!ctx) return JCB_E_INVALID;
+  if (captured) *captured = ctx->graph_captures;
+  if (launched) *launched = ctx->graph_launches;
   return JCB_OK;
 }
 

@@ -72,9 +72,18 @@ __host__ __device__ constexpr bool out_is_bf16(int epi) { return epi == EPI_BIAS
 // LNPREP (residual epilogue that also reads the old residual through TMA loads): NB fp32 chunk buffers per warp,
 // loads issued D chunks ahead, NH bf16 chunk buffers.  SHORT (out_proj, HBM-bound, 12 k-blocks per tile): deep
 // prefetch, 3 ring stages.  LONG (c_proj, 48 k-blocks per tile, tensor-bound): shallow prefetch, 5 ring stages.
-__host__ __device__ constexpr int lnprep_nb(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? 5 : 2; }
-__host__ __device__ constexpr int lnprep_d(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? 3 : 1; }
-__host__ __device__ constexpr int lnprep_nh(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? 2 : 1; }
+#ifndef JCB_LNS_NB
+#define JCB_LNS_NB 5
+#endif
+#ifndef JCB_LNS_D
+#define JCB_LNS_D 3
+#endif
+#ifndef JCB_LNS_NH
+#define JCB_LNS_NH 2
+#endif
+__host__ __device__ constexpr int lnprep_nb(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? JCB_LNS_NB : 2; }
+__host__ __device__ constexpr int lnprep_d(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? JCB_LNS_D : 1; }
+__host__ __device__ constexpr int lnprep_nh(int epi) { return epi == EPI_RESID_LNPREP_SHORT ? JCB_LNS_NH : 1; }
 
 template <int BN, int CTAS, int EPI>
 struct TileCfg {

@@ -65,6 +65,15 @@ class Context:
     def sync(self):
         check(self.lib.jcb_sync(self.handle), self.handle)
 
+    def set_graphs(self, on=True, max_views=0):
+        """CUDA graphs for small jcb_pipeline calls (include/jclip_b200.h jcb_ctx_set_graphs)."""
+        check(self.lib.jcb_ctx_set_graphs(self.handle, int(bool(on)), int(max_views)), self.handle)
+
+    def graph_stats(self):
+        c, n = ctypes.c_int64(), ctypes.c_int64()
+        check(self.lib.jcb_ctx_graph_stats(self.handle, byref(c), byref(n)), self.handle)
+        return {"captured": c.value, "launched": n.value}
+
     def trim(self):
         """Release the context's grow-only scratch (re-reserved on demand)."""
         check(self.lib.jcb_ctx_trim(self.handle), self.handle)

@@ -254,3 +254,52 @@ def test_two_towers_of_different_size_share_the_workspace(jb, cuda_dev, order):
         assert (scores[i].cpu() - sc["cs5"][0]).abs().max() <= 1e-2
         assert set(t5.tolist()) == set(topk[i].cpu().tolist())
     assert torch.equal(hp.evaluate_base(imgs), topk)
+
+
+def test_small_calls_are_served_from_cuda_graphs(jb, cuda_dev):
+    """The reference's call pattern -- one image x V views per call (test.py:1692-1742) -- is captured into a CUDA graph
+    on the second call with the same key and replayed afterwards: bit-identical top-k, device and pinned-host input,
+    several shapes interleaved, re-captured after the workspace moved, dropped when the tower is re-packed."""
+    sd = jb.synth.make_vit_state_dict(seed=4, layers=2)
+    model = jb.jclip.build_model(sd)
+    Ts = _texts(jb, 3)
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = jb.synth.make_head(2, Ts[2].numpy())
+    hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by="cs5")
+    ctx = jb.get_context(cuda_dev)
+    imgs = torch.from_numpy(jb.synth.make_views(41, 6, 9)).to(cuda_dev)
+    a, b = imgs[:1].contiguous(), imgs[1:4].contiguous()
+    ctx.set_graphs(False)
+    want_a, want_b = hp.evaluate_base(a).clone(), hp.evaluate_base(b).clone()
+    want_rows = [hp.evaluate_base(imgs[i:i + 1].contiguous()).clone() for i in range(6)]
+    ctx.set_graphs(True)
+    s0 = ctx.graph_stats()
+    for _ in range(4):
+        assert torch.equal(hp.evaluate_base(a), want_a)
+        assert torch.equal(hp.evaluate_base(b), want_b)
+    s1 = ctx.graph_stats()
+    assert s1["captured"] == s0["captured"] + 2 and s1["launched"] == s0["launched"] + 6, (s0, s1)
+    # the same graph serves other DATA of the same shape, from the device or from pinned host memory
+    for i in range(6):
+        assert torch.equal(hp.evaluate_base(imgs[i:i + 1].contiguous()), want_rows[i])
+        assert torch.equal(hp.evaluate_base(imgs[i:i + 1].cpu().pin_memory()), want_rows[i].cpu())
+    # a large call moves the workspace: the graphs are dropped and re-captured, results unchanged
+    ctx.trim()
+    big = torch.from_numpy(jb.synth.make_views(42, 40, 9)).to(cuda_dev)
+    hp.evaluate_base(big)
+    for _ in range(3):
+        assert torch.equal(hp.evaluate_base(a), want_a)
+    s2 = ctx.graph_stats()
+    assert s2["captured"] >= s1["captured"] + 1
+    # re-packing the tower (other operand type) invalidates the graph; the new one matches the un-captured path
+    prev = ctx.operand_type
+    try:
+        ctx.set_operand_type("bf16" if prev == "f16" else "f16")
+        ctx.set_graphs(False)
+        want_o = hp.evaluate_base(a).clone()
+        ctx.set_graphs(True)
+        for _ in range(3):
+            assert torch.equal(hp.evaluate_base(a), want_o)
+    finally:
+        ctx.set_operand_type(prev)
+    assert torch.equal(hp.evaluate_base(a), want_a)

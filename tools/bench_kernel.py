@@ -63,6 +63,22 @@ elif what == "gemm":
         out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == 2 else OP)
         ms = timeit(lambda: jb.blocks.gemm(A, B, out, epi, bias=bias, sync=False))
         print(f"gemm {name} M={M} N={N} K={K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s")
+elif what == "gemm_ln":
+    # the two LayerNorm-preparing residual epilogues at the bench shape (out_proj: HBM-bound, c_proj: tensor-bound)
+    C = jb._capi
+    M = n * 50
+    for name, (N, K, epi) in {"out_proj": (768, 768, C.EPI_RESID_LNPREP_SHORT), "c_proj": (768, 3072, C.EPI_RESID_LNPREP_LONG)}.items():
+        A = torch.randn(M, K, device=dev).to(OP)
+        B = (torch.randn(N, K, device=dev) * K ** -0.5).to(OP)
+        bias = torch.randn(N, device=dev)
+        resid = torch.zeros(M, N, device=dev)
+        copy = torch.empty(M, N, device=dev, dtype=OP)
+        st = [torch.zeros(M, 3, 2, device=dev) for _ in range(2)]
+        sh = [torch.zeros(M, device=dev) for _ in range(2)]
+        ms = timeit(lambda: jb.blocks.gemm(A, B, resid, epi, bias=bias, stats=st[1], out2=copy, stats_in=st[0], shift_in=sh[0],
+                                           shift_out=sh[1], sync=False))
+        gb = (2.0 * M * K + 10.0 * M * N) / 1e9
+        print(f"gemm_ln {name} M={M} N={N} K={K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.0f} TFLOP/s  {gb / ms * 1e3:.0f} GB/s")
 elif what == "tta":
     import numpy as np
     I = n
