@@ -335,7 +335,7 @@ int jcb_pipeline(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* args);
  * launches for ~0.6 ms of GPU work).  Results are bit-identical to the un-captured path.  on = 0 (or env JCB_GRAPHS=0)
  * disables and drops the captured graphs; max_views = 0 keeps the current threshold. */
 int jcb_ctx_set_graphs(jcb_ctx* ctx, int on, int64_t max_views);
-int jcb_ctx_graph_stats(const jcb_ctx* ctx, int64_t* captured, int64_t* launched);
+int jcb_ctx_graph_stats(const jcb_ctx* ctx, int64_t* captured, int64_t* launched, int64_t* failed);
 
 /* The same for a STREAM of batches (the reference's `for images in loader:` loop, test.py:1692): submit enqueues
  * everything jcb_pipeline does -- the host->device copies of the view chunks, the tower, MTA, head and, with

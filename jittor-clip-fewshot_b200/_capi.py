@@ -138,7 +138,7 @@ PROTOTYPES = {
     "jcb_logit_normalize": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "jcb_pipeline": (c_int, [c_void_p, c_void_p, POINTER(PipelineArgs)]),
     "jcb_ctx_set_graphs": (c_int, [c_void_p, c_int, c_int64]),
-    "jcb_ctx_graph_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "jcb_ctx_graph_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "jcb_pipeline_submit": (c_int, [c_void_p, c_void_p, POINTER(PipelineArgs), POINTER(c_int64)]),
     "jcb_pipeline_wait": (c_int, [c_void_p, c_int64]),
     "jcb_gemm": (c_int, [c_void_p, POINTER(GemmArgs)]),

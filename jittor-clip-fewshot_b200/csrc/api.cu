@@ -77,7 +77,9 @@ struct jcb_ctx {
   int64_t graph_max_views = 1024;
   uint64_t ws_gen = 0;               // bumped whenever `ws` is re-allocated: graphs hold pointers into it
   std::vector<struct PipelineGraph*> graphs;
-  int64_t graph_captures = 0, graph_launches = 0;
+  int64_t graph_captures = 0, graph_launches = 0, graph_failures = 0;
+  cudaStream_t capture_stream = nullptr;   // captures run here: the caller's stream may be the legacy default stream,
+                                           // which cannot be captured; the graph is LAUNCHED on the caller's stream
   // per-kernel-class CUDA-event profile (jcb_ctx_profile): event pairs recorded on the launch stream
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;           // 2 * PROF_PAIRS events, created on first use
@@ -638,6 +640,7 @@ int jcb_ctx_destroy(jcb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   graphs_clear_fwd(ctx);
+  if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->tta_ws) cudaFree(ctx->tta_ws);
   for (int i = 0; i < 2; ++i) {
@@ -1533,7 +1536,7 @@ int pipeline_try_graph(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a
     ctx->graphs.push_back(g);
   }
   g->last_use = ++tick;
-  if (g->seen++ == 0) return JCB_OK;          // first call with this key: the normal path (reserves the workspace)
+  if (g->seen++ <= 0) return JCB_OK;          // first call with this key (or a key that failed to capture): the normal path
   DeviceGuard guard(ctx->device);
   const size_t in_bytes = static_cast<size_t>(a->n_images) * a->n_views * 3 * vit->cfg.resolution * vit->cfg.resolution *
                           img_elem_bytes(a->img_dtype);
@@ -1549,21 +1552,30 @@ int pipeline_try_graph(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a
     inner.out_topk = g->topk_dev;
     const uint64_t ws_before = ctx->ws_gen;
     const int64_t launches_before = ctx->launches;
-    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g->seen = 0; return JCB_OK; }
+    if (!ctx->capture_stream && cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError(); ctx->capture_stream = nullptr; ++ctx->graph_failures; g->seen = 0; return JCB_OK;
+    }
+    cudaStream_t user_stream = ctx->stream;
+    if (cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError(); ++ctx->graph_failures; g->seen = 0; return JCB_OK;
+    }
+    ctx->stream = ctx->capture_stream;
     const int rc = pipeline_enqueue(vit, vit_zs, &inner);
+    ctx->stream = user_stream;
     cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->capture_stream, &graph);
     if (rc != JCB_OK || ce != cudaSuccess || graph == nullptr || ctx->ws_gen != ws_before) {
       cudaGetLastError();
       if (graph) cudaGraphDestroy(graph);
       ctx->launches = launches_before;
-      g->seen = 0;                             // fall back to the normal path (and try again later)
+      ++ctx->graph_failures;
+      g->seen = -1000000;                      // this key cannot be captured: stay on the normal path
       return JCB_OK;
     }
     const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
     cudaGraphDestroy(graph);
     ctx->launches = launches_before;           // captured, not launched
-    if (ie != cudaSuccess) { cudaGetLastError(); g->exec = nullptr; g->seen = 0; return JCB_OK; }
+    if (ie != cudaSuccess) { cudaGetLastError(); g->exec = nullptr; ++ctx->graph_failures; g->seen = -1000000; return JCB_OK; }
     ++ctx->graph_captures;
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(g->in_stage, a->images, in_bytes, cudaMemcpyDefault, ctx->stream));
@@ -1603,10 +1615,11 @@ int jcb_ctx_set_graphs(jcb_ctx* ctx, int on, int64_t max_views) {
   return JCB_OK;
 }
 
-int jcb_ctx_graph_stats(const jcb_ctx* ctx, int64_t* captured, int64_t* launched) {
+int jcb_ctx_graph_stats(const jcb_ctx* ctx, int64_t* captured, int64_t* launched, int64_t* failed) {
   if (!ctx) return JCB_E_INVALID;
   if (captured) *captured = ctx->graph_captures;
   if (launched) *launched = ctx->graph_launches;
+  if (failed) *failed = ctx->graph_failures;
   return JCB_OK;
 }
 

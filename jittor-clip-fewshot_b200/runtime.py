@@ -70,9 +70,9 @@ class Context:
         check(self.lib.jcb_ctx_set_graphs(self.handle, int(bool(on)), int(max_views)), self.handle)
 
     def graph_stats(self):
-        c, n = ctypes.c_int64(), ctypes.c_int64()
-        check(self.lib.jcb_ctx_graph_stats(self.handle, byref(c), byref(n)), self.handle)
-        return {"captured": c.value, "launched": n.value}
+        c, n, f = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(self.lib.jcb_ctx_graph_stats(self.handle, byref(c), byref(n), byref(f)), self.handle)
+        return {"captured": c.value, "launched": n.value, "failed": f.value}
 
     def trim(self):
         """Release the context's grow-only scratch (re-reserved on demand)."""
