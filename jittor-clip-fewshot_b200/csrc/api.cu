@@ -60,6 +60,8 @@ struct jcb_ctx {
   // generated on a second stream WHILE the towers use `ws` for the previous batch
   void* tta_ws = nullptr;
   size_t tta_ws_bytes = 0;
+  cudaStream_t tta_last_stream = nullptr;   // the stream the generator last ran on, and the end of that run: a call on
+  cudaEvent_t tta_done = nullptr;           // ANOTHER stream waits for it before it overwrites the shared scratch
   // pinned, double-buffered staging of the per-view plan (no stream synchronisation in the call)
   void* tta_plan_host[2] = {nullptr, nullptr};
   size_t tta_plan_bytes[2] = {0, 0};
@@ -656,6 +658,7 @@ int jcb_ctx_destroy(jcb_ctx* ctx) {
     if (ctx->tta_plan_host[i]) cudaFreeHost(ctx->tta_plan_host[i]);
     if (ctx->tta_plan_copied[i]) cudaEventDestroy(ctx->tta_plan_copied[i]);
   }
+  if (ctx->tta_done) cudaEventDestroy(ctx->tta_done);
   for (auto e : ctx->prof_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1238,6 +1241,8 @@ int tta_run(jcb_ctx* ctx, cudaStream_t stream, const uint8_t* src_dev, const jcb
   }
   int rc = tta_ws_reserve(ctx, need);
   if (rc) return rc;
+  if (!ctx->tta_done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->tta_done, cudaEventDisableTiming));
+  else if (ctx->tta_last_stream != stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->tta_done, 0));
   size_t bi = 0;
   for (int64_t j0 = 0; j0 < n_jobs; j0 += BATCH, ++bi) {
     const int64_t nj = std::min(BATCH, n_jobs - j0);
@@ -1270,6 +1275,8 @@ int tta_run(jcb_ctx* ctx, cudaStream_t stream, const uint8_t* src_dev, const jcb
     }
     ++ctx->launches;  // two kernels per call
   }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->tta_done, stream));
+  ctx->tta_last_stream = stream;
   return JCB_OK;
 }
 }  // namespace
