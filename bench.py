@@ -482,7 +482,7 @@ def main():
                 pass
             return topk
 
-        run_images(2, overlap=False)
+        run_images(4, overlap=False)     # first use: pinned staging, generator scratch (grows with the random crop sizes)
         jb.dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

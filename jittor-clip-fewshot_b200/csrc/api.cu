@@ -1239,7 +1239,9 @@ int tta_run(jcb_ctx* ctx, cudaStream_t stream, const uint8_t* src_dev, const jcb
     need = std::max(need, align_up(plans.back().size()) + m.tmp_bytes);
     metas.push_back(m);
   }
-  int rc = tta_ws_reserve(ctx, need);
+  // the intermediate's size depends on the (random) crop heights: reserve with 25 % head-room, so that a stream of batches
+  // stops growing the scratch (a growth waits for the whole device) after the first one or two
+  int rc = tta_ws_reserve(ctx, need > ctx->tta_ws_bytes ? need + need / 4 : need);
   if (rc) return rc;
   if (!ctx->tta_done) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->tta_done, cudaEventDisableTiming));
   else if (ctx->tta_last_stream != stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->tta_done, 0));
