@@ -1056,8 +1056,8 @@ int jcb_text_create(jcb_ctx* ctx, const jcb_text_config* cfg, jcb_text** out) {
   if (cfg->layers < 1 || cfg->layers > 64) return fail(ctx, JCB_E_INVALID, "layers=%d unsupported", cfg->layers);
   if (cfg->width % 128 != 0 || cfg->width < 256 || cfg->width > 1024 || (cfg->width != 512 && cfg->width != 768 && cfg->width != 1024))
     return fail(ctx, JCB_E_INVALID, "text width=%d unsupported (512, 768 or 1024)", cfg->width);
-  if (cfg->context_length < 1 || cfg->context_length > 80)
-    return fail(ctx, JCB_E_INVALID, "context_length=%d unsupported (max 80)", cfg->context_length);
+  if (cfg->context_length < 1 || cfg->context_length > 128)
+    return fail(ctx, JCB_E_INVALID, "context_length=%d unsupported (max 128: one attention tile per head)", cfg->context_length);
   if (cfg->embed_dim != 512) return fail(ctx, JCB_E_INVALID, "embed_dim=%d unsupported (512 only)", cfg->embed_dim);
   if (cfg->vocab_size < 1) return fail(ctx, JCB_E_INVALID, "vocab_size=%d", cfg->vocab_size);
   jcb_text* t = new jcb_text();

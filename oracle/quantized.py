@@ -30,8 +30,10 @@ def _q(x, kind):
 
 @torch.no_grad()
 def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm=True, normalize=True,
-                             act="bf16", wgt="bf16", fold=True, centre=True):
-    """fold: LayerNorm folded into the consuming GEMM (JCB_LN_FOLD=2) instead of a rounded stand-alone LayerNorm.
+                             act="bf16", wgt="bf16", fold=True, centre=True, kinds=None):
+    """kinds: optional per-tensor-class overrides of `act` / `wgt`, e.g. {"hidden": "bf16"}; classes: patch, conv_w,
+    ln1_copy, qkv_w, qkv, p, attn, out_w, ln2_copy, fc_w, hidden, proj_w (per-class attribution of the deviation).
+    fold: LayerNorm folded into the consuming GEMM (JCB_LN_FOLD=2) instead of a rounded stand-alone LayerNorm.
     centre: the 16-bit copy of the residual row is x - shift, shift = the row's mean at the previous LayerNorm point
     (what the EPI_RESID_LNPREP_* epilogues write since round 2); False = the round-1 raw copy."""
     x = _t(images)
@@ -47,7 +49,10 @@ def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm
     L = len([k for k in sd if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
     eps = 1e-5
 
-    x = torch.nn.functional.conv2d(_q(x, act), _q(conv_w, wgt), bias=None, stride=P)
+    kinds = dict(kinds or {})
+    A = lambda name: kinds.get(name, act)      # activation classes
+    Wk = lambda name: kinds.get(name, wgt)     # weight classes
+    x = torch.nn.functional.conv2d(_q(x, A("patch")), _q(conv_w, Wk("conv_w")), bias=None, stride=P)
     x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
     cls = g("visual.class_embedding").view(1, 1, -1).expand(x.shape[0], 1, -1)
     x = torch.cat([cls, x], dim=1) + g("visual.positional_embedding")
@@ -61,12 +66,12 @@ def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm
 
     state = {"shift": None}
 
-    def ln_linear(t, gam, bet, W, b):
+    def ln_linear(t, gam, bet, W, b, a_kind, w_kind):
         """LN(t) @ W^T + b the way the folded GEMM computes it (or, fold=False, a rounded stand-alone LN)."""
         if not fold:
             mean, r = ln_stats(t)
-            return _q((t - mean) * r * gam + bet, act) @ _q(W, wgt).t() + b
-        Wf = _q(W * gam, wgt)
+            return _q((t - mean) * r * gam + bet, a_kind) @ _q(W, w_kind).t() + b
+        Wf = _q(W * gam, w_kind)
         S = Wf.sum(-1)
         c = W @ bet + b
         if centre:
@@ -76,7 +81,7 @@ def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm
         else:
             tc = t
         mean, r = ln_stats(tc)
-        return r * (_q(tc, act) @ Wf.t()) - r * mean * S + c
+        return r * (_q(tc, a_kind) @ Wf.t()) - r * mean * S + c
 
     mean, r = ln_stats(x)
     x = (x - mean) * r * g("visual.ln_pre.weight") + g("visual.ln_pre.bias")
@@ -84,16 +89,17 @@ def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm
     for i in range(L):
         p = f"visual.transformer.resblocks.{i}."
         qkv = _q(ln_linear(x, g(p + "ln_1.weight"), g(p + "ln_1.bias"), g(p + "attn.in_proj_weight"),
-                           g(p + "attn.in_proj_bias")), act)
+                           g(p + "attn.in_proj_bias"), A("ln1_copy"), Wk("qkv_w")), A("qkv"))
         q, k, v = (t.view(B, S_, H, 64).permute(0, 2, 1, 3) for t in qkv.split(W, dim=-1))
         s = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(64))
         pnum = torch.exp(s - s.max(-1, keepdim=True).values)
-        o = (_q(pnum, act) @ v) / pnum.sum(-1, keepdim=True)     # P rounded, row sum in fp32
-        o = _q(o.permute(0, 2, 1, 3).reshape(B, S_, W), act)
-        x = x + o @ _q(g(p + "attn.out_proj.weight"), wgt).t() + g(p + "attn.out_proj.bias")
-        h = ln_linear(x, g(p + "ln_2.weight"), g(p + "ln_2.bias"), g(p + "mlp.c_fc.weight"), g(p + "mlp.c_fc.bias"))
-        h = _q(h * torch.sigmoid(1.702 * h), act)
-        x = x + h @ _q(g(p + "mlp.c_proj.weight"), wgt).t() + g(p + "mlp.c_proj.bias")
+        o = (_q(pnum, A("p")) @ v) / pnum.sum(-1, keepdim=True)     # P rounded, row sum in fp32
+        o = _q(o.permute(0, 2, 1, 3).reshape(B, S_, W), A("attn"))
+        x = x + o @ _q(g(p + "attn.out_proj.weight"), Wk("out_w")).t() + g(p + "attn.out_proj.bias")
+        h = ln_linear(x, g(p + "ln_2.weight"), g(p + "ln_2.bias"), g(p + "mlp.c_fc.weight"), g(p + "mlp.c_fc.bias"),
+                      A("ln2_copy"), Wk("fc_w"))
+        h = _q(h * torch.sigmoid(1.702 * h), A("hidden"))
+        x = x + h @ _q(g(p + "mlp.c_proj.weight"), Wk("proj_w")).t() + g(p + "mlp.c_proj.bias")
     c0 = x[:, 0, :]
     mean, r = c0.mean(-1, keepdim=True), None
     var = ((c0 - mean) ** 2).mean(-1, keepdim=True)

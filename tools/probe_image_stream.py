@@ -1,3 +1,5 @@
+"""Host-side timing probe of HotPath.evaluate_image_stream (in stream order vs overlapped on a second stream): ms per step
+and the host time of every TTAViews call.  python tools/probe_image_stream.py   (PIN=1: bind to the GPU's NUMA node first)"""
 import os, sys, time, types
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
