@@ -706,8 +706,11 @@ __device__ __forceinline__ void mf_density(const float* __restrict__ X, int ldx,
 // NT = 512 threads and one CTA per SM for the headline view counts (V = 65: 168 KB of shared memory); NT = 128 and up to
 // four CTAs per SM for V <= 32, where a problem is a few KB and 512 threads mostly wait at barriers (N = 1 and N = 16
 // crops: thousands of tiny problems per step).
+// NT = 32 / 64: one or two warps per problem for the smallest view counts (V = 2 at N = 1 crop: 12 480 problems per step whose
+// ~50 block-wide iterations are pure barrier latency with four warps; with one warp a barrier is free and 16 problems share
+// an SM).
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 512 ? 1 : 4) mta_fast_kernel(const MtaDev a) {
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64 ? 8 : 16))) mta_fast_kernel(const MtaDev a) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float mta_smem[];
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA, ldx = a.ldx, ldp = a.ldp;
@@ -957,9 +960,20 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     dim3 fgrid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
     const size_t fsmem = mf_smem_bytes(V, C, D);
     if (V <= 32) {
-      cudaError_t e = ensure_dynamic_smem(mta_fast_kernel<128>, fsmem);
-      if (e != cudaSuccess) return e;
-      mta_fast_kernel<128><<<fgrid, 128, fsmem, stream>>>(a);
+      static int nt_env = -1;     // A/B: JCB_MTA_NT = 32 | 64 | 128 forces the small-V thread count
+      if (nt_env < 0) { const char* e = getenv("JCB_MTA_NT"); nt_env = e ? atoi(e) : 0; }
+      const int nt = nt_env ? nt_env : (V <= 4 ? 32 : (V <= 12 ? 64 : 128));
+      cudaError_t e = cudaSuccess;
+      if (nt == 32) {
+        if ((e = ensure_dynamic_smem(mta_fast_kernel<32>, fsmem)) != cudaSuccess) return e;
+        mta_fast_kernel<32><<<fgrid, 32, fsmem, stream>>>(a);
+      } else if (nt == 64) {
+        if ((e = ensure_dynamic_smem(mta_fast_kernel<64>, fsmem)) != cudaSuccess) return e;
+        mta_fast_kernel<64><<<fgrid, 64, fsmem, stream>>>(a);
+      } else {
+        if ((e = ensure_dynamic_smem(mta_fast_kernel<128>, fsmem)) != cudaSuccess) return e;
+        mta_fast_kernel<128><<<fgrid, 128, fsmem, stream>>>(a);
+      }
     } else {
       cudaError_t e = ensure_dynamic_smem(mta_fast_kernel<MF_THREADS>, MTA_SMEM_LIMIT);
       if (e != cudaSuccess) return e;
