@@ -1333,7 +1333,7 @@ int jcb_mta(jcb_ctx* ctx, const float* feats_dev, const float* text_dev, int64_t
   MtaSet set{feats_dev, text_dev, out_mode_dev, out_logits_dev};
   LAUNCH_P(ctx, JCB_KC_MTA, mta_flops(n_images, n_views, n_classes, dim), static_cast<double>(n_images) * (n_views + 1) * dim * 4,
            launch_mta(&set, 1, n_images, n_views, n_classes, dim, to_params(params),
-                      scratch ? static_cast<float*>(ctx->ws) : nullptr, ctx->stream));
+                      scratch ? static_cast<float*>(ctx->ws) : nullptr, ctx->stream, ctx->dev_status, ctx->num_sms));
   return JCB_OK;
 }
 
@@ -1440,7 +1440,7 @@ int pipeline_enqueue(jcb_vit* vit, jcb_vit* vit_zs, const jcb_pipeline_args* a) 
   MtaSet sets[3] = {{feats, a->text_pt_t_dev, m_pt, nullptr},
                     {feats, a->text_hand_t_dev, m_hand, nullptr},
                     {feats_zs, a->text_zs_t_dev, m_zs, nullptr}};
-  LAUNCH_P(ctx, JCB_KC_MTA, 3.0 * mta_flops(I, V, C, E), 3.0 * I * (V + 1) * E * 4, launch_mta(sets, 3, I, V, C, E, MtaParams(), scratch, ctx->stream));
+  LAUNCH_P(ctx, JCB_KC_MTA, 3.0 * mta_flops(I, V, C, E), 3.0 * I * (V + 1) * E * 4, launch_mta(sets, 3, I, V, C, E, MtaParams(), scratch, ctx->stream, ctx->dev_status, ctx->num_sms));
   // Channel_LP, logit_normalize, fusion, top-k                        test.py:1710-1738
   HeadArgs h;
   h.m_pt = m_pt; h.m_hand = m_hand; h.m_zs = m_zs;

@@ -133,8 +133,10 @@ struct MtaSet {
 // bytes of global scratch launch_mta needs (0 when a problem fits in shared memory)
 size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D);
 // n_sets independent (feats, text) problems per image in one launch: grid = (I, n_sets)
+// dev_status + num_sms given: softmax(100 X T) runs as a bf16 x 3-limb GEMM on the tensor cores (launch_gemm) for
+// C <= 512; otherwise (or JCB_MTA_PROBS=simt) the fp32 SIMT kernel
 cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, int D, const MtaParams& p,
-                       float* scratch, cudaStream_t stream);
+                       float* scratch, cudaStream_t stream, int* dev_status = nullptr, int num_sms = 0);
 
 enum HeadScore : int { SCORE_LOGITS = 0, SCORE_CS = 1, SCORE_CS1 = 2, SCORE_CS2 = 3, SCORE_CS3 = 4, SCORE_CS4 = 5, SCORE_CS5 = 6, SCORE_COUNT = 7 };
 // Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  cudaFuncSetAttribute acts on the current

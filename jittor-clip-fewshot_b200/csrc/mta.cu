@@ -202,6 +202,76 @@ __global__ void __launch_bounds__(256, 1) mta_probs_kernel(const ProbsDev a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The same probabilities on the tensor cores (round 2): logits = 100 X T is a [rows, 512] x [512, 403] contraction per
+// text bank that must keep fp32 accuracy (bf16 logits move the modes by 1e-3).  Every fp32 value is split into three
+// bf16 limbs, x = x1 + x2 + x3 (24 significand bits, fp32's exponent range -- no underflow of the small limbs, which is
+// what rules fp16 limbs out), and the six limb products of weight >= 2^-16,
+//     x.t ~= x1 t1 + x1 t2 + x1 t3 + x2 t1 + x2 t2 + x3 t1        (dropped: <= 2^-24 relative),
+// are ONE bf16 GEMM with the limbs concatenated along K:  A' = [X1 X1 X1 X2 X2 X3],  B' = [T1 T2 T3 T1 T2 T1],
+// K' = 6 D = 3072 -- the tower's own tcgen05 kernel (gemm.cu, fp32 accumulation in TMEM, fp32 output), 26 GFLOP per bank
+// instead of 8.6 GFLOP of fp32 SIMT FMAs at a third of the SIMT peak.  A row softmax kernel finishes.
+__device__ __forceinline__ void split3(float x, uint16_t (&l)[3]) {
+  const __nv_bfloat16 a = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(a);                     // exact
+  const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b);                    // exact
+  const __nv_bfloat16 c = __float2bfloat16_rn(r2);
+  l[0] = __bfloat16_as_ushort(a); l[1] = __bfloat16_as_ushort(b); l[2] = __bfloat16_as_ushort(c);
+}
+// X [rows, D] fp32 -> A' [rows, 6 D] bf16, blocks (1, 1, 1, 2, 2, 3)
+__global__ void __launch_bounds__(256) mta_split_x_kernel(const float* __restrict__ X, long long rows, int D,
+                                                          uint16_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * D) return;
+  const long long r = i / D;
+  const int d = static_cast<int>(i - r * D);
+  uint16_t l[3];
+  split3(X[i], l);
+  uint16_t* o = out + r * 6 * D + d;
+  o[0] = l[0]; o[D] = l[0]; o[2 * D] = l[0]; o[3 * D] = l[1]; o[4 * D] = l[1]; o[5 * D] = l[2];
+}
+// T^T [D, C] fp32 (the orientation solve_mta receives) -> B' [CP, 6 D] bf16, blocks (1, 2, 3, 1, 2, 1); rows >= C zero
+__global__ void __launch_bounds__(256) mta_split_t_kernel(const float* __restrict__ Tt, int C, int CP, int D,
+                                                          uint16_t* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= CP * D) return;
+  const int d = i / CP, c = i - d * CP;          // threads along c: coalesced reads of Tt
+  uint16_t l[3] = {0, 0, 0};
+  if (c < C) split3(Tt[static_cast<long long>(d) * C + c], l);
+  uint16_t* o = out + static_cast<long long>(c) * 6 * D + d;
+  o[0] = l[0]; o[D] = l[1]; o[2 * D] = l[2]; o[3 * D] = l[0]; o[4 * D] = l[1]; o[5 * D] = l[0];
+}
+// P[r, :] = softmax(scale * L[r, 0:C]) (test.py:1411), one warp per row; L has leading dimension CP
+__global__ void __launch_bounds__(256) mta_softmax_rows_kernel(const float* __restrict__ L, long long rows, int C, int CP,
+                                                               float scale, float* __restrict__ P) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* l = L + r * CP;
+  float v[16];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = lane + 32 * j;
+    v[j] = c < C ? l[c] * scale : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = (lane + 32 * j < C) ? expf(v[j] - mx) : 0.f;
+    sum += v[j];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (lane + 32 * j < C) P[r * C + lane + 32 * j] = v[j] * inv;
+}
+constexpr int TCP_CP = 512;   // class count padded to the GEMM's N granularity (C <= 512)
+
+// ---------------------------------------------------------------------------------------------------
 // Large view counts (V = 513 in the reference's test.py: 512 crops + the centre view).  One CTA per (image, bank) cannot
 // hold the problem on chip, and doing its two V x V x {C, D} Gram matrices and the V^3 rank select inside that one CTA
 // took 76 ms per 16 images (3 banks) -- 48 CTAs on 148 SMs.  Those three pieces are batched over ALL problems here:
@@ -902,9 +972,19 @@ static bool mta_fast_fits(int V, int C, int D) {
   return mta_use_probs_kernel(C, D) && D % 128 == 0 && mf_smem_bytes(V, C, D) <= MTA_SMEM_LIMIT && mta_fast_enabled();
 }
 
+// bytes of the tensor-core probabilities path for `rows` view rows per bank and `n_sets` banks: A' limbs (one copy per
+// distinct feature tensor, at most n_sets), B' limbs and the fp32 logits
+static size_t tcp_bytes(size_t n_sets, size_t rows, int D) {
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  return n_sets * (up(rows * 6 * D * 2) + up(static_cast<size_t>(TCP_CP) * 6 * D * 2) + up(rows * TCP_CP * 4));
+}
+static bool mta_tc_probs_possible(int C, int D) { return C <= TCP_CP && C <= 512 && D % 64 == 0 && D >= 64; }
+
 size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D) {
   size_t b = 0;
   if (mta_use_probs_kernel(C, D)) b += (static_cast<size_t>(n_problems) * V * C * sizeof(float) + 255) / 256 * 256;
+  // (n_problems = n_sets * images: n_sets banks of n_problems / n_sets * V rows each = n_problems * V rows in total)
+  if (mta_use_probs_kernel(C, D) && mta_tc_probs_possible(C, D)) b += tcp_bytes(1, static_cast<size_t>(n_problems) * V, D) + 3 * 4 * 256 + tcp_bytes(MTA_MAX_SETS, 0, D);
   if (!mta_fast_fits(V, C, D) && !mta_fits_smem(V, C, D)) {
     const long long be = big_elems(V, C, D, V | 1), bp = big_pre_elems(V, V | 1);
     b += static_cast<size_t>(n_problems) * static_cast<size_t>(be > bp ? be : bp) * sizeof(float);
@@ -913,7 +993,7 @@ size_t mta_scratch_bytes(int64_t n_problems, int V, int C, int D) {
 }
 
 cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, int D, const MtaParams& p,
-                       float* scratch, cudaStream_t stream) {
+                       float* scratch, cudaStream_t stream, int* dev_status, int num_sms) {
   if (V < 1 || C < 1 || D < 32 || D % 32 != 0 || D > 1024) return cudaErrorInvalidValue;
   if (V > 2048) return cudaErrorInvalidValue;  // small state must stay well inside shared memory
   if (n_sets < 1 || n_sets > MTA_MAX_SETS) return cudaErrorInvalidValue;
@@ -936,20 +1016,66 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
   if (mta_use_probs_kernel(C, D)) {
     if (scratch == nullptr) return cudaErrorInvalidValue;
     const size_t p_bytes = (static_cast<size_t>(n_sets) * I * V * C * sizeof(float) + 255) / 256 * 256;
-    ProbsDev pd;
-    for (int s2 = 0; s2 < MTA_MAX_SETS; ++s2) pd.sets[s2] = a.sets[s2];
-    pd.rows = static_cast<long long>(I) * V;
-    pd.C = C; pd.D = D; pd.scale = 100.0f / p.temperature; pd.P = scratch;
-    {
-      cudaError_t e = ensure_dynamic_smem(mta_probs_kernel, PB_SMEM);
+    const long long rows = static_cast<long long>(I) * V;
+    static int tc_env = -1;   // A/B: JCB_MTA_PROBS=simt keeps the fp32 SIMT kernel
+    if (tc_env < 0) { const char* e = getenv("JCB_MTA_PROBS"); tc_env = (e && e[0] == 's') ? 0 : 1; }
+    // taken at EVERY batch size: a row's probabilities must not depend on how many other rows share the launch (the
+    // path's pass-size and batch-split invariance is bit-exact); at one image the three extra launches per bank cost ~40 us
+    const bool tc = tc_env && dev_status != nullptr && num_sms > 0 && mta_tc_probs_possible(C, D);
+    if (tc) {
+      auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+      uint8_t* w = reinterpret_cast<uint8_t*>(scratch) + p_bytes;     // behind P; sized by mta_scratch_bytes
+      const size_t a_b = up(static_cast<size_t>(rows) * 6 * D * 2), b_b = up(static_cast<size_t>(TCP_CP) * 6 * D * 2);
+      const size_t l_b = up(static_cast<size_t>(rows) * TCP_CP * 4);
+      const float* split_of[MTA_MAX_SETS];
+      uint16_t* a_of[MTA_MAX_SETS];
+      int n_split = 0;
+      for (int s2 = 0; s2 < n_sets; ++s2) {
+        // banks that share a feature tensor (prompt-tuned and hand-crafted text on the same tower) share its limbs
+        uint16_t* ap = nullptr;
+        for (int q = 0; q < n_split; ++q)
+          if (split_of[q] == sets[s2].feats) ap = a_of[q];
+        if (!ap) {
+          ap = reinterpret_cast<uint16_t*>(w);
+          w += a_b;
+          split_of[n_split] = sets[s2].feats;
+          a_of[n_split++] = ap;
+          const long long n = rows * D;
+          mta_split_x_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sets[s2].feats, rows, D, ap);
+        }
+        uint16_t* bp = reinterpret_cast<uint16_t*>(w);
+        w += b_b;
+        float* lg = reinterpret_cast<float*>(w);
+        w += l_b;
+        mta_split_t_kernel<<<(TCP_CP * D + 255) / 256, 256, 0, stream>>>(sets[s2].text, C, TCP_CP, D, bp);
+        GemmArgs g;
+        g.A = reinterpret_cast<const __nv_bfloat16*>(ap); g.B = reinterpret_cast<const __nv_bfloat16*>(bp);
+        g.lda = 6 * D; g.ldb = 6 * D; g.M = static_cast<int>(rows); g.N = TCP_CP; g.K = 6 * D;
+        g.bias = nullptr; g.epilogue = EPI_F32; g.out = lg; g.ldo = TCP_CP; g.f16 = 0;
+        cudaError_t e = launch_gemm(g, dev_status, num_sms, stream);
+        if (e != cudaSuccess) return e;
+        mta_softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+            lg, rows, C, TCP_CP, 100.0f / p.temperature, scratch + static_cast<long long>(s2) * rows * C);
+      }
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    } else {
+      ProbsDev pd;
+      for (int s2 = 0; s2 < MTA_MAX_SETS; ++s2) pd.sets[s2] = a.sets[s2];
+      pd.rows = rows;
+      pd.C = C; pd.D = D; pd.scale = 100.0f / p.temperature; pd.P = scratch;
+      {
+        cudaError_t e = ensure_dynamic_smem(mta_probs_kernel, PB_SMEM);
+        if (e != cudaSuccess) return e;
+      }
+      dim3 pgrid(static_cast<unsigned>((pd.rows + PB_ROWS - 1) / PB_ROWS), static_cast<unsigned>(n_sets));
+      mta_probs_kernel<<<pgrid, 256, PB_SMEM, stream>>>(pd);
+      cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
     }
-    dim3 pgrid(static_cast<unsigned>((pd.rows + PB_ROWS - 1) / PB_ROWS), static_cast<unsigned>(n_sets));
-    mta_probs_kernel<<<pgrid, 256, PB_SMEM, stream>>>(pd);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     a.P = scratch;
-    scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + p_bytes);
+    scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + p_bytes +
+                                       (mta_tc_probs_possible(C, D) ? tcp_bytes(static_cast<size_t>(n_sets), static_cast<size_t>(rows), D) : 0));
   }
   if (a.P != nullptr && D % 128 == 0 && mf_smem_bytes(V, C, D) <= MTA_SMEM_LIMIT && mta_fast_enabled()) {
     a.ldx = mf_pad(D);
