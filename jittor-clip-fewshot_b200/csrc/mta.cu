@@ -40,6 +40,12 @@ struct MtaDev {
   // pre-pass kernels (mta_gram_big_kernel, mta_bw_big_kernel); this kernel is then only the iterative solver
   const float* A_pre;   // [n_sets * I, V, ldA] or nullptr
   const float* bw_pre;  // [n_sets * I, V] or nullptr
+  // fast kernel: text banks that share ONE feature tensor (prompt-tuned and hand-crafted text on the same tower; all
+  // three in the single-tower pipeline) are solved by the same CTA: the view embeddings are brought on chip, multiplied
+  // into their Gram matrix and rank-selected for the bandwidths once per image instead of once per bank
+  int n_groups, max_group;   // max_group = the largest group_count: affinity slots in shared memory
+  int group_count[MTA_MAX_SETS];
+  int group_sets[MTA_MAX_SETS][MTA_MAX_SETS];
 };
 
 template <int NW>
@@ -786,9 +792,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA, ldx = a.ldx, ldp = a.ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long img = blockIdx.x;
-  const MtaSet& set = a.sets[blockIdx.y];
-  const float* __restrict__ Xg = set.feats + img * V * D;
-  const float* __restrict__ Tt = set.text;
+  const int group = blockIdx.y;
+  const int nb = a.group_count[group];                   // banks solved by this CTA (they share the feature tensor)
+  const float* __restrict__ Xg = a.sets[a.group_sets[group][0]].feats + img * V * D;
 
   float* s_mode = mta_smem;           // [D]
   float* s_new = s_mode + D;          // [D]
@@ -800,23 +806,25 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64
   float* s_red = s_sq + V;            // [32]
   float* big = s_red + 32;
   big = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(big) + 15) & ~static_cast<uintptr_t>(15));
-  float* R = big;                                        // P [V, ldp], later X [V, ldx]
+  float* R = big;                                        // P [V, ldp] of one bank at a time, later X [V, ldx]
   const int r_elems = V * (ldp > ldx ? ldp : ldx);
-  float* A = R + r_elems;                                // affinity [V, ldA]
-  float* Dm = A + ((V * ldA + 3) & ~3);                  // Gram of X, then the pairwise distances [V, ldA]
+  const int a_elems = (V * ldA + 3) & ~3;
+  float* A_all = R + r_elems;                            // affinities [nb][V, ldA]
+  float* Dm = A_all + a.max_group * a_elems;             // Gram of X, then the pairwise distances [V, ldA]
 
-  // ---- 1+2. this problem's V x C block of softmax(100 X T) (mta_probs_kernel), zero padded to ldp columns
-  {
-    const float* Pg = a.P + (static_cast<long long>(blockIdx.y) * a.I + img) * V * C;
+  for (int b = 0; b < nb; ++b) {
+    // ---- 1+2. this problem's V x C block of softmax(100 X T), zero padded to ldp columns
+    const int si = a.group_sets[group][b];
+    const float* Pg = a.P + (static_cast<long long>(si) * a.I + img) * V * C;
     for (int i = tid; i < V * ldp; i += NT) {
       const int v = i / ldp, c = i - v * ldp;
       R[i] = c < C ? __ldg(Pg + v * C + c) : 0.f;
     }
+    __syncthreads();
+    // ---- 3. affinity A = P P^T                                    (test.py:1411)
+    mf_gram<NT>(R, ldp, ldp >> 2, V, A_all + b * a_elems, ldA);
+    __syncthreads();
   }
-  __syncthreads();
-  // ---- 3. affinity A = P P^T                                    (test.py:1411)
-  mf_gram<NT>(R, ldp, ldp >> 2, V, A, ldA);
-  __syncthreads();
   // ---- 4. the view embeddings replace P on chip
   for (int i = tid; i < V * (D >> 2); i += NT) {
     const int v = i / (D >> 2), c4 = i - v * (D >> 2);
@@ -851,92 +859,99 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64
     acc = warp_sum(acc);
     if (lane == 0) s_bw[i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
   }
-  // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
-  for (int i = tid; i < V; i += NT) s_y[i] = 1.0f / static_cast<float>(V);
-  for (int d = tid; d < D; d += NT) s_mode[d] = X[d];
-  __syncthreads();
-
   const float inv_lambda_y = 1.0f / a.p.lambda_y;
-  for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
-    mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);                // :1426
-    for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
-      for (int i = warp; i < V; i += NW) {                   // z = (rho + lambda_q A y) / lambda_y
-        float s = 0.f;
-        for (int j = lane; j < V; j += 32) s = fmaf(A[i * ldA + j], s_y[j], s);
-        s = warp_sum(s);
-        if (lane == 0) s_z[i] = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s);
-      }
-      __syncthreads();
-      if (warp == 0) {                                             // y <- softmax(z), ||y_old - y||
-        float mx = -INFINITY;
-        for (int i = lane; i < V; i += 32) mx = fmaxf(mx, s_z[i]);
-        mx = warp_max(mx);
-        float zs = 0.f;
-        for (int i = lane; i < V; i += 32) {
-          const float e = expf(s_z[i] - mx);
-          s_z[i] = e;
-          zs += e;
-        }
-        zs = warp_sum(zs);
-        const float inv = 1.0f / zs;
-        float diff = 0.f;
-        for (int i = lane; i < V; i += 32) {
-          const float yn = s_z[i] * inv;
-          const float t = s_y[i] - yn;
-          diff = fmaf(t, t, diff);
-          s_y[i] = yn;
-        }
-        diff = warp_sum(diff);
-        if (lane == 0) s_red[31] = diff;
-      }
-      __syncthreads();
-      if (sqrtf(s_red[31]) < a.p.th || it >= a.p.max_iter) break;  // :1436
-    }
-    for (int it = 1;; ++it) {                                      // mode loop :1443-1453
-      mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);              // :1446
-      float nrm = 0.f;
-      for (int d = tid; d < D; d += NT) {
-        float s = 0.f, wsum = 0.f;
-        for (int i = 0; i < V; ++i) {
-          const float w = s_dens[i] * s_y[i];                      // :1447
-          wsum += w;
-          s = fmaf(w, X[i * ldx + d], s);
-        }
-        s = s / wsum;                                              // :1448
-        s_new[d] = s;
-        nrm = fmaf(s, s, nrm);
-      }
-      nrm = mf_block_sum<NT>(nrm, s_red);
-      const float inv = 1.0f / sqrtf(nrm);                         // :1449
-      float diff = 0.f;
-      for (int d = tid; d < D; d += NT) {
-        const float m = s_new[d] * inv;
-        const float t = s_mode[d] - m;
-        diff = fmaf(t, t, diff);
-        s_new[d] = m;
-      }
-      diff = mf_block_sum<NT>(diff, s_red);
-      for (int d = tid; d < D; d += NT) s_mode[d] = s_new[d];
-      __syncthreads();
-      if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
-    }
-  }
+  for (int b = 0; b < nb; ++b) {
+    const MtaSet& set = a.sets[a.group_sets[group][b]];
+    const float* __restrict__ Tt = set.text;
+    const float* A = A_all + b * a_elems;
+    __syncthreads();   // the previous bank's outputs have been read from s_mode; s_bw is complete
+    // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
+    for (int i = tid; i < V; i += NT) s_y[i] = 1.0f / static_cast<float>(V);
+    for (int d = tid; d < D; d += NT) s_mode[d] = X[d];
+    __syncthreads();
 
-  // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
-  for (int d = tid; d < D; d += NT) set.out_mode[img * D + d] = s_mode[d];
-  if (set.out_logits) {
-    for (int c = tid; c < C; c += NT) {
-      float s = 0.f;
-      for (int d = 0; d < D; ++d) s = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s);
-      set.out_logits[img * C + c] = s * 100.0f;
+    for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
+      mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);                // :1426
+      for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
+        for (int i = warp; i < V; i += NW) {                   // z = (rho + lambda_q A y) / lambda_y
+          float s2 = 0.f;
+          for (int j = lane; j < V; j += 32) s2 = fmaf(A[i * ldA + j], s_y[j], s2);
+          s2 = warp_sum(s2);
+          if (lane == 0) s_z[i] = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s2);
+        }
+        __syncthreads();
+        if (warp == 0) {                                             // y <- softmax(z), ||y_old - y||
+          float mx = -INFINITY;
+          for (int i = lane; i < V; i += 32) mx = fmaxf(mx, s_z[i]);
+          mx = warp_max(mx);
+          float zs = 0.f;
+          for (int i = lane; i < V; i += 32) {
+            const float e = expf(s_z[i] - mx);
+            s_z[i] = e;
+            zs += e;
+          }
+          zs = warp_sum(zs);
+          const float inv = 1.0f / zs;
+          float diff = 0.f;
+          for (int i = lane; i < V; i += 32) {
+            const float yn = s_z[i] * inv;
+            const float t = s_y[i] - yn;
+            diff = fmaf(t, t, diff);
+            s_y[i] = yn;
+          }
+          diff = warp_sum(diff);
+          if (lane == 0) s_red[31] = diff;
+        }
+        __syncthreads();
+        if (sqrtf(s_red[31]) < a.p.th || it >= a.p.max_iter) break;  // :1436
+      }
+      for (int it = 1;; ++it) {                                      // mode loop :1443-1453
+        mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);              // :1446
+        float nrm = 0.f;
+        for (int d = tid; d < D; d += NT) {
+          float s2 = 0.f, wsum = 0.f;
+          for (int i = 0; i < V; ++i) {
+            const float w = s_dens[i] * s_y[i];                      // :1447
+            wsum += w;
+            s2 = fmaf(w, X[i * ldx + d], s2);
+          }
+          s2 = s2 / wsum;                                            // :1448
+          s_new[d] = s2;
+          nrm = fmaf(s2, s2, nrm);
+        }
+        nrm = mf_block_sum<NT>(nrm, s_red);
+        const float inv = 1.0f / sqrtf(nrm);                         // :1449
+        float diff = 0.f;
+        for (int d = tid; d < D; d += NT) {
+          const float m = s_new[d] * inv;
+          const float t = s_mode[d] - m;
+          diff = fmaf(t, t, diff);
+          s_new[d] = m;
+        }
+        diff = mf_block_sum<NT>(diff, s_red);
+        for (int d = tid; d < D; d += NT) s_mode[d] = s_new[d];
+        __syncthreads();
+        if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
+      }
+    }
+
+    // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
+    for (int d = tid; d < D; d += NT) set.out_mode[img * D + d] = s_mode[d];
+    if (set.out_logits) {
+      for (int c = tid; c < C; c += NT) {
+        float s2 = 0.f;
+        for (int d = 0; d < D; ++d) s2 = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s2);
+        set.out_logits[img * C + c] = s2 * 100.0f;
+      }
     }
   }
 }
 
-size_t mf_smem_bytes(int V, int C, int D) {
+size_t mf_smem_bytes(int V, int C, int D, int banks = 1) {
   const int ldx = mf_pad(D), ldp = mf_pad(C), ldA = V | 1;
   const size_t small = sizeof(float) * (2 * D + 5 * V + 32) + 16;
-  const size_t bigf = static_cast<size_t>(V) * (ldp > ldx ? ldp : ldx) + 2 * static_cast<size_t>((V * ldA + 3) & ~3);
+  // P / X region + one affinity per bank the CTA solves + the distance matrix
+  const size_t bigf = static_cast<size_t>(V) * (ldp > ldx ? ldp : ldx) + (banks + 1) * static_cast<size_t>((V * ldA + 3) & ~3);
   return small + bigf * sizeof(float);
 }
 
@@ -1083,8 +1098,23 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     a.in_smem = 1;
     a.scratch = nullptr;
     a.scratch_stride = 0;
-    dim3 fgrid(static_cast<unsigned>(I), static_cast<unsigned>(n_sets));
-    const size_t fsmem = mf_smem_bytes(V, C, D);
+    a.n_groups = 0;
+    for (int s2 = 0; s2 < n_sets; ++s2) {
+      int g = -1;
+      for (int q = 0; q < a.n_groups; ++q)
+        if (sets[a.group_sets[q][0]].feats == sets[s2].feats) g = q;
+      if (g < 0) { g = a.n_groups++; a.group_count[g] = 0; }
+      a.group_sets[g][a.group_count[g]++] = s2;
+    }
+    a.max_group = 1;
+    for (int q = 0; q < a.n_groups; ++q) a.max_group = a.group_count[q] > a.max_group ? a.group_count[q] : a.max_group;
+    if (mf_smem_bytes(V, C, D, a.max_group) > MTA_SMEM_LIMIT) {   // no room for several affinities (V > 65): one bank per CTA
+      a.n_groups = n_sets;
+      a.max_group = 1;
+      for (int s2 = 0; s2 < n_sets; ++s2) { a.group_count[s2] = 1; a.group_sets[s2][0] = s2; }
+    }
+    dim3 fgrid(static_cast<unsigned>(I), static_cast<unsigned>(a.n_groups));
+    const size_t fsmem = mf_smem_bytes(V, C, D, a.max_group);
     if (V <= 32) {
       static int nt_env = -1;     // A/B: JCB_MTA_NT = 32 | 64 | 128 forces the small-V thread count
       if (nt_env < 0) { const char* e = getenv("JCB_MTA_NT"); nt_env = e ? atoi(e) : 0; }
