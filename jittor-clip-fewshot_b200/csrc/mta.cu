@@ -1108,7 +1108,16 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
     }
     a.max_group = 1;
     for (int q = 0; q < a.n_groups; ++q) a.max_group = a.group_count[q] > a.max_group ? a.group_count[q] : a.max_group;
-    if (mf_smem_bytes(V, C, D, a.max_group) > MTA_SMEM_LIMIT) {   // no room for several affinities (V > 65): one bank per CTA
+    // Sharing pays when there are more problems than SMs (a wave of one-bank CTAs would not fit anyway); with a handful
+    // of images (the reference's one-image-per-call loop) three CTAs in parallel beat one CTA doing three solves in a
+    // row.  Either way a bank's arithmetic is the same instruction sequence: the results are bit-identical.
+    int sms = num_sms;
+    if (sms <= 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (mf_smem_bytes(V, C, D, a.max_group) > MTA_SMEM_LIMIT || I * n_sets <= sms) {   // (or no room for several affinities: V > 65)
       a.n_groups = n_sets;
       a.max_group = 1;
       for (int s2 = 0; s2 < n_sets; ++s2) { a.group_count[s2] = 1; a.group_sets[s2][0] = s2; }

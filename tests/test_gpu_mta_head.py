@@ -303,3 +303,26 @@ def test_small_calls_are_served_from_cuda_graphs(jb, cuda_dev):
     finally:
         ctx.set_operand_type(prev)
     assert torch.equal(hp.evaluate_base(a), want_a)
+
+
+def test_mta_is_bit_identical_across_batch_splits(jb, cuda_dev):
+    """solve_mta for 200 images x 3 banks in one call (one CTA per image solves all banks that share its feature
+    tensor; probabilities from the tensor-core GEMM) equals the same images in calls of 1, 7 and 50 (one bank per CTA
+    below the SM count), bit for bit: a row's result never depends on what else is in the launch."""
+    sd = jb.synth.make_vit_state_dict(seed=4, layers=1)
+    model = jb.jclip.build_model(sd)
+    Ts = _texts(jb, 3)
+    lp = jb.Channel_LP()
+    lp.scale1.data, lp.bias1.data, lp.fc.weight.data, lp.fc.bias.data = jb.synth.make_head(2, Ts[2].numpy())
+    hp = jb.HotPath(model, jb.TextBank(Ts[0], Ts[1], Ts[2], cuda_dev), lp, rank_by="cs5")
+    imgs = (jb.synth.make_views_torch(51, 200, 5, cuda_dev) * 255).round_().to(torch.uint8)
+    ctx = jb.get_context(cuda_dev)
+    ctx.set_graphs(False)
+    try:
+        topk, feats, scores = hp.evaluate_base(imgs, return_feats=True, return_scores=True)
+        for step in (1, 7, 50):
+            for lo in range(0, 200, step * 4):          # a sample of the splits
+                t, f, sc = hp.evaluate_base(imgs[lo:lo + step].contiguous(), return_feats=True, return_scores=True)
+                assert torch.equal(t, topk[lo:lo + step]) and torch.equal(sc, scores[lo:lo + step]), (step, lo)
+    finally:
+        ctx.set_graphs(True)

@@ -119,9 +119,13 @@ def test_lora_update_refreshes_packed_weights(jb, cuda_dev, tower):
     x = torch.from_numpy(jb.synth.make_views(6, 1, 2).reshape(2, 3, 224, 224)).to(cuda_dev)
     f0 = model.visual(x, apply_clip_norm=True, normalize=True).clone()      # B = 0 -> no-op adapters
     rng = np.random.default_rng(0)
-    layers[3].q_proj.w_lora_B.data = (0.05 * rng.standard_normal((768, 4))).astype(np.float32)
+    # apply_lora draws A from an unseeded generator (as the reference's kaiming_uniform_ does): pin it, and make B large
+    # enough that the effect of ONE adapter on the unit-norm embedding is far above rounding (it was marginal at 0.05)
+    layers[3].q_proj.w_lora_A.data = rng.uniform(-768 ** -0.5, 768 ** -0.5, (4, 768)).astype(np.float32)
+    f0 = model.visual(x, apply_clip_norm=True, normalize=True).clone()      # still a no-op: B = 0
+    layers[3].q_proj.w_lora_B.data = (0.5 * rng.standard_normal((768, 4))).astype(np.float32)
     f1 = model.visual(x, apply_clip_norm=True, normalize=True)
-    assert not torch.allclose(f0, f1, atol=1e-4)
+    assert (f0 - f1).abs().max() > 1e-4
     layers[3].q_proj.w_lora_B.data = np.zeros((768, 4), np.float32)
     f2 = model.visual(x, apply_clip_norm=True, normalize=True)
     assert torch.equal(f0, f2)
