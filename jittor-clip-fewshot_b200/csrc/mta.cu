@@ -1117,7 +1117,9 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    if (mf_smem_bytes(V, C, D, a.max_group) > MTA_SMEM_LIMIT || I * n_sets <= sms) {   // (or no room for several affinities: V > 65)
+    static int group_env = -1;   // A/B: JCB_MTA_GROUP=0 keeps one bank per CTA
+    if (group_env < 0) { const char* e = getenv("JCB_MTA_GROUP"); group_env = (e && e[0] == '0') ? 0 : 1; }
+    if (mf_smem_bytes(V, C, D, a.max_group) > MTA_SMEM_LIMIT || I * n_sets <= sms || !group_env) {   // (or no room for several affinities: V > 65)
       a.n_groups = n_sets;
       a.max_group = 1;
       for (int s2 = 0; s2 < n_sets; ++s2) { a.group_count[s2] = 1; a.group_sets[s2][0] = s2; }
@@ -1140,6 +1142,8 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
         mta_fast_kernel<128><<<fgrid, 128, fsmem, stream>>>(a);
       }
     } else {
+      // (A/B this round: the same solver with 128 threads per CTA takes 2.3x as long per bank -- 3.25 vs 1.61 ms per step
+      // un-grouped -- so running the banks of a CTA concurrently on 128-thread groups would gain < 25 % of the iterations)
       cudaError_t e = ensure_dynamic_smem(mta_fast_kernel<MF_THREADS>, MTA_SMEM_LIMIT);
       if (e != cudaSuccess) return e;
       mta_fast_kernel<MF_THREADS><<<fgrid, MF_THREADS, fsmem, stream>>>(a);
