@@ -511,6 +511,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                   const uint64_t h2 = f2_mul(x2, k05);
                   float t0, t1;
                   f2_unpack(f2_mul(x2, k851), t0, t1);
+                  // (A/B round 2: tanh.approx.f16x2 -- one MUFU op per two elements at the same 2^-11 relative error -- needs
+                  // three conversions per pair around it and ran c_fc at 22.5 instead of 20.7 ms per step: the epilogue's
+                  // instruction count, not its MUFU count, is what the power-capped step feels)
                   x2 = f2_fma(h2, f2_pack(tanh_approx(t0), tanh_approx(t1)), h2);
                 }
                 f2_unpack(x2, f[2 * e], f[2 * e + 1]);
