@@ -298,12 +298,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       __syncwarp();
-      // QuickGELU epilogues work on h = x / 2 (x sigmoid(1.702 x) = h + h tanh(1.702 h)): the factor 1/2 rides in the
-      // additive terms and in the row scale -- exact in binary floating point, one multiply per element less
-      constexpr float HALF = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LNFOLD_GELU_BF16) ? 0.5f : 1.0f;
       for (int i = lane; i < CW; i += 32) {
-        s_bias[i] = p.bias ? HALF * __ldg(p.bias + n_blk * BN + col0 + i) : 0.0f;
-        if (is_lnfold(EPI)) s_csum[i] = HALF * __ldg(p.colsum + n_blk * BN + col0 + i);
+        s_bias[i] = p.bias ? __ldg(p.bias + n_blk * BN + col0 + i) : 0.0f;
+        if (is_lnfold(EPI)) s_csum[i] = __ldg(p.colsum + n_blk * BN + col0 + i);
       }
       __syncwarp();
       const int row0e = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M + q * 32;   // this warp's 32 rows
@@ -448,10 +445,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           ln_r = 1.0f / sqrtf(var + 1e-5f);
           ln_nmr = -mean * ln_r;
         }
-        // GELU: r2 carries the 1/2 as well (the additive terms were halved when they were staged)
-        const uint64_t r2 = GELU ? f2_pack(0.5f * ln_r, 0.5f * ln_r) : f2_pack(ln_r, ln_r), nmr2 = f2_pack(ln_nmr, ln_nmr);
-        const uint64_t k05 = f2_pack(0.5f, 0.5f), k1702 = f2_pack(1.702f, 1.702f);
-        (void)r2; (void)nmr2; (void)k05; (void)k1702;
+        const uint64_t r2 = f2_pack(ln_r, ln_r), nmr2 = f2_pack(ln_nmr, ln_nmr);
+        const uint64_t k05 = f2_pack(0.5f, 0.5f), k851 = f2_pack(0.851f, 0.851f);
+        (void)r2; (void)nmr2; (void)k05; (void)k851;
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted; the smem
         // staging holds GROUP chunks so the generic->async proxy fence (MEMBAR + ERRBAR, ~17 % of all
         // stall samples when issued per chunk) and the TMA issue happen once per GROUP chunks
@@ -508,16 +504,19 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
               for (int e = 0; e < 4; ++e) {   // two columns per instruction
                 const uint64_t a2 = f2_pack(__uint_as_float(cur[8 * j + 2 * e]), __uint_as_float(cur[8 * j + 2 * e + 1]));
-                uint64_t x2 = FOLD ? f2_fma(a2, r2, bb2[4 * j + e]) : (GELU ? f2_fma(a2, k05, bb2[4 * j + e]) : f2_add(a2, bb2[4 * j + e]));
+                uint64_t x2 = FOLD ? f2_fma(a2, r2, bb2[4 * j + e]) : f2_add(a2, bb2[4 * j + e]);
                 if (GELU) {
-                  // x * sigmoid(1.702 x)  (reference jclip/model.py:27) = h + h tanh(0.851 x), h = 0.5 x (x2 holds h here): one
-                  // MUFU op per element (tanh.approx, rel. error 2^-11: at the level of the 16-bit rounding of the output)
-                  const uint64_t h2 = x2;
+                  // x * sigmoid(1.702 x)  (reference jclip/model.py:27) = h + h tanh(0.851 x), h = 0.5 x: one MUFU op
+                  // per element (tanh.approx, rel. error 2^-11, below the bf16 rounding of the output)
+                  const uint64_t h2 = f2_mul(x2, k05);
                   float t0, t1;
-                  f2_unpack(f2_mul(h2, k1702), t0, t1);
+                  f2_unpack(f2_mul(x2, k851), t0, t1);
                   // (A/B round 2: tanh.approx.f16x2 -- one MUFU op per two elements at the same 2^-11 relative error -- needs
                   // three conversions per pair around it and ran c_fc at 22.5 instead of 20.7 ms per step: the epilogue's
-                  // instruction count, not its MUFU count, is what the power-capped step feels)
+                  // instruction count, not its MUFU count, is what the power-capped step feels.  The opposite experiment --
+                  // folding the 1/2 into the row scale and the staged additive terms, one multiply per element LESS,
+                  // bit-identical -- was slower too, 23.3-24.2 vs 22.6 ms on the same box, profiles/r02z_ab_gelu_epilogue.log:
+                  // this epilogue's schedule is a local optimum of ptxas, leave it alone)
                   x2 = f2_fma(h2, f2_pack(tanh_approx(t0), tanh_approx(t1)), h2);
                 }
                 f2_unpack(x2, f[2 * e], f[2 * e + 1]);
