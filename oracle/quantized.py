@@ -30,9 +30,11 @@ def _q(x, kind):
 
 @torch.no_grad()
 def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm=True, normalize=True,
-                             act="bf16", wgt="bf16", fold=True, centre=True, kinds=None):
+                             act="bf16", wgt="bf16", fold=True, centre=True, kinds=None, layer_kind=None):
     """kinds: optional per-tensor-class overrides of `act` / `wgt`, e.g. {"hidden": "bf16"}; classes: patch, conv_w,
     ln1_copy, qkv_w, qkv, p, attn, out_w, ln2_copy, fc_w, hidden, proj_w (per-class attribution of the deviation).
+    layer_kind: optional callable block index -> operand type of EVERY 16-bit tensor of that block (overrides act / wgt /
+    kinds inside the blocks; per-layer attribution).
     fold: LayerNorm folded into the consuming GEMM (JCB_LN_FOLD=2) instead of a rounded stand-alone LayerNorm.
     centre: the 16-bit copy of the residual row is x - shift, shift = the row's mean at the previous LayerNorm point
     (what the EPI_RESID_LNPREP_* epilogues write since round 2); False = the round-1 raw copy."""
@@ -86,7 +88,12 @@ def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm
     mean, r = ln_stats(x)
     x = (x - mean) * r * g("visual.ln_pre.weight") + g("visual.ln_pre.bias")
     B, S_, W = x.shape
+    base_A, base_W = A, Wk
     for i in range(L):
+        if layer_kind is not None:
+            A = Wk = (lambda name, k=layer_kind(i): k)
+        else:
+            A, Wk = base_A, base_W
         p = f"visual.transformer.resblocks.{i}."
         qkv = _q(ln_linear(x, g(p + "ln_1.weight"), g(p + "ln_1.bias"), g(p + "attn.in_proj_weight"),
                            g(p + "attn.in_proj_bias"), A("ln1_copy"), Wk("qkv_w")), A("qkv"))
