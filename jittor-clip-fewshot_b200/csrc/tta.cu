@@ -90,8 +90,6 @@ __device__ __forceinline__ void axis_coeffs(const AxisDev& a, int kind, int X, i
 enum TtaOut : int { OUT_U8 = 0, OUT_PATCH_BF16 = 1, OUT_PATCH_F16 = 2 };
 struct PatchEmit {        // OUT_PATCH_*: patch geometry and the per-channel affine map of the pixel (rowwise.cu im2col_kernel)
   int P, Gp;              // patch edge, patches per row (S / P)
-  int shift;              // log2(P) when P is a power of two (the word-wide body then splits x with a shift and a mask:
-                          // four run-time integer divisions per store were a third of its instructions), else -1
   float a[3], b[3];       // pixel -> a[c] * u8 + b[c]
 };
 
@@ -229,10 +227,6 @@ __device__ __forceinline__ void v_rows_fast(const uint8_t* __restrict__ t, long 
     int wt[KW];
 #pragma unroll
     for (int y = 0; y < KW; ++y) wt[y] = kk[yy * kmax + y];
-    // OUT_PATCH_*: everything of the destination that depends on the row only
-    const int yrow = y_begin + yy;
-    const int PP = pe.P * pe.P;
-    const long long row_off = OUT == OUT_U8 ? 0 : static_cast<long long>(yrow / pe.P) * pe.Gp * (3LL * PP) + (yrow % pe.P) * pe.P;
     const uint32_t* base = reinterpret_cast<const uint32_t*>(t + static_cast<long long>(ymin[yy]) * S);
     for (int e = lane; e < 3 * G; e += 32) {
       const int c = (e >= G) + (e >= 2 * G);
@@ -259,17 +253,16 @@ __device__ __forceinline__ void v_rows_fast(const uint8_t* __restrict__ t, long 
         reinterpret_cast<uint32_t*>(o + (static_cast<long long>(c) * S + y_begin + yy) * S)[go] = r4;
       } else {
         // the four pixels (x = 4 go .. 4 go + 3 of row y) are four consecutive columns of one patch row: one 8-byte store
-        const int x0 = 4 * go;
-        const int px = pe.shift >= 0 ? (x0 >> pe.shift) : x0 / pe.P;
-        const int xin = pe.shift >= 0 ? (x0 & (pe.P - 1)) : x0 - px * pe.P;
-        const long long off = row_off + static_cast<long long>(px) * (3 * PP) + c * PP + xin;
+        const int y = y_begin + yy, x0 = 4 * go;
+        const long long prow = static_cast<long long>(y / pe.P) * pe.Gp + x0 / pe.P;
+        const int col = (c * pe.P + y % pe.P) * pe.P + x0 % pe.P;
         const float pa = pe.a[c], pb = pe.b[c];
         const float f0 = fmaf(static_cast<float>(r4 & 0xFFu), pa, pb), f1 = fmaf(static_cast<float>((r4 >> 8) & 0xFFu), pa, pb);
         const float f2 = fmaf(static_cast<float>((r4 >> 16) & 0xFFu), pa, pb), f3 = fmaf(static_cast<float>(r4 >> 24), pa, pb);
         uint2 h;
         h.x = pack_h2<OUT == OUT_PATCH_F16>(f0, f1);
         h.y = pack_h2<OUT == OUT_PATCH_F16>(f2, f3);
-        *reinterpret_cast<uint2*>(o + off * 2) = h;
+        *reinterpret_cast<uint2*>(o + (prow * (3LL * pe.P * pe.P) + col) * 2) = h;
       }
     }
   }
@@ -420,9 +413,6 @@ cudaError_t launch_tta(const uint8_t* src, const void* views_dev, int64_t n_jobs
     if (patch < 4 || patch % 4 != 0 || S % patch != 0) return cudaErrorInvalidValue;
     pe.P = patch;
     pe.Gp = S / patch;
-    pe.shift = -1;
-    for (int b = 2; b < 12; ++b)
-      if ((1 << b) == patch) pe.shift = b;
     // the same expressions as rowwise.cu im2col_kernel evaluates for uint8 input: bit-identical patches
     const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f}, std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
     for (int c = 0; c < 3; ++c) {

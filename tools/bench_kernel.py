@@ -84,7 +84,7 @@ elif what == "tta":
     I = n
     rng = np.random.default_rng(0)
     imgs = [rng.integers(0, 256, (375, 500, 3), dtype=np.uint8) for _ in range(I)]
-    gen = jb.TTAViews(n_crops=64, seed=0)
+    gen = jb.TTAViews(n_crops=64, seed=0, emit=os.environ.get("EMIT", "views"))   # EMIT=patches: fused with the tower's front end
     jobs = gen.draw_jobs([im.shape[:2] for im in imgs])
     import time
     out = gen(imgs, jobs=jobs)
