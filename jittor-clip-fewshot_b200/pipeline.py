@@ -180,6 +180,9 @@ class HotPath:
                 if bufs[b] is None or bufs[b].numel() < n or bufs[b].dtype != dtype:
                     bufs[b] = torch.empty(n, dtype=dtype, device=device)
                     main.wait_stream(torch.cuda.current_stream(device))
+                    if overlap:      # written on `side`, read on `main`, allocated on the caller's stream: the caching
+                        bufs[b].record_stream(side)      # allocator must not hand the block out again (after a later
+                        bufs[b].record_stream(main)      # re-size) before both streams are done with it
                 if overlap and consumed[b] is not None:
                     side.wait_event(consumed[b])            # the towers have read what this buffer held two batches ago
                 views = tta(imgs, out=bufs[b][:n], stream=side if overlap else None)
