@@ -670,7 +670,6 @@ constexpr size_t MTA_SMEM_LIMIT = 220 * 1024;
 // Measured on B200 at V = 65 (ncu, profiles/r01l_*): the first kernel spent 65 % of its 1.0 M cycles per problem
 // in the per-pair dots of the set-up and ran 8 warps per SM.
 constexpr int MF_THREADS = 512;
-constexpr int MF_WARPS = MF_THREADS / 32;
 
 // row stride (floats) >= n: a multiple of 4 (16-byte rows) whose quarter is odd, so 8 consecutive rows read as
 // float4 at the same column hit 8 different 4-bank groups
@@ -678,19 +677,6 @@ __host__ __device__ inline int mf_pad(int n) {
   int ld = (n + 3) & ~3;
   if (((ld >> 2) & 1) == 0) ld += 4;
   return ld;
-}
-
-template <int NT>
-__device__ __forceinline__ float mf_block_sum(float v, float* s_red) {
-  constexpr int NW = NT / 32;
-  v = warp_sum(v);
-  __syncthreads();  // protect s_red from the previous use
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) t += s_red[w];
-  return t;
 }
 
 // G[i * ldg + j] = sum_k M[i * ld + k] M[j * ld + k] for i, j < V, k < 4 * K4 (columns past the logical width are
@@ -746,45 +732,224 @@ __device__ void mf_gram(const float* __restrict__ M, int ld, int K4, int V, floa
   }
 }
 
-// gaussian_kernel(mode, bandwidth, X)  (test.py:1310-1313): one warp per view, the mode in registers
-template <int NT>
-__device__ __forceinline__ void mf_density(const float* __restrict__ X, int ldx, const float* s_mode,
-                                           const float* s_bw, float* s_dens, int V, int D) {
-  constexpr int NW = NT / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nq = D >> 7;  // float4 per lane, D % 128 == 0, D <= 1024
-  float4 m[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    if (q < nq) m[q] = *reinterpret_cast<const float4*>(s_mode + 128 * q + 4 * lane);
-  for (int i = warp; i < V; i += NW) {
-    const float* xr = X + i * ldx + 4 * lane;
-    float acc = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < nq) {
-        const float4 x = *reinterpret_cast<const float4*>(xr + 128 * q);
-        float t = x.x - m[q].x; acc = fmaf(t, t, acc);
-        t = x.y - m[q].y; acc = fmaf(t, t, acc);
-        t = x.z - m[q].z; acc = fmaf(t, t, acc);
-        t = x.w - m[q].w; acc = fmaf(t, t, acc);
-      }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float dist = sqrtf(acc);  // jt.norm(...), then dist**2 as the reference does
-      const float bw = s_bw[i];
-      s_dens[i] = expf(-(dist * dist) / (2.0f * bw * bw));
-    }
-  }
-  __syncthreads();
+// ---- the iterations of ONE bank, run by a group of GW warps (all warps of the CTA, or a third of them when the CTA's
+// banks iterate side by side).  Every sum is taken in an order that depends on (V, D) only, never on GW: the density of
+// a view by 16 lanes, a row of A y by one thread, the mode update as MF_IQ partial sums over fixed view ranges per
+// 128-column slot.  So a bank gives the same bits whether it has the CTA to itself (few images per call) or shares it.
+constexpr int MF_IQ = 4;
+__host__ __device__ inline int mf_iq(int V) { return V >= 16 ? MF_IQ : 1; }
+// floats of one bank's iteration state: mode [D], partial sums [iq, D] (the first D double as the new mode), y, density,
+// density * y, z [V rounded up to 4], reduction slots [32]
+__host__ __device__ inline int mf_state_floats(int V, int D) { return D + mf_iq(V) * D + 4 * ((V + 3) & ~3) + 32; }
+
+__device__ __forceinline__ void mf_bar(int id, int nthreads) {
+  if (nthreads == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// NT = 512 threads and one CTA per SM for the headline view counts (V = 65: 168 KB of shared memory); NT = 128 and up to
-// four CTAs per SM for V <= 32, where a problem is a few KB and 512 threads mostly wait at barriers (N = 1 and N = 16
-// crops: thousands of tiny problems per step).
-// NT = 32 / 64: one or two warps per problem for the smallest view counts (V = 2 at N = 1 crop: 12 480 problems per step whose
-// ~50 block-wide iterations are pure barrier latency with four warps; with one warp a barrier is free and 16 problems share
+// gaussian_kernel(mode, bandwidth, X)  (test.py:1310-1313): 16 lanes per view, two views per warp pass, the mode in
+// registers.  out[i] = density_i, or density_i * y_i (test.py:1447) for the mode loop
+template <bool WITH_Y, int MAXQ>
+__device__ __forceinline__ void mf_density_q(const float* __restrict__ X, int ldx, const float* s_mode, const float* s_bw,
+                                           const float* s_y, float* s_out, int V, int D, int gw, int GW) {
+  const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+  const int nq = D >> 6;  // float4 per lane, D % 64 == 0; MAXQ = 0: any D, the mode is re-read from shared memory
+  float4 m[MAXQ > 0 ? MAXQ : 1];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q)
+    if (q < nq) m[q] = *reinterpret_cast<const float4*>(s_mode + 64 * q + 4 * sub);
+  for (int p = gw; 2 * p < V; p += GW) {
+    const int i = 2 * p + half;
+    const float* xr = X + (i < V ? i : V - 1) * ldx + 4 * sub;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (MAXQ > 0) {
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q)
+        if (q < nq) {
+          const float4 x = *reinterpret_cast<const float4*>(xr + 64 * q);
+          float t = x.x - m[q].x; a0 = fmaf(t, t, a0);
+          t = x.y - m[q].y; a1 = fmaf(t, t, a1);
+          t = x.z - m[q].z; a2 = fmaf(t, t, a2);
+          t = x.w - m[q].w; a3 = fmaf(t, t, a3);
+        }
+    } else {
+#pragma unroll 4
+      for (int q = 0; q < nq; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(xr + 64 * q);
+        const float4 mm = *reinterpret_cast<const float4*>(s_mode + 64 * q + 4 * sub);
+        float t = x.x - mm.x; a0 = fmaf(t, t, a0);
+        t = x.y - mm.y; a1 = fmaf(t, t, a1);
+        t = x.z - mm.z; a2 = fmaf(t, t, a2);
+        t = x.w - mm.w; a3 = fmaf(t, t, a3);
+      }
+    }
+    float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0 && i < V) {
+      const float dist = sqrtf(acc);  // jt.norm(...), then dist**2 as the reference does
+      const float bw = s_bw[i];
+      const float dens = expf(-(dist * dist) / (2.0f * bw * bw));
+      s_out[i] = WITH_Y ? dens * s_y[i] : dens;
+    }
+  }
+}
+
+template <bool WITH_Y>
+__device__ __forceinline__ void mf_density(const float* __restrict__ X, int ldx, const float* s_mode, const float* s_bw,
+                                           const float* s_y, float* s_out, int V, int D, int gw, int GW) {
+  if (D <= 512) mf_density_q<WITH_Y, 8>(X, ldx, s_mode, s_bw, s_y, s_out, V, D, gw, GW);   // (CLIP ViT-B: 512)
+  else mf_density_q<WITH_Y, 0>(X, ldx, s_mode, s_bw, s_y, s_out, V, D, gw, GW);
+}
+
+__device__ __forceinline__ void mf_solve_bank(const MtaDev& a, const MtaSet& set, long long img, const float* __restrict__ X,
+                              const float* __restrict__ A, const float* s_bw, float* st, int gw, int GW, int bar_id) {
+  const int V = a.V, C = a.C, D = a.D, ldA = a.ldA, ldx = a.ldx;
+  const int lane = threadIdx.x & 31, gt = gw * 32 + lane, GT = GW * 32;
+  const int vp = (V + 3) & ~3, iq_n = mf_iq(V), nds = D >> 7;
+  float* s_mode = st;                  // [D]
+  float* s_part = s_mode + D;          // [iq_n, D]; row 0 becomes the new mode
+  float* s_y = s_part + iq_n * D;      // [vp]
+  float* s_dens = s_y + vp;            // [vp]
+  float* s_w = s_dens + vp;            // [vp]
+  float* s_z = s_w + vp;               // [vp]
+  float* s_red = s_z + vp;             // [32]
+  const float inv_lambda_y = 1.0f / a.p.lambda_y, lambda_q = a.p.lambda_q, th = a.p.th;
+  const int max_iter = a.p.max_iter;
+
+  mf_bar(bar_id, GT);   // (banks one after another: the previous bank's mode has been written out)
+  // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
+  for (int i = gt; i < vp; i += GT) s_y[i] = i < V ? 1.0f / static_cast<float>(V) : 0.f;
+  for (int d = gt; d < D; d += GT) s_mode[d] = X[d];
+  mf_bar(bar_id, GT);
+
+  for (int outer = 0; outer < max_iter; ++outer) {                 // test.py:1424, :1455-1457
+    mf_density<false>(X, ldx, s_mode, s_bw, s_y, s_dens, V, D, gw, GW);   // :1426
+    mf_bar(bar_id, GT);
+    for (int it = 1;; ++it) {                                       // inlierness loop :1430-1438
+      for (int i = gt; i < V; i += GT) {                            // z = (rho + lambda_q A y) / lambda_y, a row per thread
+        const float* ar = A + i * ldA;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int j = 0;
+        for (; j + 4 <= V; j += 4) {
+          const float4 y4 = *reinterpret_cast<const float4*>(s_y + j);
+          s0 = fmaf(ar[j], y4.x, s0);
+          s1 = fmaf(ar[j + 1], y4.y, s1);
+          s2 = fmaf(ar[j + 2], y4.z, s2);
+          s3 = fmaf(ar[j + 3], y4.w, s3);
+        }
+        for (; j < V; ++j) s0 = fmaf(ar[j], s_y[j], s0);
+        s_z[i] = inv_lambda_y * (s_dens[i] + lambda_q * ((s0 + s1) + (s2 + s3)));
+      }
+      mf_bar(bar_id, GT);
+      if (gw == 0) {                                                // y <- softmax(z), ||y_old - y||
+        float mx = -INFINITY;
+        for (int i = lane; i < V; i += 32) mx = fmaxf(mx, s_z[i]);
+        mx = warp_max(mx);
+        float zs = 0.f;
+        for (int i = lane; i < V; i += 32) {
+          const float e = expf(s_z[i] - mx);
+          s_z[i] = e;
+          zs += e;
+        }
+        zs = warp_sum(zs);
+        const float inv = 1.0f / zs;
+        float diff = 0.f;
+        for (int i = lane; i < V; i += 32) {
+          const float yn = s_z[i] * inv;
+          const float t = s_y[i] - yn;
+          diff = fmaf(t, t, diff);
+          s_y[i] = yn;
+        }
+        diff = warp_sum(diff);
+        if (lane == 0) s_red[31] = diff;
+      }
+      mf_bar(bar_id, GT);
+      if (sqrtf(s_red[31]) < th || it >= max_iter) break;          // :1436
+    }
+    const int q4 = (V + iq_n - 1) / iq_n;
+    for (int it = 1;; ++it) {                                       // mode loop :1443-1453
+      mf_density<true>(X, ldx, s_mode, s_bw, s_y, s_w, V, D, gw, GW);     // :1446-1447: w = density * y
+      mf_bar(bar_id, GT);
+      // sum_i w_i x_i (:1448) as iq_n partial sums over fixed view ranges, one warp per (range, 128-column slot)
+      for (int u = gw; u < nds * iq_n; u += GW) {
+        const int ds = u % nds, qi = u / nds;
+        const int i0 = qi * q4, i1 = (i0 + q4 < V) ? i0 + q4 : V;
+        const float* xc = X + 128 * ds + 4 * lane;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+          const float w = s_w[i];
+          const float4 x = *reinterpret_cast<const float4*>(xc + i * ldx);
+          acc.x = fmaf(w, x.x, acc.x);
+          acc.y = fmaf(w, x.y, acc.y);
+          acc.z = fmaf(w, x.z, acc.z);
+          acc.w = fmaf(w, x.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(s_part + qi * D + 128 * ds + 4 * lane) = acc;
+      }
+      mf_bar(bar_id, GT);
+      for (int ds = gw; ds < nds; ds += GW) {                       // / sum_i w_i, and the slot's share of ||.||^2
+        float wsum = 0.f;
+        for (int i = lane; i < V; i += 32) wsum += s_w[i];
+        wsum = warp_sum(wsum);
+        float* pc = s_part + 128 * ds + 4 * lane;
+        float4 s = *reinterpret_cast<const float4*>(pc);
+        for (int qi = 1; qi < iq_n; ++qi) {
+          const float4 t = *reinterpret_cast<const float4*>(pc + qi * D);
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        s.x = s.x / wsum; s.y = s.y / wsum; s.z = s.z / wsum; s.w = s.w / wsum;   // :1448
+        *reinterpret_cast<float4*>(pc) = s;
+        float nrm = fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, s.w * s.w)));
+        nrm = warp_sum(nrm);
+        if (lane == 0) s_red[ds] = nrm;
+      }
+      mf_bar(bar_id, GT);
+      float nrm = 0.f;
+      for (int ds = 0; ds < nds; ++ds) nrm += s_red[ds];
+      const float inv = 1.0f / sqrtf(nrm);                          // :1449
+      for (int ds = gw; ds < nds; ds += GW) {
+        const int d = 128 * ds + 4 * lane;
+        float4 mnew = *reinterpret_cast<const float4*>(s_part + d);
+        const float4 mold = *reinterpret_cast<const float4*>(s_mode + d);
+        mnew.x *= inv; mnew.y *= inv; mnew.z *= inv; mnew.w *= inv;
+        float t = mold.x - mnew.x, diff = t * t;
+        t = mold.y - mnew.y; diff = fmaf(t, t, diff);
+        t = mold.z - mnew.z; diff = fmaf(t, t, diff);
+        t = mold.w - mnew.w; diff = fmaf(t, t, diff);
+        *reinterpret_cast<float4*>(s_mode + d) = mnew;
+        diff = warp_sum(diff);
+        if (lane == 0) s_red[8 + ds] = diff;
+      }
+      mf_bar(bar_id, GT);
+      float diff = 0.f;
+      for (int ds = 0; ds < nds; ++ds) diff += s_red[8 + ds];
+      if (sqrtf(diff) < th || it >= max_iter) break;                // :1452
+    }
+  }
+
+  // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
+  for (int d = gt; d < D; d += GT) set.out_mode[img * D + d] = s_mode[d];
+  if (set.out_logits) {
+    const float* __restrict__ Tt = set.text;
+    for (int c = gt; c < C; c += GT) {
+      float s2 = 0.f;
+      for (int d = 0; d < D; ++d) s2 = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s2);
+      set.out_logits[img * C + c] = s2 * 100.0f;
+    }
+  }
+}
+
+// NT = 512 threads and one CTA per SM for the headline view counts (V = 65: 215 KB of shared memory with three banks);
+// NT = 128 and up to four CTAs per SM for V <= 32, where a problem is a few KB and 512 threads mostly wait at barriers
+// (N = 1 and N = 16 crops: thousands of tiny problems per step).
+// NT = 32 / 64: one or two warps per problem for the smallest view counts (V = 2 at N = 1 crop: 12 480 problems per step
+// whose ~50 iterations are pure barrier latency with four warps; with one warp a barrier is free and 16 problems share
 // an SM).
+// With NT = 512 the banks of a CTA iterate SIDE BY SIDE, each on NW / nb warps with its own named barrier and state: the
+// iterations are latency- and barrier-bound (a few hundred instructions between barriers), so three independent
+// instruction streams fill the issue slots one stream leaves empty.
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64 ? 8 : 16))) mta_fast_kernel(const MtaDev a) {
   constexpr int NW = NT / 32;
@@ -796,21 +961,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64
   const int nb = a.group_count[group];                   // banks solved by this CTA (they share the feature tensor)
   const float* __restrict__ Xg = a.sets[a.group_sets[group][0]].feats + img * V * D;
 
-  float* s_mode = mta_smem;           // [D]
-  float* s_new = s_mode + D;          // [D]
-  float* s_bw = s_new + D;            // [V]
-  float* s_y = s_bw + V;              // [V]
-  float* s_dens = s_y + V;            // [V]
-  float* s_z = s_dens + V;            // [V]
-  float* s_sq = s_z + V;              // [V]
-  float* s_red = s_sq + V;            // [32]
-  float* big = s_red + 32;
-  big = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(big) + 15) & ~static_cast<uintptr_t>(15));
-  float* R = big;                                        // P [V, ldp] of one bank at a time, later X [V, ldx]
+  const int vp = (V + 3) & ~3;
+  float* s_bw = mta_smem;             // [vp]
+  float* s_sq = s_bw + vp;            // [vp]
+  float* R = s_sq + vp;                                  // P [V, ldp] of one bank at a time, later X [V, ldx]
   const int r_elems = V * (ldp > ldx ? ldp : ldx);
   const int a_elems = (V * ldA + 3) & ~3;
   float* A_all = R + r_elems;                            // affinities [nb][V, ldA]
-  float* Dm = A_all + a.max_group * a_elems;             // Gram of X, then the pairwise distances [V, ldA]
+  float* U = A_all + a.max_group * a_elems;              // Gram of X, then the pairwise distances [V, ldA]; afterwards
+  float* Dm = U;                                         // the iteration state of the banks
 
   for (int b = 0; b < nb; ++b) {
     // ---- 1+2. this problem's V x C block of softmax(100 X T), zero padded to ldp columns
@@ -859,100 +1018,33 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64
     acc = warp_sum(acc);
     if (lane == 0) s_bw[i] = sqrtf(0.5f * (acc / static_cast<float>(a.k)));
   }
-  const float inv_lambda_y = 1.0f / a.p.lambda_y;
-  for (int b = 0; b < nb; ++b) {
-    const MtaSet& set = a.sets[a.group_sets[group][b]];
-    const float* __restrict__ Tt = set.text;
-    const float* A = A_all + b * a_elems;
-    __syncthreads();   // the previous bank's outputs have been read from s_mode; s_bw is complete
-    // ---- 6. initialise: y uniform, mode = un-augmented view        (test.py:1414-1418)
-    for (int i = tid; i < V; i += NT) s_y[i] = 1.0f / static_cast<float>(V);
-    for (int d = tid; d < D; d += NT) s_mode[d] = X[d];
-    __syncthreads();
+  __syncthreads();   // s_bw is complete; the distances are dead, their memory becomes the banks' state
 
-    for (int outer = 0; outer < a.p.max_iter; ++outer) {            // test.py:1424, :1455-1457
-      mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);                // :1426
-      for (int it = 1;; ++it) {                                      // inlierness loop :1430-1438
-        for (int i = warp; i < V; i += NW) {                   // z = (rho + lambda_q A y) / lambda_y
-          float s2 = 0.f;
-          for (int j = lane; j < V; j += 32) s2 = fmaf(A[i * ldA + j], s_y[j], s2);
-          s2 = warp_sum(s2);
-          if (lane == 0) s_z[i] = inv_lambda_y * (s_dens[i] + a.p.lambda_q * s2);
-        }
-        __syncthreads();
-        if (warp == 0) {                                             // y <- softmax(z), ||y_old - y||
-          float mx = -INFINITY;
-          for (int i = lane; i < V; i += 32) mx = fmaxf(mx, s_z[i]);
-          mx = warp_max(mx);
-          float zs = 0.f;
-          for (int i = lane; i < V; i += 32) {
-            const float e = expf(s_z[i] - mx);
-            s_z[i] = e;
-            zs += e;
-          }
-          zs = warp_sum(zs);
-          const float inv = 1.0f / zs;
-          float diff = 0.f;
-          for (int i = lane; i < V; i += 32) {
-            const float yn = s_z[i] * inv;
-            const float t = s_y[i] - yn;
-            diff = fmaf(t, t, diff);
-            s_y[i] = yn;
-          }
-          diff = warp_sum(diff);
-          if (lane == 0) s_red[31] = diff;
-        }
-        __syncthreads();
-        if (sqrtf(s_red[31]) < a.p.th || it >= a.p.max_iter) break;  // :1436
-      }
-      for (int it = 1;; ++it) {                                      // mode loop :1443-1453
-        mf_density<NT>(X, ldx, s_mode, s_bw, s_dens, V, D);              // :1446
-        float nrm = 0.f;
-        for (int d = tid; d < D; d += NT) {
-          float s2 = 0.f, wsum = 0.f;
-          for (int i = 0; i < V; ++i) {
-            const float w = s_dens[i] * s_y[i];                      // :1447
-            wsum += w;
-            s2 = fmaf(w, X[i * ldx + d], s2);
-          }
-          s2 = s2 / wsum;                                            // :1448
-          s_new[d] = s2;
-          nrm = fmaf(s2, s2, nrm);
-        }
-        nrm = mf_block_sum<NT>(nrm, s_red);
-        const float inv = 1.0f / sqrtf(nrm);                         // :1449
-        float diff = 0.f;
-        for (int d = tid; d < D; d += NT) {
-          const float m = s_new[d] * inv;
-          const float t = s_mode[d] - m;
-          diff = fmaf(t, t, diff);
-          s_new[d] = m;
-        }
-        diff = mf_block_sum<NT>(diff, s_red);
-        for (int d = tid; d < D; d += NT) s_mode[d] = s_new[d];
-        __syncthreads();
-        if (sqrtf(diff) < a.p.th || it >= a.p.max_iter) break;       // :1452
-      }
-    }
-
-    // ---- 7. outputs: mode (test.py:1461) and optionally 100 * mode @ T (ood.py:819)
-    for (int d = tid; d < D; d += NT) set.out_mode[img * D + d] = s_mode[d];
-    if (set.out_logits) {
-      for (int c = tid; c < C; c += NT) {
-        float s2 = 0.f;
-        for (int d = 0; d < D; ++d) s2 = fmaf(s_mode[d], __ldg(Tt + static_cast<long long>(d) * C + c), s2);
-        set.out_logits[img * C + c] = s2 * 100.0f;
-      }
-    }
+  int b0 = 0, b1 = nb, gw = warp, GW = NW, bar = 0;
+  float* st = U;
+  if (NT == 512 && nb > 1) {         // side by side: bank b on warps [b GW, (b + 1) GW), barrier 1 + b, its own state
+    GW = NW / nb;
+    b0 = warp / GW;
+    if (b0 >= nb) return;            // spare warp (16 = 3 x 5 + 1)
+    b1 = b0 + 1;
+    gw = warp - b0 * GW;
+    bar = 1 + b0;
+    st = U + b0 * mf_state_floats(V, D);
   }
+  for (int b = b0; b < b1; ++b)
+    mf_solve_bank(a, a.sets[a.group_sets[group][b]], img, X, A_all + b * a_elems, s_bw, st, gw, GW, bar);
 }
 
+// banks whose iteration state is live at the same time: the 512-thread kernel (V > 32) iterates its banks side by side
+static int mf_states(int V, int banks) { return V > 32 ? banks : 1; }
 size_t mf_smem_bytes(int V, int C, int D, int banks = 1) {
-  const int ldx = mf_pad(D), ldp = mf_pad(C), ldA = V | 1;
-  const size_t small = sizeof(float) * (2 * D + 5 * V + 32) + 16;
-  // P / X region + one affinity per bank the CTA solves + the distance matrix
-  const size_t bigf = static_cast<size_t>(V) * (ldp > ldx ? ldp : ldx) + (banks + 1) * static_cast<size_t>((V * ldA + 3) & ~3);
-  return small + bigf * sizeof(float);
+  const int ldx = mf_pad(D), ldp = mf_pad(C), ldA = V | 1, vp = (V + 3) & ~3;
+  const size_t a_elems = (static_cast<size_t>(V) * ldA + 3) & ~static_cast<size_t>(3);
+  // bandwidths + squared norms, the P / X region, one affinity per bank the CTA solves, and the region that first holds
+  // the distance matrix and then the banks' iteration state
+  const size_t state = static_cast<size_t>(mf_states(V, banks)) * mf_state_floats(V, D);
+  const size_t bigf = static_cast<size_t>(V) * (ldp > ldx ? ldp : ldx) + banks * a_elems + (a_elems > state ? a_elems : state);
+  return (2 * vp + bigf) * sizeof(float) + 16;
 }
 
 
