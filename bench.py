@@ -544,6 +544,32 @@ def main():
         other_operands = {"operands": alt, "value": n_total / (ms_a / 1e3), "unit": UNIT, "ms_per_step": ms_a,
                           "identical_top5_sets_vs_headline_operands": float((out_a.sort(dim=1).values == out.sort(dim=1).values).all(dim=1).float().mean()),
                           "note": "same kernels, tcgen05 kind::f16 runs fp16 and bf16 operands at the same rate; NOT used for value / e2e / roofline"}
+    # ---- informational: the same device-resident step with the adapters APPLIED as low-rank GEMMs instead of merged
+    #      (jcb_ctx_set_lora_mode; the towers are re-packed): what a caller that swaps adapters per request pays
+    lora_applied = None
+    if not args.no_e2e:
+        ctx.set_lora_mode("applied")
+        try:
+            for _ in range(2):
+                r = step_device()
+                out_l = gather.result(r if G == 1 else gather.submit(r))
+            jb.dist.barrier()
+            torch.cuda.synchronize()
+            step_no[0] = 0
+            ev0.record()
+            for _ in range(K):
+                step_device()
+            finish_steps()
+            ev1.record()
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_lora_mode("merged")
+        ms_l = jb.dist.max_over_ranks(ev0.elapsed_time(ev1), dev) / K
+        lora_applied = {"value": n_total / (ms_l / 1e3), "unit": UNIT, "ms_per_step": ms_l,
+                        "identical_top5_sets_vs_merged": float((out_l.sort(dim=1).values == out.sort(dim=1).values).all(dim=1).float().mean()),
+                        "note": "jcb_ctx_set_lora_mode(JCB_LORA_APPLIED): y = W x + b + s B (A x) (test.py:388-398) as a narrow tcgen05 GEMM "
+                                "+ a second TMA operand pair accumulated into the QKV tile, stand-alone LayerNorm schedule; "
+                                "NOT used for value / e2e / roofline (those run the default merged mode)"}
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     clocks = sampler.summary()
@@ -664,7 +690,7 @@ def main():
                        **({"shard_check": shard_check} if shard_check else {}),
                        **({"topk_all_gather": "every step, asynchronous (dist.AsyncTopkGather)" if G == 1 else
                            f"once per {K} timed steps, inside the timed region"} if world > 1 else {})),
-        "e2e": e2e, "e2e_from_images": e2e_img, "cls_only_last_block": cls_only, "other_operand_type": other_operands, "single_image_call": single, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "e2e_from_images": e2e_img, "cls_only_last_block": cls_only, "other_operand_type": other_operands, "lora_applied": lora_applied, "single_image_call": single, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
     return 0

@@ -35,7 +35,7 @@ extern "C" {
 #define JCB_E_KERNEL (-5)      /* a kernel reported a device-side status (pipeline timeout) */
 #define JCB_E_NOMEM (-6)
 
-#define JCB_ABI_VERSION 3
+#define JCB_ABI_VERSION 4
 
 typedef struct jcb_ctx jcb_ctx;
 typedef struct jcb_vit jcb_vit;
@@ -100,6 +100,22 @@ int jcb_ctx_set_cls_only_last_block(jcb_ctx* ctx, int on);
 #define JCB_OPERAND_F16 1
 int jcb_ctx_set_operand_type(jcb_ctx* ctx, int operand_type);
 int jcb_ctx_get_operand_type(const jcb_ctx* ctx);
+/* How the towers packed AFTER this call carry their LoRA adapters (reference LinearLoRA.execute, test.py:378-398):
+ *   JCB_LORA_MERGED  (default; env JCB_LORA=merged): W' = W + s B A in fp32, rounded to 16 bits once at pack time
+ *                    (the `merged` branch, test.py:310-313, :386); the tower runs exactly the zero-shot schedule.
+ *   JCB_LORA_APPLIED (env JCB_LORA=applied): y = W x + b + s B (A x), the branch the reference evaluates in eval mode
+ *                    (test.py:388-398; SURVEY.md App. B: Jittor's eval() never merges).  Base weights stay un-merged;
+ *                    per layer one narrow GEMM U = x [A_q; A_k; A_v]^T, and the projection GEMM accumulates
+ *                    U [s B_q | s B_k | s B_v]^T into the same TMEM accumulator through a second TMA operand pair
+ *                    (likewise out_proj for 'o' adapters).  The ranks of q, k, v of one layer must sum to <= 64 (r <= 64
+ *                    for 'o').  This schedule keeps the LayerNorms as stand-alone passes (the folded epilogues would
+ *                    need the low-rank term pre-divided by the row's 1 / sigma), so it is the slower of the two; it
+ *                    exists for callers that swap adapters per request.
+ * A tower keeps the mode it was finalized with (jcb_vit_lora_mode / jcb_text_lora_mode). */
+#define JCB_LORA_MERGED 0
+#define JCB_LORA_APPLIED 1
+int jcb_ctx_set_lora_mode(jcb_ctx* ctx, int mode);
+int jcb_ctx_get_lora_mode(const jcb_ctx* ctx);
 /* Give the grow-only scratch of the context (tower pass buffers, view-generator scratch, host-input staging) back to
  * the device allocator; it is re-reserved on demand.  Waits for the device.  JCB_E_STATE while submissions are in flight. */
 int jcb_ctx_trim(jcb_ctx* ctx);
@@ -130,7 +146,8 @@ int64_t jcb_ctx_launch_count(const jcb_ctx* ctx);
 #define JCB_KC_HEAD 11
 #define JCB_KC_OTHER 12
 #define JCB_KC_TTA 13
-#define JCB_KC_COUNT 14
+#define JCB_KC_GEMM_LORA 14   /* LoRA applied: the narrow down-projection GEMMs */
+#define JCB_KC_COUNT 15
 int jcb_ctx_profile(jcb_ctx* ctx, int enable);
 int jcb_ctx_profile_read(const jcb_ctx* ctx, int kernel_class, double* total_ms, int64_t* launches,
                          int64_t* timed_launches, double* flops, double* bytes);
@@ -164,6 +181,8 @@ int jcb_vit_clear_lora(jcb_vit* vit);
 int jcb_vit_finalize(jcb_vit* vit);
 /* JCB_OPERAND_* the device weights were packed with by the last jcb_vit_finalize. */
 int jcb_vit_operand_type(const jcb_vit* vit);
+/* JCB_LORA_* the adapters were packed with by the last jcb_vit_finalize. */
+int jcb_vit_lora_mode(const jcb_vit* vit);
 
 /* `CLIP.encode_image(image)` (jclip/model.py:199-200 -> VisionTransformer.execute :104-126).
  *   images_dev   [n_views, 3, R, R] on the device, element type `img_dtype`
@@ -203,6 +222,7 @@ int jcb_text_set_lora(jcb_text* text, int layer, int proj, const float* A, const
 int jcb_text_clear_lora(jcb_text* text);
 int jcb_text_finalize(jcb_text* text);
 int jcb_text_operand_type(const jcb_text* text);
+int jcb_text_lora_mode(const jcb_text* text);
 /* tokens_dev [n_seq, context_length] int64 (what `clip.tokenize` returns); out_dev [n_seq, embed_dim] float32;
  * normalize != 0 fuses `/ norm(dim=-1)` (test.py:929) */
 int jcb_encode_text(jcb_text* text, const int64_t* tokens_dev, int64_t n_seq, int normalize, float* out_dev);
@@ -378,6 +398,11 @@ typedef struct jcb_gemm_args {
   const float* shift_in_dev;
   float* shift_out_dev;     /* LNPREP: [M] or NULL */
   int64_t stats_in_row_stride;
+  /* optional second operand pair accumulated into the same tile: C = A B^T + A2 B2^T (LoRA applied, test.py:388-398) */
+  const void* A2_dev;       /* [M, K2] row-major, leading dimension lda2; NULL / K2 = 0: none */
+  const void* B2_dev;       /* [N, K2] row-major, leading dimension ldb2 */
+  int32_t K2;               /* multiple of 64 */
+  int64_t lda2, ldb2;
 } jcb_gemm_args;
 int jcb_gemm(jcb_ctx* ctx, const jcb_gemm_args* args);
 /* Weight preparation of a LayerNorm-folded GEMM: Wf[n,k] = round16(gamma[k] W[n,k]); S[n] = sum_k Wf[n,k];

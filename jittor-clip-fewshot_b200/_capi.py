@@ -15,18 +15,20 @@ LIB_PATH = PKG_DIR / "libjclip_b200.so"
 
 JCB_OK = 0
 JCB_E_INVALID, JCB_E_CUDA, JCB_E_STATE, JCB_E_NO_DEVICE, JCB_E_KERNEL, JCB_E_NOMEM = -1, -2, -3, -4, -5, -6
-JCB_ABI_VERSION = 3
+JCB_ABI_VERSION = 4
 MAX_INFLIGHT = 4   # JCB_MAX_INFLIGHT
 IMG_F32, IMG_BF16, IMG_U8, IMG_PATCHES_BF16, IMG_PATCHES_F16 = 0, 1, 2, 3, 4
 PROJ_Q, PROJ_K, PROJ_V, PROJ_O = 0, 1, 2, 3
 SCORE_NAMES = ("logits", "cs", "cs1", "cs2", "cs3", "cs4", "cs5")
 SCORE_INDEX = {n: i for i, n in enumerate(SCORE_NAMES)}
-KC_COUNT = 14
+KC_COUNT = 15
 FILTER_BILINEAR, FILTER_BICUBIC = 0, 1
 # JCB_EPI_* (epilogue 3, the conv1 scatter, no longer exists)
 EPI_BIAS_16, EPI_BIAS_GELU_16, EPI_BIAS_RESID_F32, EPI_F32 = 0, 1, 2, 4
 EPI_LNFOLD_16, EPI_LNFOLD_GELU_16, EPI_RESID_LNPREP_SHORT, EPI_RESID_LNPREP_LONG = 5, 6, 7, 8
 OPERAND_BF16, OPERAND_F16 = 0, 1
+LORA_MERGED, LORA_APPLIED = 0, 1
+LORA_MODES = {"merged": LORA_MERGED, "applied": LORA_APPLIED}
 OPERAND_NAMES = {"bf16": OPERAND_BF16, "f16": OPERAND_F16, "fp16": OPERAND_F16, "float16": OPERAND_F16,
                  "bfloat16": OPERAND_BF16}
 
@@ -68,7 +70,8 @@ class GemmArgs(Structure):
                 ("operand_type", c_int32), ("bias_dev", c_void_p), ("epilogue", c_int32), ("stats_slots", c_int32),
                 ("out_dev", c_void_p), ("ldo", c_int64), ("stats_dev", c_void_p), ("colsum_dev", c_void_p),
                 ("out2_dev", c_void_p), ("stats_in_dev", c_void_p), ("shift_in_dev", c_void_p),
-                ("shift_out_dev", c_void_p), ("stats_in_row_stride", c_int64)]
+                ("shift_out_dev", c_void_p), ("stats_in_row_stride", c_int64),
+                ("A2_dev", c_void_p), ("B2_dev", c_void_p), ("K2", c_int32), ("lda2", c_int64), ("ldb2", c_int64)]
 
 
 class PipelineArgs(Structure):
@@ -96,6 +99,10 @@ PROTOTYPES = {
     "jcb_ctx_get_operand_type": (c_int, [c_void_p]),
     "jcb_vit_operand_type": (c_int, [c_void_p]),
     "jcb_text_operand_type": (c_int, [c_void_p]),
+    "jcb_ctx_set_lora_mode": (c_int, [c_void_p, c_int]),
+    "jcb_ctx_get_lora_mode": (c_int, [c_void_p]),
+    "jcb_vit_lora_mode": (c_int, [c_void_p]),
+    "jcb_text_lora_mode": (c_int, [c_void_p]),
     "jcb_ctx_trim": (c_int, [c_void_p]),
     "jcb_sync": (c_int, [c_void_p]),
     "jcb_last_error": (c_char_p, [c_void_p]),

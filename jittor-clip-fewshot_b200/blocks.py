@@ -26,8 +26,9 @@ def _ctx(t):
 
 
 def gemm(A, B, out, epilogue, bias=None, ldo=None, stats=None, colsum=None, out2=None, stats_in=None, shift_in=None,
-         shift_out=None, stats_in_row_stride=1, sync=True):
-    """out (+)= A[M,K] @ B[N,K]^T with the fused epilogue `epilogue` (_capi.EPI_*)."""
+         shift_out=None, stats_in_row_stride=1, sync=True, A2=None, B2=None, K2=None):
+    """out (+)= A[M,K] @ B[N,K]^T (+ A2[:, :K2] @ B2[:, :K2]^T, accumulated in the same tile) with the fused epilogue
+    `epilogue` (_capi.EPI_*)."""
     ctx = _ctx(A)
     g = _capi.GemmArgs()
     g.A_dev, g.B_dev = A.data_ptr(), B.data_ptr()
@@ -47,6 +48,10 @@ def gemm(A, B, out, epilogue, bias=None, ldo=None, stats=None, colsum=None, out2
     g.shift_in_dev = shift_in.data_ptr() if shift_in is not None else None
     g.shift_out_dev = shift_out.data_ptr() if shift_out is not None else None
     g.stats_in_row_stride = int(stats_in_row_stride)
+    if A2 is not None:
+        g.A2_dev, g.B2_dev = A2.data_ptr(), B2.data_ptr()
+        g.K2 = int(K2) if K2 is not None else A2.shape[1]
+        g.lda2, g.ldb2 = A2.stride(0), B2.stride(0)
     check(ctx.lib.jcb_gemm(ctx.handle, byref(g)), ctx.handle)
     if sync:
         ctx.sync()

@@ -73,6 +73,8 @@ struct jcb_ctx {
   int ln_fold = 2;                   // LayerNorm folded into the GEMMs (EPI_LNFOLD_* / EPI_RESID_LNPREP_*):
                                      // 0 none, 1 ln_1 only (c_proj -> QKV), 2 ln_1 and ln_2
   int operand_f16 = 1;               // 16-bit operand type towers are packed with: 1 = fp16 (default), 0 = bf16
+  int lora_applied = 0;              // how towers packed from now on carry their LoRA adapters: 0 = merged into the
+                                     // weights (default), 1 = applied as low-rank GEMMs (jcb_ctx_set_lora_mode)
   char err[512] = {0};
   // CUDA graphs of whole small pipelines (see PipelineGraph below)
   int graphs_on = 1;
@@ -219,7 +221,15 @@ struct LayerDev {
   // LayerNorm folded into the consuming GEMM: gamma-scaled weights, their column sums S and the constants c
   __nv_bfloat16 *in_wf = nullptr, *fc_wf = nullptr;
   float *in_S = nullptr, *in_c = nullptr, *fc_S = nullptr, *fc_c = nullptr;
+  // LoRA applied (jcb_ctx_set_lora_mode): the adapters of the packed in_proj / of out_proj side by side,
+  // down = [A_q; A_k; A_v; 0] as [LORA_U_COLS, W] and up = [s B_q | s B_k | s B_v | 0] in the rows of its projection as
+  // [3W, LORA_K2] ([W, LORA_K2] for out_proj); nullptr when the layer has no adapter there
+  __nv_bfloat16 *lin_dn = nullptr, *lin_up = nullptr, *lout_dn = nullptr, *lout_up = nullptr;
 };
+// columns of the low-rank intermediate U = x [A_q; A_k; A_v]^T (the GEMM kernel's minimum N) and the k extent the
+// second operand pair of the projection GEMM reads of it (one 64-wide k-block: the ranks of q, k, v together <= 64)
+constexpr int LORA_U_COLS = 128;
+constexpr int LORA_K2 = 64;
 
 // What the image tower and the text tower share: a stack of pre-LN transformer blocks with packed-QKV
 // attention (+ LoRA adapters merged at pack time), the fp32 staging of the reference state dict and the
@@ -227,6 +237,7 @@ struct LayerDev {
 struct TowerBase {
   jcb_ctx* ctx = nullptr;
   int f16 = 0;                                       // operand type the device weights were packed with (jcb_*_finalize)
+  int lora_applied = 0;                              // LoRA mode they were packed with
   uint64_t gen = 0;                                  // bumped by every finalize (captured graphs key on it)
   int W = 0, L = 0, heads = 0, tokens = 0;           // width, blocks, heads (W / 64), tokens per sequence
   std::string prefix;                                // state-dict prefix of the blocks
@@ -301,6 +312,7 @@ struct TowerWs {
   __nv_bfloat16* ln_out;  // [n*T, W]
   __nv_bfloat16* qkv;     // [n*T, 3W]
   __nv_bfloat16* attn;    // [n*T, W]
+  __nv_bfloat16* lora_u;  // [n*T, LORA_U_COLS]  LoRA applied: x A^T of the projection about to run
   // LayerNorm fold: per-row partial (sum, sum of squares) [n*T, W/256, 2] of the centred 16-bit copy of the residual
   // stream and the per-row shift [n*T] it was centred by; two of each, because the producer GEMM of LayerNorm point
   // i + 1 reads the statistics of point i while its other tiles already write those of point i + 1
@@ -310,7 +322,8 @@ struct TowerWs {
 size_t tower_ws_bytes_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n) {
   const size_t big = std::max(n * GG * KP, n * T * 4 * W) * 2;
   return align_up(big) + align_up(n * T * W * 4) + align_up(n * T * W * 2) + align_up(n * T * 3 * W * 2) +
-         align_up(n * T * W * 2) + 2 * align_up(n * T * ((W + 255) / 256) * 8) + 2 * align_up(n * T * 4);
+         align_up(n * T * W * 2) + align_up(n * T * LORA_U_COLS * 2) + 2 * align_up(n * T * ((W + 255) / 256) * 8) +
+         2 * align_up(n * T * 4);
 }
 size_t tower_ws_bytes(const jcb_vit* v, int64_t n) {
   return tower_ws_bytes_dims(v->W, v->tokens, static_cast<size_t>(v->grid) * v->grid, v->kpatch, n);
@@ -322,6 +335,7 @@ TowerWs tower_ws_carve_dims(size_t W, size_t T, size_t GG, size_t KP, int64_t n,
   w.ln_out = b.take<__nv_bfloat16>(n * T * W);
   w.qkv = b.take<__nv_bfloat16>(n * T * 3 * W);
   w.attn = b.take<__nv_bfloat16>(n * T * W);
+  w.lora_u = b.take<__nv_bfloat16>(n * T * LORA_U_COLS);
   for (int i = 0; i < 2; ++i) w.stats[i] = b.take<float>(n * T * ((W + 255) / 256) * 2);
   for (int i = 0; i < 2; ++i) w.shift[i] = b.take<float>(n * T);
   return w;
@@ -342,6 +356,11 @@ struct LnArgs {
   const float* shift_in = nullptr;
   float* shift_out = nullptr;
   int64_t in_stride = 1;
+  // second operand pair of the GEMM (LoRA applied): out = A B^T + A2 B2^T
+  const __nv_bfloat16* A2 = nullptr;
+  const __nv_bfloat16* B2 = nullptr;
+  int K2 = 0;
+  int64_t lda2 = 0, ldb2 = 0;
 };
 
 int run_gemm(jcb_ctx* ctx, int cls, int f16, const __nv_bfloat16* A, const __nv_bfloat16* B, int M, int N, int K,
@@ -350,13 +369,14 @@ int run_gemm(jcb_ctx* ctx, int cls, int f16, const __nv_bfloat16* A, const __nv_
   g.stats = ln.stats; g.stats_slots = ln.slots; g.colsum = ln.colsum; g.out2 = ln.out2; g.ldo2 = N;   // out2 / stats are dense
   g.stats_in = ln.stats_in; g.shift_in = ln.shift_in; g.shift_out = ln.shift_out; g.stats_in_row_stride = ln.in_stride;
   g.A = A; g.B = B; g.lda = K; g.ldb = K; g.M = M; g.N = N; g.K = K; g.f16 = f16;
+  g.A2 = ln.A2; g.B2 = ln.B2; g.K2 = ln.K2; g.lda2 = ln.lda2; g.ldb2 = ln.ldb2;
   g.bias = bias; g.epilogue = epi; g.out = out; g.ldo = ldo;
   // algorithmic bytes: A + B read once, C written once (read-modify-write for the residual epilogue)
   const bool lnprep = epi == EPI_RESID_LNPREP_SHORT || epi == EPI_RESID_LNPREP_LONG;
   const double out_b = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_LNFOLD_BF16 || epi == EPI_LNFOLD_GELU_BF16)
                            ? 2.0 : (epi == EPI_BIAS_RESID_F32 ? 8.0 : (lnprep ? 10.0 : 4.0));
-  const double bytes = 2.0 * M * K + 2.0 * N * K + out_b * M * N;
-  LAUNCH_P(ctx, cls, 2.0 * M * N * K, bytes, launch_gemm(g, ctx->dev_status, ctx->num_sms, ctx->stream));
+  const double bytes = 2.0 * M * (K + ln.K2) + 2.0 * N * (K + ln.K2) + out_b * M * N;
+  LAUNCH_P(ctx, cls, 2.0 * M * N * (K + ln.K2), bytes, launch_gemm(g, ctx->dev_status, ctx->num_sms, ctx->stream));
   return JCB_OK;
 }
 
@@ -449,12 +469,30 @@ int tower_blocks(TowerBase* t, int64_t n, const TowerWs& w, int causal, bool cls
     }
     return JCB_OK;
   }
+  // LoRA applied (jcb_ctx_set_lora_mode; the form the reference evaluates, test.py:388-398: W x + b + s B (A x)):
+  // U = x [A_q; A_k; A_v]^T as one narrow GEMM, then the projection GEMM accumulates U (s B)^T into the same TMEM
+  // tile through its second operand pair -- the base weights stay un-merged, an adapter swap re-packs 2 x r rows.
+  auto lora_pair = [&](const __nv_bfloat16* x, const __nv_bfloat16* dn, const __nv_bfloat16* up, LnArgs* a) -> int {
+    if (!dn) return JCB_OK;
+    int rc2 = run_gemm(ctx, JCB_KC_GEMM_LORA, f16, x, dn, M, LORA_U_COLS, W, nullptr, EPI_BIAS_BF16, w.lora_u, LORA_U_COLS);
+    if (rc2) return rc2;
+    a->A2 = w.lora_u; a->B2 = up; a->K2 = LORA_K2; a->lda2 = LORA_U_COLS; a->ldb2 = LORA_K2;
+    return JCB_OK;
+  };
   for (int l = 0; l < t->L; ++l) {
     const LayerDev& L = t->layers[l];
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, f16, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W))) return rc;
+    {
+      LnArgs a;
+      if ((rc = lora_pair(w.ln_out, L.lin_dn, L.lin_up, &a))) return rc;
+      if ((rc = run_gemm(ctx, JCB_KC_GEMM_QKV, f16, w.ln_out, L.in_w, M, 3 * W, W, L.in_b, EPI_BIAS_BF16, w.qkv, 3 * W, a))) return rc;
+    }
     LAUNCH_P(ctx, JCB_KC_ATTENTION, 4.0 * n * t->heads * T * T * 64, MW * (6 + 2),
              launch_attention(w.qkv, n, T, t->heads, w.attn, s, causal, ctx->dev_status, ctx->num_sms, f16));
-    if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, f16, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
+    {
+      LnArgs a;
+      if ((rc = lora_pair(w.attn, L.lout_dn, L.lout_up, &a))) return rc;
+      if ((rc = run_gemm(ctx, JCB_KC_GEMM_OUT, f16, w.attn, L.out_w, M, W, W, L.out_b, EPI_BIAS_RESID_F32, w.tokens, W, a))) return rc;
+    }
     LAUNCH_P(ctx, JCB_KC_LAYERNORM, 0, MW * (4 + 2), launch_layernorm(w.tokens, M, W, L.ln2_g, L.ln2_b, w.ln_out, s, f16));
     if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC1, f16, w.ln_out, L.fc_w, M, 4 * W, W, L.fc_b, EPI_BIAS_GELU_BF16, w.big, 4 * W))) return rc;
     if ((rc = run_gemm(ctx, JCB_KC_GEMM_FC2, f16, w.big, L.proj_w, M, W, 4 * W, L.proj_b, EPI_BIAS_RESID_F32, w.tokens, W))) return rc;
@@ -606,6 +644,8 @@ int jcb_ctx_create(int device, jcb_ctx** out) {
     ctx->cls_only_last = (env_cls && env_cls[0] == '1') ? 1 : 0;
     const char* env_op = getenv("JCB_OPERANDS");   // "bf16" | "f16" (default): see jcb_ctx_set_operand_type
     ctx->operand_f16 = (env_op && (env_op[0] == 'b' || env_op[0] == 'B')) ? 0 : 1;
+    const char* env_lm = getenv("JCB_LORA");       // "applied" | "merged" (default): see jcb_ctx_set_lora_mode
+    ctx->lora_applied = (env_lm && (env_lm[0] == 'a' || env_lm[0] == 'A')) ? 1 : 0;
     const char* env_g = getenv("JCB_GRAPHS");
     ctx->graphs_on = (env_g && env_g[0] == '0') ? 0 : 1;
     const char* env = getenv("JCB_LN_FOLD");
@@ -707,6 +747,20 @@ int jcb_ctx_set_operand_type(jcb_ctx* ctx, int operand_type) {
 
 int jcb_ctx_get_operand_type(const jcb_ctx* ctx) { return ctx ? (ctx->operand_f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
 
+int jcb_ctx_set_lora_mode(jcb_ctx* ctx, int mode) {
+  if (!ctx) return JCB_E_INVALID;
+  if (mode != JCB_LORA_MERGED && mode != JCB_LORA_APPLIED)
+    return fail(ctx, JCB_E_INVALID, "lora mode must be JCB_LORA_MERGED (0) or JCB_LORA_APPLIED (1)");
+  ctx->lora_applied = mode == JCB_LORA_APPLIED ? 1 : 0;
+  return JCB_OK;
+}
+
+int jcb_ctx_get_lora_mode(const jcb_ctx* ctx) { return ctx ? (ctx->lora_applied ? JCB_LORA_APPLIED : JCB_LORA_MERGED) : JCB_E_INVALID; }
+
+int jcb_vit_lora_mode(const jcb_vit* v) { return v ? (v->lora_applied ? JCB_LORA_APPLIED : JCB_LORA_MERGED) : JCB_E_INVALID; }
+
+int jcb_text_lora_mode(const jcb_text* t) { return t ? (t->lora_applied ? JCB_LORA_APPLIED : JCB_LORA_MERGED) : JCB_E_INVALID; }
+
 int jcb_vit_operand_type(const jcb_vit* v) { return v ? (v->f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
 
 int jcb_text_operand_type(const jcb_text* t) { return t ? (t->f16 ? JCB_OPERAND_F16 : JCB_OPERAND_BF16) : JCB_E_INVALID; }
@@ -797,7 +851,8 @@ int jcb_ctx_profile_read(const jcb_ctx* ctx, int kernel_class, double* total_ms,
 
 const char* jcb_kernel_class_name(int kernel_class) {
   static const char* names[JCB_KC_COUNT] = {"im2col", "gemm_patch", "embed_ln", "gemm_qkv", "attention", "gemm_out",
-                                            "layernorm", "gemm_fc1", "gemm_fc2", "tail", "mta", "head", "other", "tta_views"};
+                                            "layernorm", "gemm_fc1", "gemm_fc2", "tail", "mta", "head", "other", "tta_views",
+                                            "gemm_lora"};
   return kernel_class >= 0 && kernel_class < JCB_KC_COUNT ? names[kernel_class] : "?";
 }
 
@@ -874,6 +929,7 @@ struct Packer {
   int begin(size_t arena_bytes, size_t max_tensor_elems) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     t->f16 = ctx->operand_f16;   // the tower keeps the operand type it was packed with until the next finalize
+    t->lora_applied = ctx->lora_applied;
     ++t->gen;
     if (!t->arena || t->arena_bytes < arena_bytes) {
       if (t->arena) cudaFree(t->arena);
@@ -941,9 +997,43 @@ struct Packer {
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return JCB_OK;
   }
+  // LoRA applied: the adapters of one projection GEMM side by side (see LayerDev).  `adapters` = (row offset of the
+  // projection inside the packed weight, adapter); rows = rows of the packed weight.  s is folded into the up matrix.
+  int up_lora_applied(const std::vector<std::pair<size_t, const LoraAdapter*>>& adapters, size_t rows,
+                      __nv_bfloat16** dn, __nv_bfloat16** up) {
+    *dn = *up = nullptr;
+    if (adapters.empty()) return JCB_OK;
+    cudaStream_t s = ctx->stream;
+    const size_t W = t->W;
+    int r_total = 0;
+    for (auto& ad : adapters) r_total += ad.second->r;
+    if (r_total > LORA_K2)
+      return fail(ctx, JCB_E_INVALID, "LoRA applied: the ranks of one projection GEMM sum to %d (max %d); use JCB_LORA_MERGED",
+                  r_total, LORA_K2);
+    std::vector<float> hd(static_cast<size_t>(LORA_U_COLS) * W, 0.f), hu(rows * LORA_K2, 0.f);
+    int j0 = 0;
+    for (auto& ad : adapters) {
+      const LoraAdapter* a = ad.second;
+      for (int j = 0; j < a->r; ++j) std::copy(a->A.begin() + j * W, a->A.begin() + (j + 1) * W, hd.begin() + (j0 + j) * W);
+      for (size_t n = 0; n < W; ++n)
+        for (int j = 0; j < a->r; ++j) hu[(ad.first + n) * LORA_K2 + j0 + j] = a->scaling * a->B[n * a->r + j];
+      j0 += a->r;
+    }
+    *dn = b.take<__nv_bfloat16>(hd.size());
+    *up = b.take<__nv_bfloat16>(hu.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(tmp_w, hd.data(), hd.size() * 4, cudaMemcpyHostToDevice, s));
+    LAUNCH(ctx, launch_cast_bf16(tmp_w, *dn, static_cast<int64_t>(hd.size()), s, t->f16));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));   // hd / tmp_w are reused
+    CUDA_TRY(ctx, cudaMemcpyAsync(tmp_w, hu.data(), hu.size() * 4, cudaMemcpyHostToDevice, s));
+    LAUNCH(ctx, launch_cast_bf16(tmp_w, *up, static_cast<int64_t>(hu.size()), s, t->f16));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return JCB_OK;
+  }
   int pack_blocks() {
     const size_t W = t->W;
     t->layers.assign(t->L, LayerDev());
+    const bool applied = t->lora_applied != 0;
+    const std::vector<std::pair<size_t, const LoraAdapter*>> none;
     int rc;
     for (int li = 0; li < t->L; ++li) {
       LayerDev& Ld = t->layers[li];
@@ -954,8 +1044,12 @@ struct Packer {
       }
       auto ito = t->lora.find(li * 4 + JCB_PROJ_O);
       if (ito != t->lora.end()) out_ad.push_back({0, &ito->second});
-      if ((rc = up_bf16(blk(t, li, "attn.in_proj_weight"), 3 * W, W, &Ld.in_w, in_ad))) return rc;
-      if ((rc = up_bf16(blk(t, li, "attn.out_proj.weight"), W, W, &Ld.out_w, out_ad))) return rc;
+      if ((rc = up_bf16(blk(t, li, "attn.in_proj_weight"), 3 * W, W, &Ld.in_w, applied ? none : in_ad))) return rc;
+      if ((rc = up_bf16(blk(t, li, "attn.out_proj.weight"), W, W, &Ld.out_w, applied ? none : out_ad))) return rc;
+      if (applied) {
+        if ((rc = up_lora_applied(in_ad, 3 * W, &Ld.lin_dn, &Ld.lin_up))) return rc;
+        if ((rc = up_lora_applied(out_ad, W, &Ld.lout_dn, &Ld.lout_up))) return rc;
+      }
       if ((rc = up_bf16(blk(t, li, "mlp.c_fc.weight"), 4 * W, W, &Ld.fc_w, {}))) return rc;
       if ((rc = up_bf16(blk(t, li, "mlp.c_proj.weight"), W, 4 * W, &Ld.proj_w, {}))) return rc;
       if ((rc = up_f32(blk(t, li, "attn.in_proj_bias"), &Ld.in_b))) return rc;
@@ -966,7 +1060,7 @@ struct Packer {
       if ((rc = up_f32(blk(t, li, "ln_1.bias"), &Ld.ln1_b))) return rc;
       if ((rc = up_f32(blk(t, li, "ln_2.weight"), &Ld.ln2_g))) return rc;
       if ((rc = up_f32(blk(t, li, "ln_2.bias"), &Ld.ln2_b))) return rc;
-      if (ctx->ln_fold) {
+      if (ctx->ln_fold && !applied) {   // LoRA applied runs the stand-alone LayerNorm schedule (tower_blocks)
         if ((rc = up_folded(blk(t, li, "attn.in_proj_weight"), 3 * W, W, in_ad, Ld.ln1_g, Ld.ln1_b, Ld.in_b, &Ld.in_wf,
                             &Ld.in_S, &Ld.in_c))) return rc;
         if ((rc = up_folded(blk(t, li, "mlp.c_fc.weight"), 4 * W, W, {}, Ld.ln2_g, Ld.ln2_b, Ld.fc_b, &Ld.fc_wf, &Ld.fc_S,
@@ -985,8 +1079,10 @@ struct Packer {
 
 size_t blocks_arena_bytes(size_t W, size_t L) {
   // packed weights + biases / LayerNorm vectors, plus the LayerNorm-folded copies of in_proj / c_fc (Wf, S, c)
+  // (LoRA applied: the down / up matrices of in_proj and out_proj; the folded copies are not packed then)
   return L * (align_up(3 * W * W * 2) + align_up(W * W * 2) + 2 * align_up(4 * W * W * 2) + 8 * align_up(4 * W * 4) +
-              align_up(3 * W * W * 2) + align_up(4 * W * W * 2) + 4 * align_up(4 * W * 4));
+              align_up(3 * W * W * 2) + align_up(4 * W * W * 2) + 4 * align_up(4 * W * 4) +
+              2 * align_up(LORA_U_COLS * W * 2) + align_up(3 * W * LORA_K2 * 2) + align_up(W * LORA_K2 * 2));
 }
 
 int tower_set_param(TowerBase* t, const char* name, const float* data, int64_t numel) {
@@ -1681,6 +1777,10 @@ int jcb_gemm(jcb_ctx* ctx, const jcb_gemm_args* g) {
   ln.stats = g->stats_dev; ln.slots = g->stats_slots; ln.colsum = g->colsum_dev; ln.out2 = g->out2_dev;
   ln.stats_in = g->stats_in_dev; ln.shift_in = g->shift_in_dev; ln.shift_out = g->shift_out_dev;
   ln.in_stride = g->stats_in_row_stride > 0 ? g->stats_in_row_stride : 1;
+  if (g->K2 > 0) {
+    ln.A2 = static_cast<const __nv_bfloat16*>(g->A2_dev); ln.B2 = static_cast<const __nv_bfloat16*>(g->B2_dev);
+    ln.K2 = g->K2; ln.lda2 = g->lda2 > 0 ? g->lda2 : g->K2; ln.ldb2 = g->ldb2 > 0 ? g->ldb2 : g->K2;
+  }
   return run_gemm(ctx, JCB_KC_OTHER, g->operand_type == JCB_OPERAND_F16, static_cast<const __nv_bfloat16*>(g->A_dev),
                   static_cast<const __nv_bfloat16*>(g->B_dev), g->M, g->N, g->K, g->bias_dev, g->epilogue, g->out_dev, g->ldo, ln);
 }

@@ -109,6 +109,7 @@ struct TileCfg {
 
 struct GemmDev {
   int M, N, K;
+  int K2;                // k extent of the SECOND operand pair (tmA2 / tmB2) accumulated into the same tile; 0 = none
   const float* bias;
   void* out;
   long long ldo;
@@ -135,7 +136,8 @@ constexpr int TRACE_TILES = 96;
 
 template <int BN, int EPI, int CTAS, bool F16>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                                          const CUtensorMap& tmOut2, const GemmDev& p) {
+                                          const CUtensorMap& tmOut2, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                                          const GemmDev& p) {
   using Cfg = TileCfg<BN, CTAS, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GROUP = Cfg::GROUP;
@@ -171,11 +173,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   const int n_tiles = p.N / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = p.K / BLOCK_K;
+  // C = A B^T + A2 B2^T: the k-blocks of the second operand pair (LoRA applied: A2 = x A_lora^T, B2 = s B_lora) follow
+  // the first pair's through the same ring into the same TMEM accumulator
+  const int num_kb1 = p.K / BLOCK_K;
+  const int num_kb = num_kb1 + p.K2 / BLOCK_K;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.K2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
     tma_prefetch_desc(&tmOut);
     if (is_lnprep(EPI)) {
       tma_prefetch_desc(&tmOut2);
@@ -223,16 +232,20 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           if (kb == num_kb - 1) JCB_TRACE(6);
           uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          const bool second = kb >= num_kb1;
+          const CUtensorMap* ta = second ? &tmA2 : &tmA;
+          const CUtensorMap* tb = second ? &tmB2 : &tmB;
+          const int k0 = (second ? kb - num_kb1 : kb) * BLOCK_K;
           if (PAIR) {
             // the leader's barrier collects the bytes of BOTH CTAs; a complete_tx that lands before the
             // leader's expect_tx just drives the transaction count negative for a moment
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
-            tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+            tma_load_2d_pair(sa, ta, &full_bar[stage], k0, m0);
+            tma_load_2d_pair(sb, tb, &full_bar[stage], k0, n0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n0);
+            tma_load_2d(sa, ta, &full_bar[stage], k0, m0);
+            tma_load_2d(sb, tb, &full_bar[stage], k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -568,16 +581,18 @@ template <int BN, int EPI, bool F16>
 __global__ void __launch_bounds__(64 + 32 * epi_warps_of(EPI), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const GemmDev p) {
-  gemm_body<BN, EPI, 1, F16>(tmA, tmB, tmOut, tmOut2, p);
+  gemm_body<BN, EPI, 1, F16>(tmA, tmB, tmOut, tmOut2, tmA2, tmB2, p);
 }
 
 template <int BN, int EPI, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * epi_warps_of(EPI), 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                         const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                          const GemmDev p) {
-  gemm_body<BN, EPI, 2, F16>(tmA, tmB, tmOut, tmOut2, p);
+  gemm_body<BN, EPI, 2, F16>(tmA, tmB, tmOut, tmOut2, tmA2, tmB2, p);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
@@ -652,13 +667,18 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
     if (!make_tmap_2d(&tmOut2, op_dt, a.out2, a.M, a.N, a.ldo2, 32, 64)) return cudaErrorInvalidValue;
   }
   if (is_lnfold(EPI) && (!a.stats || !a.colsum || a.stats_slots < 1)) return cudaErrorInvalidValue;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;   // second operand pair (GemmArgs::A2): placeholders when absent
+  if (a.K2 > 0) {
+    if (!make_tmap_2d(&tmA2, op_dt, a.A2, a.M, a.K2, a.lda2, BLOCK_M, BLOCK_K)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmB2, op_dt, a.B2, a.N, a.K2, a.ldb2, Cfg::B_ROWS, BLOCK_K)) return cudaErrorInvalidValue;
+  }
   auto kern = CTAS == 2 ? gemm_tcgen05_2cta_kernel<BN, EPI, F16> : gemm_tcgen05_kernel<BN, EPI, F16>;
   {
     cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
   }
   GemmDev p;
-  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.K2 = a.K2;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.status = dev_status;
   p.stats = a.stats; p.stats_slots = a.stats_slots; p.colsum = a.colsum;
   p.stats_in = a.stats_in; p.shift_in = a.shift_in; p.shift_out = a.shift_out;
@@ -682,7 +702,7 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   const int tiles = ((a.M + tile_m - 1) / tile_m) * (a.N / BN);
   const int units = num_sms / CTAS;                       // CTAs or CTA pairs that fit the chip
   const int grid = (tiles < units ? tiles : units) * CTAS;
-  kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, p);
+  kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, tmA2, tmB2, p);
   if (trace_path) {   // debug only: synchronous dump of CTA 0's role timeline (cycles relative to its first stamp)
     std::vector<long long> h(TRACE_TILES * 8);
     cudaStreamSynchronize(stream);
@@ -752,6 +772,10 @@ cudaError_t launch_gemm(const GemmArgs& a, int* dev_status, int num_sms, cudaStr
   if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.K % BLOCK_K != 0 || a.N % 128 != 0) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.lda % 8) ||
       (a.ldb % 8) || (a.ldo % 8) || (reinterpret_cast<uintptr_t>(a.out) & 15))
+    return cudaErrorInvalidValue;
+  if (a.K2 < 0 || a.K2 % BLOCK_K != 0) return cudaErrorInvalidValue;
+  if (a.K2 > 0 && (!a.A2 || !a.B2 || (reinterpret_cast<uintptr_t>(a.A2) & 15) || (reinterpret_cast<uintptr_t>(a.B2) & 15) ||
+                   (a.lda2 % 8) || (a.ldb2 % 8) || a.lda2 < a.K2 || a.ldb2 < a.K2))
     return cudaErrorInvalidValue;
   // BN = 256 whenever N allows it; 128 otherwise (only used by generic/test shapes).
   if (g_ctas == 2) {

@@ -36,6 +36,12 @@ struct GemmArgs {
   const __nv_bfloat16* B = nullptr;  // [N, K] row-major (nn.Linear weight layout), leading dimension ldb
   int64_t lda = 0, ldb = 0;
   int M = 0, N = 0, K = 0;
+  // optional second operand pair accumulated into the same output tile: C = A B^T + A2 B2^T (LoRA in applied form,
+  // test.py:388-398: A2 = x A_lora^T [M, K2], B2 = s B_lora [N, K2]); K2 % 64 == 0, 0 = none
+  const __nv_bfloat16* A2 = nullptr;
+  const __nv_bfloat16* B2 = nullptr;
+  int64_t lda2 = 0, ldb2 = 0;
+  int K2 = 0;
   const float* bias = nullptr;       // [N] or nullptr
   int epilogue = EPI_BIAS_BF16;
   void* out = nullptr;               // bf16 or fp32 according to the epilogue

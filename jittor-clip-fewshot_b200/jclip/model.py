@@ -231,8 +231,9 @@ class VisionTransformer(Module):
             h = c_void_p()
             check(ctx.lib.jcb_vit_create(ctx.handle, byref(cfg), byref(h)), ctx.handle)
             self._vit, self._ctx, self._dirty = h, ctx, True
-        if not self._dirty and ctx.lib.jcb_vit_operand_type(self._vit) != ctx.lib.jcb_ctx_get_operand_type(ctx.handle):
-            self._dirty = True      # the context's operand type changed since the weights were packed
+        if not self._dirty and (ctx.lib.jcb_vit_operand_type(self._vit) != ctx.lib.jcb_ctx_get_operand_type(ctx.handle) or
+                                ctx.lib.jcb_vit_lora_mode(self._vit) != ctx.lib.jcb_ctx_get_lora_mode(ctx.handle)):
+            self._dirty = True      # the context's operand type / LoRA mode changed since the weights were packed
         if self._dirty:
             lib = ctx.lib
             for name, p in self.named_parameters("visual."):
@@ -370,7 +371,8 @@ class CLIP(Module):
             h = c_void_p()
             check(lib.jcb_text_create(ctx.handle, byref(cfg), byref(h)), ctx.handle)
             self._text, self._text_ctx, self._text_dirty = h, ctx, True
-        if not self._text_dirty and lib.jcb_text_operand_type(self._text) != lib.jcb_ctx_get_operand_type(ctx.handle):
+        if not self._text_dirty and (lib.jcb_text_operand_type(self._text) != lib.jcb_ctx_get_operand_type(ctx.handle) or
+                                     lib.jcb_text_lora_mode(self._text) != lib.jcb_ctx_get_lora_mode(ctx.handle)):
             self._text_dirty = True
         if self._text_dirty:
             named = [("token_embedding.weight", self.token_embedding.weight), ("positional_embedding", self.positional_embedding),

@@ -58,6 +58,20 @@ class Context:
     def operand_type(self):
         return "f16" if self.lib.jcb_ctx_get_operand_type(self.handle) == _capi.OPERAND_F16 else "bf16"
 
+    def set_lora_mode(self, name):
+        """How the towers packed from now on carry their LoRA adapters: "merged" (default: W + s B A in fp32, rounded once)
+        or "applied" (y = W x + b + s B (A x) as low-rank tcgen05 GEMMs accumulated into the projection's TMEM tile, the
+        branch the reference evaluates, test.py:388-398; include/jclip_b200.h jcb_ctx_set_lora_mode).  Models re-pack lazily."""
+        try:
+            code = _capi.LORA_MODES[str(name).lower()]
+        except KeyError:
+            raise ValueError(f"lora mode must be 'merged' or 'applied', got {name!r}") from None
+        check(self.lib.jcb_ctx_set_lora_mode(self.handle, code), self.handle)
+
+    @property
+    def lora_mode(self):
+        return "applied" if self.lib.jcb_ctx_get_lora_mode(self.handle) == _capi.LORA_APPLIED else "merged"
+
     @property
     def operand_torch_dtype(self):
         return torch.float16 if self.operand_type == "f16" else torch.bfloat16

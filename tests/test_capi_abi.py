@@ -34,13 +34,13 @@ def test_library_exports_every_declared_symbol(jb):
 def test_binding_matches_header(jb):
     assert sorted(jb._capi.PROTOTYPES) == _header_functions()
     lib = jb.load_library()
-    assert lib.jcb_abi_version() == jb._capi.JCB_ABI_VERSION == 3
+    assert lib.jcb_abi_version() == jb._capi.JCB_ABI_VERSION == 4
 
 
 def test_header_is_plain_c(tmp_path):
     """extern "C", plain pointers and sizes, no C++ / torch types: the header compiles as C11."""
     c = tmp_path / "t.c"
-    c.write_text('#include "jclip_b200.h"\nint main(void){ jcb_mta_params p; (void)p; return JCB_ABI_VERSION - 3; }\n')
+    c.write_text('#include "jclip_b200.h"\nint main(void){ jcb_mta_params p; (void)p; return JCB_ABI_VERSION - 4; }\n')
     subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(c)],
                    check=True)
 
