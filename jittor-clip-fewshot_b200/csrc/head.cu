@@ -5,6 +5,9 @@
 // per-row mean); fusion test.py:1710-1736; topk test.py:1738 / :1774; ood.py:875-883.
 // In the reference every one of these runs on a [1, 403] tensor inside the per-image Python loop, with
 // a `.tolist()` host sync per image; batch semantics here are "each image = its own [1, C] call".
+#include <cstdlib>
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -71,11 +74,21 @@ __device__ void topk_block(float* score, int C, int k, int32_t* out, float* s_re
   }
 }
 
+// One image = one CTA, or one thread-block CLUSTER of HEAD_CLUSTER CTAs (launch_head decides): the five [C, D] x [D]
+// products are split over the cluster's CTAs by class -- every class is still one warp's dot product, summed in the same
+// lane order -- and land in the LEADER CTA's shared memory through distributed shared memory; the leader then normalises,
+// fuses and ranks exactly as the single CTA does.  So both forms give the same bits; the cluster form turns ~50 dependent
+// L2 round trips per warp into ~7 (one image per call, the reference's own loop: 154 -> ~35 us).
+constexpr int HEAD_CLUSTER = 8;
+
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   extern __shared__ __align__(16) float head_smem[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = static_cast<int>(cluster.block_rank()), csize = static_cast<int>(cluster.num_blocks());
   const int C = a.C, D = a.D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long img = blockIdx.x;
+  const long long img = blockIdx.x / csize;
   float* s_pt = head_smem;        // 100 * m_pt          [D]
   float* s_hand = s_pt + D;       // 100 * m_hand        [D]
   float* s_zs = s_hand + D;       // 100 * m_zs          [D]
@@ -96,6 +109,9 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     s_u2[d] = a.scale1[d] * zs + a.bias1[d];
   }
   __syncthreads();
+  // where lane 0 leaves a class's five sums: the leader CTA's score arrays (this CTA's own when there is no cluster)
+  float* r_sc = csize > 1 ? cluster.map_shared_rank(s_sc, 0) : s_sc;
+  float* r_l2 = csize > 1 ? cluster.map_shared_rank(s_l2, 0) : s_l2;
   float* lg = s_sc + SCORE_LOGITS * C;
   float* cs = s_sc + SCORE_CS * C;
   float* cs1 = s_sc + SCORE_CS1 * C;
@@ -107,7 +123,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   // sixteen 16-byte loads of a class are issued before the first FMA -- the scalar loop below kept one L2 round trip
   // per 32 columns on the critical path (0.7 ms per 128 images, profiles/r01u_bench_n1.json)
   const bool vec = D == 512 && a.vec_ok;
-  for (int c = warp; c < C; c += HEAD_WARPS) {
+  for (int c = crank * HEAD_WARPS + warp; c < C; c += HEAD_WARPS * csize) {
     const float* w = a.fc_w + static_cast<long long>(c) * D;
     const float* tp = a.T_pt + static_cast<long long>(c) * D;
     const float* th = a.T_hand + static_cast<long long>(c) * D;
@@ -148,14 +164,19 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
     z1 = warp_sum(z1); z2 = warp_sum(z2); d0 = warp_sum(d0); d1 = warp_sum(d1); d3 = warp_sum(d3);
     if (lane == 0) {
       const float b = a.fc_b[c];
-      lg[c] = z1 + b;      // logits1 (pre-normalisation)      :1715
-      s_l2[c] = z2 + b;    // logits2                          :1716
-      cs[c] = d0;          // cosine_similarity                :1729
-      cs1[c] = d1;         // cosine_similarity1               :1730
-      cs3[c] = d3;         // cosine_similarity3               :1731
+      r_sc[SCORE_LOGITS * C + c] = z1 + b;   // logits1 (pre-normalisation)      :1715
+      r_l2[c] = z2 + b;                      // logits2                          :1716
+      r_sc[SCORE_CS * C + c] = d0;           // cosine_similarity                :1729
+      r_sc[SCORE_CS1 * C + c] = d1;          // cosine_similarity1               :1730
+      r_sc[SCORE_CS3 * C + c] = d3;          // cosine_similarity3               :1731
     }
   }
-  __syncthreads();
+  if (csize > 1) {
+    cluster.sync();          // every CTA's sums are in the leader's shared memory (release / acquire at cluster scope)
+    if (crank != 0) return;  // nobody reads the other CTAs' shared memory: they may leave
+  } else {
+    __syncthreads();
+  }
   normalize_row_inplace(lg, C, s_red);                           // :1717
   normalize_row_inplace(s_l2, C, s_red);                         // :1718
   for (int c = tid; c < C; c += HEAD_THREADS) lg[c] = (lg[c] + s_l2[c]) / 2.0f;  // :1721
@@ -286,8 +307,27 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream) {
   HeadArgs b = a;
   b.vec_ok = ((reinterpret_cast<uintptr_t>(a.T_pt) | reinterpret_cast<uintptr_t>(a.T_hand) |
                reinterpret_cast<uintptr_t>(a.T_zs) | reinterpret_cast<uintptr_t>(a.fc_w)) & 15) == 0;
-  head_kernel<<<static_cast<unsigned>(a.I), HEAD_THREADS, smem, stream>>>(b);
-  return cudaGetLastError();
+  // few images: a cluster of CTAs per image (bit-identical, see head_kernel); many: the images fill the chip already.
+  // JCB_HEAD_CLUSTER=0 / 1 forces one form (tests, A/B).
+  const char* env = getenv("JCB_HEAD_CLUSTER");
+  const bool clustered = env ? env[0] == '1' : (a.I <= 512 && a.C >= 2 * HEAD_WARPS * HEAD_CLUSTER);
+  if (!clustered) {
+    head_kernel<<<static_cast<unsigned>(a.I), HEAD_THREADS, smem, stream>>>(b);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(a.I) * HEAD_CLUSTER);
+  cfg.blockDim = dim3(HEAD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = HEAD_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, head_kernel, b);
 }
 
 cudaError_t launch_cosine_topk(const float* feats, const float* text, int64_t n, int C, int D, float scale, int k,

@@ -7,6 +7,9 @@
 // test.py:310-313 (merge_BA).
 #include <algorithm>
 
+#include <cstdlib>
+#include <cooperative_groups.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -311,21 +314,35 @@ text_embed_ln_kernel(const long long* __restrict__ ids, long long rows, int T, i
 }
 
 // ------------------------------------------------------------------------------------------ tail
-constexpr int TAIL_VIEWS = 16;   // sequences per CTA: proj [W, E] is streamed from L2 once per CTA
+// ln_post(row) @ proj, L2 norm (jclip/model.py:121-124, :211-214; test.py:1706).  TAIL_VIEWS sequences per CTA so that
+// proj [W, E] is streamed from L2 once per 16 sequences; warp w owns output columns 64 w + lane and 64 w + 32 + lane.
+// The k dimension is summed as TAIL_SPLIT partial sums over consecutive k ranges, added up in range order, and the
+// squared norm as one warp-shuffle sum per 64-column slice, slices added in order -- an order that ONE CTA can follow
+// (many views: the default form) and that a CLUSTER of TAIL_SPLIT CTAs can follow as well, CTA j taking k range j:
+// partial sums travel to the CTA that owns their column slice through distributed shared memory, slice norms to every
+// CTA.  Both forms give the same bits.  The cluster form is for few views (one image x 65 views per call, the
+// reference's own loop): the 192 dependent L2 round trips of the k loop become 24 (139 -> ~25 us per call).
+constexpr int TAIL_VIEWS = 16;
 constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_SPLIT = 8;     // k ranges = warps per CTA = CTAs per cluster
 
-template <int NV, int E>
+template <int NV, int E, bool CLUSTER>
 __global__ void __launch_bounds__(TAIL_THREADS)
 tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const float* __restrict__ g,
             const float* __restrict__ b, const float* __restrict__ proj, int normalize, float* __restrict__ out,
             const int* __restrict__ row_idx) {
+  namespace cg = cooperative_groups;
   constexpr int W = NV * 128;
-  constexpr int EPT = E / TAIL_THREADS;  // outputs per thread
+  constexpr int KR = W / TAIL_SPLIT;      // k values per range
+  static_assert(E == 64 * (TAIL_THREADS / 32) && TAIL_THREADS / 32 == TAIL_SPLIT && KR % 4 == 0, "tail tiling");
   extern __shared__ __align__(16) float tail_smem[];
   float (*s_x)[W] = reinterpret_cast<float (*)[W]>(tail_smem);                                     // [TAIL_VIEWS][W]
-  float (*s_part)[TAIL_THREADS / 32] = reinterpret_cast<float (*)[TAIL_THREADS / 32]>(tail_smem + TAIL_VIEWS * W);
+  float (*s_q)[TAIL_VIEWS] = reinterpret_cast<float (*)[TAIL_VIEWS]>(tail_smem + TAIL_VIEWS * W);  // [slice][view]
+  // cluster form: partial sums of THIS CTA's column slice from every k range, [range][view][64]
+  float (*s_in)[TAIL_VIEWS][64] = reinterpret_cast<float (*)[TAIL_VIEWS][64]>(tail_smem + TAIL_VIEWS * W + TAIL_SPLIT * TAIL_VIEWS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long v0 = static_cast<long long>(blockIdx.x) * TAIL_VIEWS;
+  const int crank = CLUSTER ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+  const long long v0 = static_cast<long long>(CLUSTER ? blockIdx.x / TAIL_SPLIT : blockIdx.x) * TAIL_VIEWS;
   for (int vv = warp; vv < TAIL_VIEWS; vv += TAIL_THREADS / 32) {  // ln_post on the CLS row of view v0 + vv  (jclip/model.py:121)
     const long long view = v0 + vv;
     float4 v[NV];
@@ -345,38 +362,90 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
     for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(s_x[vv])[lane + 32 * i] = v[i];
   }
   __syncthreads();
-  float acc[TAIL_VIEWS][EPT];
+  const int col = 64 * warp + lane;       // this thread's output columns: col, col + 32
+  float tot[TAIL_VIEWS][2];
 #pragma unroll
-  for (int v = 0; v < TAIL_VIEWS; ++v)
+  for (int v = 0; v < TAIL_VIEWS; ++v) tot[v][0] = tot[v][1] = 0.f;
+  const int j0 = CLUSTER ? crank : 0, j1 = CLUSTER ? crank + 1 : TAIL_SPLIT;
+  for (int j = j0; j < j1; ++j) {   // x @ proj  (jclip/model.py:123-124), fp32: one partial sum per k range
+    float part[TAIL_VIEWS][2];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) acc[v][e] = 0.f;
-  for (int k = 0; k < W; k += 4) {  // x @ proj  (jclip/model.py:123-124), fp32; four k per step, x read as float4
-    float pw[4][EPT];
+    for (int v = 0; v < TAIL_VIEWS; ++v) part[v][0] = part[v][1] = 0.f;
+    for (int k = j * KR; k < (j + 1) * KR; k += 4) {   // four k per step, x read as float4
+      float pw[4][2];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
+      for (int kk = 0; kk < 4; ++kk) {
+        pw[kk][0] = __ldg(proj + static_cast<long long>(k + kk) * E + col);
+        pw[kk][1] = __ldg(proj + static_cast<long long>(k + kk) * E + col + 32);
+      }
 #pragma unroll
-      for (int e = 0; e < EPT; ++e)
-        pw[kk][e] = __ldg(proj + static_cast<long long>(k + kk) * E + threadIdx.x + e * TAIL_THREADS);
+      for (int v = 0; v < TAIL_VIEWS; ++v) {
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[v][k]);
 #pragma unroll
-    for (int v = 0; v < TAIL_VIEWS; ++v) {
-      const float4 xv = *reinterpret_cast<const float4*>(&s_x[v][k]);
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        acc[v][e] = fmaf(xv.x, pw[0][e], acc[v][e]);
-        acc[v][e] = fmaf(xv.y, pw[1][e], acc[v][e]);
-        acc[v][e] = fmaf(xv.z, pw[2][e], acc[v][e]);
-        acc[v][e] = fmaf(xv.w, pw[3][e], acc[v][e]);
+        for (int e = 0; e < 2; ++e) {
+          part[v][e] = fmaf(xv.x, pw[0][e], part[v][e]);
+          part[v][e] = fmaf(xv.y, pw[1][e], part[v][e]);
+          part[v][e] = fmaf(xv.z, pw[2][e], part[v][e]);
+          part[v][e] = fmaf(xv.w, pw[3][e], part[v][e]);
+        }
       }
     }
+    if (CLUSTER) {   // to the CTA that owns this warp's column slice (CTA `warp`), slot of k range j
+      float (*dst)[TAIL_VIEWS][64] = cg::this_cluster().map_shared_rank(s_in, warp);
+#pragma unroll
+      for (int v = 0; v < TAIL_VIEWS; ++v) {
+        dst[j][v][lane] = part[v][0];
+        dst[j][v][lane + 32] = part[v][1];
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < TAIL_VIEWS; ++v) {
+        tot[v][0] = __fadd_rn(tot[v][0], part[v][0]);
+        tot[v][1] = __fadd_rn(tot[v][1], part[v][1]);
+      }
+    }
+  }
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    // this CTA finishes column slice `crank`: warp w takes views w and w + 8, lane l columns l and l + 32 of the slice
+    float x[2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int v = warp + 8 * h;
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < TAIL_SPLIT; ++j) {
+        t0 = __fadd_rn(t0, s_in[j][v][lane]);
+        t1 = __fadd_rn(t1, s_in[j][v][lane + 32]);
+      }
+      x[h][0] = t0; x[h][1] = t1;
+      const float q = warp_sum(__fmaf_rn(t1, t1, __fmul_rn(t0, t0)));
+      if (lane < TAIL_SPLIT) cluster.map_shared_rank(s_q, lane)[crank][v] = q;   // the slice norm to every CTA
+    }
+    cluster.sync();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int v = warp + 8 * h;
+      const long long view = v0 + v;
+      if (view >= n_views) continue;
+      float inv = 1.0f;
+      if (normalize) {
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < TAIL_SPLIT; ++i) sq = __fadd_rn(sq, s_q[i][v]);
+        inv = 1.0f / sqrtf(sq);
+      }
+      out[view * E + 64 * crank + lane] = x[h][0] * inv;
+      out[view * E + 64 * crank + lane + 32] = x[h][1] * inv;
+    }
+    return;
   }
   // f / ||f||_2  (test.py:1706)
 #pragma unroll
   for (int v = 0; v < TAIL_VIEWS; ++v) {
-    float s = 0.f;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) s += acc[v][e] * acc[v][e];
-    s = warp_sum(s);
-    if (lane == 0) s_part[v][warp] = s;
+    const float q = warp_sum(__fmaf_rn(tot[v][1], tot[v][1], __fmul_rn(tot[v][0], tot[v][0])));
+    if (lane == 0) s_q[warp][v] = q;
   }
   __syncthreads();
 #pragma unroll
@@ -385,13 +454,13 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
     if (view >= n_views) break;
     float inv = 1.0f;
     if (normalize) {
-      float s = 0.f;
+      float sq = 0.f;
 #pragma unroll
-      for (int w = 0; w < TAIL_THREADS / 32; ++w) s += s_part[v][w];
-      inv = 1.0f / sqrtf(s);
+      for (int i = 0; i < TAIL_SPLIT; ++i) sq = __fadd_rn(sq, s_q[i][v]);
+      inv = 1.0f / sqrtf(sq);
     }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) out[view * E + threadIdx.x + e * TAIL_THREADS] = acc[v][e] * inv;
+    out[view * E + col] = tot[v][0] * inv;
+    out[view * E + col + 32] = tot[v][1] * inv;
   }
 }
 
@@ -541,16 +610,39 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
                         const float* proj, int E, int normalize, float* out, cudaStream_t stream, const int* row_idx) {
   if (W % 128 != 0 || E != 512) return cudaErrorInvalidValue;
   if (n_views == 0) return cudaSuccess;
-  const unsigned grid = static_cast<unsigned>((n_views + TAIL_VIEWS - 1) / TAIL_VIEWS);
-  const size_t smem = sizeof(float) * (static_cast<size_t>(TAIL_VIEWS) * W + TAIL_VIEWS * (TAIL_THREADS / 32));
-  {
+  const unsigned groups = static_cast<unsigned>((n_views + TAIL_VIEWS - 1) / TAIL_VIEWS);
+  // few views: a cluster of TAIL_SPLIT CTAs per 16 views, one k range each (bit-identical, see tail_kernel); many: one
+  // CTA per 16 views streams proj once.  JCB_TAIL_CLUSTER=0 / 1 forces one form (tests, A/B).
+  const char* env = getenv("JCB_TAIL_CLUSTER");
+  const bool clustered = env ? env[0] == '1' : groups * TAIL_SPLIT <= 296;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(TAIL_VIEWS) * W + TAIL_SPLIT * TAIL_VIEWS +
+                                       (clustered ? TAIL_SPLIT * TAIL_VIEWS * 64 : 0));
+  if (!clustered) {
     cudaError_t e = cudaSuccess;
-    JCB_DISPATCH_NV(W, (e = ensure_dynamic_smem(tail_kernel<NV, 512>, smem)));
+    JCB_DISPATCH_NV(W, (e = ensure_dynamic_smem(tail_kernel<NV, 512, false>, smem)));
     if (e != cudaSuccess) return e;
+    JCB_DISPATCH_NV(W, (tail_kernel<NV, 512, false><<<groups, TAIL_THREADS, smem, stream>>>(tokens, n_views, T, g, b, proj,
+                                                                                          normalize, out, row_idx)));
+    return cudaGetLastError();
   }
-  JCB_DISPATCH_NV(W, (tail_kernel<NV, 512><<<grid, TAIL_THREADS, smem, stream>>>(tokens, n_views, T, g, b, proj,
-                                                                                normalize, out, row_idx)));
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * TAIL_SPLIT);
+  cfg.blockDim = dim3(TAIL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TAIL_SPLIT;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const long long nv = n_views;
+  cudaError_t e = cudaSuccess;
+  JCB_DISPATCH_NV(W, (e = ensure_dynamic_smem(tail_kernel<NV, 512, true>, smem)));
+  if (e != cudaSuccess) return e;
+  JCB_DISPATCH_NV(W, (e = cudaLaunchKernelEx(&cfg, tail_kernel<NV, 512, true>, tokens, nv, T, g, b, proj, normalize, out, row_idx)));
+  return e;
 }
 
 cudaError_t launch_text_embed_ln(const long long* ids, int64_t n_seq, int T, int W, int vocab, const float* tok_emb,
