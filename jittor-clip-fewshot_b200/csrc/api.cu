@@ -17,6 +17,10 @@
 using namespace jcb;
 
 namespace jcb {
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("JCB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
   if (bytes <= 48 * 1024) return cudaSuccess;
   int dev = 0;

@@ -102,6 +102,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
 
   if (warp_idx == 0) {
     // ===================================================================== TMA producer
@@ -351,8 +353,7 @@ cudaError_t launch_atc(const CUtensorMap& tmQKV, const CUtensorMap& tmOut, const
   if (e != cudaSuccess) return e;
   const long long max_ctas = 2LL * num_sms;
   const unsigned grid = static_cast<unsigned>(p.n_items < max_ctas ? p.n_items : max_ctas);
-  kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(tmQKV, tmOut, p);
-  return cudaGetLastError();
+  return launch_pdl(kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, tmQKV, tmOut, p);
 }
 
 }  // namespace

@@ -214,6 +214,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_smem);
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; operands, bias, statistics
+  // and the residual stream are touched only below
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp_idx == 0) {
     // ===================================================================== TMA producer (every CTA)
@@ -702,7 +706,11 @@ cudaError_t launch_cfg(const GemmArgs& a, int* dev_status, int num_sms, cudaStre
   const int tiles = ((a.M + tile_m - 1) / tile_m) * (a.N / BN);
   const int units = num_sms / CTAS;                       // CTAs or CTA pairs that fit the chip
   const int grid = (tiles < units ? tiles : units) * CTAS;
-  kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOut2, tmA2, tmB2, p);
+  {
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(Cfg::NUM_THREADS), Cfg::SMEM_BYTES, stream, 1, tmA, tmB, tmOut, tmOut2,
+                               tmA2, tmB2, p);
+    if (e != cudaSuccess) return e;
+  }
   if (trace_path) {   // debug only: synchronous dump of CTA 0's role timeline (cycles relative to its first stamp)
     std::vector<long long> h(TRACE_TILES * 8);
     cudaStreamSynchronize(stream);

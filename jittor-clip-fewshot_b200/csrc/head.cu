@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadArgs a) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = static_cast<int>(cluster.block_rank()), csize = static_cast<int>(cluster.num_blocks());
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   const int C = a.C, D = a.D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long img = blockIdx.x / csize;
@@ -311,24 +313,11 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t stream) {
   // JCB_HEAD_CLUSTER=0 / 1 forces one form (tests, A/B).
   const char* env = getenv("JCB_HEAD_CLUSTER");
   const bool clustered = env ? env[0] == '1' : (a.I <= 512 && a.C >= 2 * HEAD_WARPS * HEAD_CLUSTER);
-  if (!clustered) {
-    head_kernel<<<static_cast<unsigned>(a.I), HEAD_THREADS, smem, stream>>>(b);
-    return cudaGetLastError();
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(a.I) * HEAD_CLUSTER);
-  cfg.blockDim = dim3(HEAD_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = HEAD_CLUSTER;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, head_kernel, b);
+  if (!clustered) return launch_pdl(head_kernel, dim3(static_cast<unsigned>(a.I)), dim3(HEAD_THREADS), smem, stream, 1, b);
+  return launch_pdl(head_kernel, dim3(static_cast<unsigned>(a.I) * HEAD_CLUSTER), dim3(HEAD_THREADS), smem, stream,
+                    HEAD_CLUSTER, b);
 }
+
 
 cudaError_t launch_cosine_topk(const float* feats, const float* text, int64_t n, int C, int D, float scale, int k,
                                int32_t* out_topk, float* out_scores, cudaStream_t stream) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <utility>
 #include <vector>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -152,6 +153,37 @@ cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
 template <class F>
 inline cudaError_t ensure_dynamic_smem(F* func, size_t bytes) {
   return ensure_dynamic_smem(reinterpret_cast<const void*>(func), bytes);
+}
+
+// Launch `kern` as a programmatic dependent of the kernel in front of it in `stream` (ptx.cuh griddep_wait): EVERY kernel
+// launched through this MUST call griddep_wait() before its first access to global memory another kernel produced or
+// still reads.  cluster_x > 1 adds a run-time cluster dimension.  JCB_PDL=0 launches them as ordinary kernels.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 struct HeadArgs {

@@ -227,6 +227,8 @@ __device__ __forceinline__ void split3(float x, uint16_t (&l)[3]) {
 // X [rows, D] fp32 -> A' [rows, 6 D] bf16, blocks (1, 1, 1, 2, 2, 3)
 __global__ void __launch_bounds__(256) mta_split_x_kernel(const float* __restrict__ X, long long rows, int D,
                                                           uint16_t* __restrict__ out) {
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= rows * D) return;
   const long long r = i / D;
@@ -239,6 +241,8 @@ __global__ void __launch_bounds__(256) mta_split_x_kernel(const float* __restric
 // T^T [D, C] fp32 (the orientation solve_mta receives) -> B' [CP, 6 D] bf16, blocks (1, 2, 3, 1, 2, 1); rows >= C zero
 __global__ void __launch_bounds__(256) mta_split_t_kernel(const float* __restrict__ Tt, int C, int CP, int D,
                                                           uint16_t* __restrict__ out) {
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= CP * D) return;
   const int d = i / CP, c = i - d * CP;          // threads along c: coalesced reads of Tt
@@ -250,6 +254,8 @@ __global__ void __launch_bounds__(256) mta_split_t_kernel(const float* __restric
 // P[r, :] = softmax(scale * L[r, 0:C]) (test.py:1411), one warp per row; L has leading dimension CP
 __global__ void __launch_bounds__(256) mta_softmax_rows_kernel(const float* __restrict__ L, long long rows, int C, int CP,
                                                                float scale, float* __restrict__ P) {
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -954,6 +960,8 @@ template <int NT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : (NT == 128 ? 4 : (NT == 64 ? 8 : 16))) mta_fast_kernel(const MtaDev a) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float mta_smem[];
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   const int V = a.V, C = a.C, D = a.D, ldA = a.ldA, ldx = a.ldx, ldp = a.ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long img = blockIdx.x;
@@ -1148,21 +1156,23 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
           split_of[n_split] = sets[s2].feats;
           a_of[n_split++] = ap;
           const long long n = rows * D;
-          mta_split_x_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(sets[s2].feats, rows, D, ap);
+          if (cudaError_t e = launch_pdl(mta_split_x_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream, 1,
+                                         sets[s2].feats, rows, D, ap)) return e;
         }
         uint16_t* bp = reinterpret_cast<uint16_t*>(w);
         w += b_b;
         float* lg = reinterpret_cast<float*>(w);
         w += l_b;
-        mta_split_t_kernel<<<(TCP_CP * D + 255) / 256, 256, 0, stream>>>(sets[s2].text, C, TCP_CP, D, bp);
+        if (cudaError_t e = launch_pdl(mta_split_t_kernel, dim3((TCP_CP * D + 255) / 256), dim3(256), 0, stream, 1, sets[s2].text, C,
+                                       TCP_CP, D, bp)) return e;
         GemmArgs g;
         g.A = reinterpret_cast<const __nv_bfloat16*>(ap); g.B = reinterpret_cast<const __nv_bfloat16*>(bp);
         g.lda = 6 * D; g.ldb = 6 * D; g.M = static_cast<int>(rows); g.N = TCP_CP; g.K = 6 * D;
         g.bias = nullptr; g.epilogue = EPI_F32; g.out = lg; g.ldo = TCP_CP; g.f16 = 0;
         cudaError_t e = launch_gemm(g, dev_status, num_sms, stream);
         if (e != cudaSuccess) return e;
-        mta_softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
-            lg, rows, C, TCP_CP, 100.0f / p.temperature, scratch + static_cast<long long>(s2) * rows * C);
+        if ((e = launch_pdl(mta_softmax_rows_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream, 1, lg, rows, C,
+                            TCP_CP, 100.0f / p.temperature, scratch + static_cast<long long>(s2) * rows * C)) != cudaSuccess) return e;
       }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
@@ -1225,20 +1235,20 @@ cudaError_t launch_mta(const MtaSet* sets, int n_sets, int64_t I, int V, int C, 
       cudaError_t e = cudaSuccess;
       if (nt == 32) {
         if ((e = ensure_dynamic_smem(mta_fast_kernel<32>, fsmem)) != cudaSuccess) return e;
-        mta_fast_kernel<32><<<fgrid, 32, fsmem, stream>>>(a);
+        if ((e = launch_pdl(mta_fast_kernel<32>, fgrid, dim3(32), fsmem, stream, 1, a)) != cudaSuccess) return e;
       } else if (nt == 64) {
         if ((e = ensure_dynamic_smem(mta_fast_kernel<64>, fsmem)) != cudaSuccess) return e;
-        mta_fast_kernel<64><<<fgrid, 64, fsmem, stream>>>(a);
+        if ((e = launch_pdl(mta_fast_kernel<64>, fgrid, dim3(64), fsmem, stream, 1, a)) != cudaSuccess) return e;
       } else {
         if ((e = ensure_dynamic_smem(mta_fast_kernel<128>, fsmem)) != cudaSuccess) return e;
-        mta_fast_kernel<128><<<fgrid, 128, fsmem, stream>>>(a);
+        if ((e = launch_pdl(mta_fast_kernel<128>, fgrid, dim3(128), fsmem, stream, 1, a)) != cudaSuccess) return e;
       }
     } else {
       // (A/B this round: the same solver with 128 threads per CTA takes 2.3x as long per bank -- 3.25 vs 1.61 ms per step
       // un-grouped -- so running the banks of a CTA concurrently on 128-thread groups would gain < 25 % of the iterations)
       cudaError_t e = ensure_dynamic_smem(mta_fast_kernel<MF_THREADS>, MTA_SMEM_LIMIT);
       if (e != cudaSuccess) return e;
-      mta_fast_kernel<MF_THREADS><<<fgrid, MF_THREADS, fsmem, stream>>>(a);
+      if ((e = launch_pdl(mta_fast_kernel<MF_THREADS>, fgrid, dim3(MF_THREADS), fsmem, stream, 1, a)) != cudaSuccess) return e;
     }
     return cudaGetLastError();
   }

@@ -296,6 +296,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (kernels.h launch_pdl) may become resident
+// while the kernel in front of it in the stream is still running: everything up to griddep_wait() -- barrier
+// initialisation, TMEM allocation, tensor-map prefetch, the cluster's first synchronisation -- overlaps that kernel's
+// tail, and the launch latency itself disappears from the chain (~70 dependent kernels per pipeline call).
+// griddep_wait() returns once ALL prerequisite grids have completed and their memory is visible; nothing that another
+// kernel wrote may be read, and nothing it may still read may be written, before it.  Both are no-ops in a kernel
+// launched without the attribute / without a dependent.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

@@ -39,6 +39,8 @@ template <int DT, bool F16>
 __global__ void __launch_bounds__(384)
 im2col_kernel(const void* __restrict__ images, unsigned n_patches, int R, int P, int G, int apply_norm,
               __nv_bfloat16* __restrict__ patches) {
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   constexpr int EPT = 8;   // 8 pixels per thread for every input type: one fully coalesced 16-byte store per lane
   const int K = 3 * P * P;
   const int col = static_cast<int>(threadIdx.x) * EPT;  // (c, i, j) with j % EPT == 0
@@ -213,6 +215,8 @@ embed_ln_kernel(float* __restrict__ tokens, long long rows, int T, const float* 
                 const float* __restrict__ g1, const float* __restrict__ b1, __nv_bfloat16* __restrict__ y,
                 float* __restrict__ stats, int stats_slots, const float* __restrict__ patch_out,
                 float* __restrict__ shift) {
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   constexpr int W = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -341,6 +345,8 @@ tail_kernel(const float* __restrict__ tokens, long long n_views, int T, const fl
   // cluster form: partial sums of THIS CTA's column slice from every k range, [range][view][64]
   float (*s_in)[TAIL_VIEWS][64] = reinterpret_cast<float (*)[TAIL_VIEWS][64]>(tail_smem + TAIL_VIEWS * W + TAIL_SPLIT * TAIL_VIEWS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  griddep_wait();               // programmatic dependent launch (ptx.cuh): nothing global is touched above
+  griddep_launch_dependents();
   const int crank = CLUSTER ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
   const long long v0 = static_cast<long long>(CLUSTER ? blockIdx.x / TAIL_SPLIT : blockIdx.x) * TAIL_VIEWS;
   for (int vv = warp; vv < TAIL_VIEWS; vv += TAIL_THREADS / 32) {  // ln_post on the CLS row of view v0 + vv  (jclip/model.py:121)
@@ -558,9 +564,10 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
   const int64_t want = (n_patches + IM2COL_UNROLL - 1) / IM2COL_UNROLL;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * (1536 / threads) * 2));
   const unsigned np = static_cast<unsigned>(n_patches);
+  cudaError_t pdl_err = cudaSuccess;
 #define JCB_IM2COL(DT)                                                                                              \
-  if (f16) im2col_kernel<DT, true><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches); \
-  else im2col_kernel<DT, false><<<grid, threads, 0, stream>>>(images, np, resolution, patch, G, apply_norm, patches)
+  if (f16) pdl_err = launch_pdl(im2col_kernel<DT, true>, dim3(grid), dim3(threads), 0, stream, 1, images, np, resolution, patch, G, apply_norm, patches); \
+  else pdl_err = launch_pdl(im2col_kernel<DT, false>, dim3(grid), dim3(threads), 0, stream, 1, images, np, resolution, patch, G, apply_norm, patches)
   switch (img_dtype) {
     case IMG_F32: JCB_IM2COL(IMG_F32); break;
     case IMG_BF16: JCB_IM2COL(IMG_BF16); break;
@@ -568,7 +575,7 @@ cudaError_t launch_im2col(const void* images, int img_dtype, int64_t n_views, in
     default: return cudaErrorInvalidValue;
   }
 #undef JCB_IM2COL
-  return cudaGetLastError();
+  return pdl_err;
 }
 
 #define JCB_DISPATCH_NV(W, CALL)               \
@@ -600,10 +607,11 @@ cudaError_t launch_embed_ln(float* tokens, int64_t n_views, int T, int W, const 
   const long long rows = n_views * T;
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
-  JCB_DISPATCH_NV_H(W, f16, (embed_ln_kernel<NV, F16><<<grid, LN_WARPS * 32, 0, stream>>>(
-                                tokens, rows, T, cls, pos, vpt, n_vpt, g_pre, b_pre, g1, b1, y, stats, stats_slots,
-                                patch_out, shift)));
-  return cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  JCB_DISPATCH_NV_H(W, f16, (e = launch_pdl(embed_ln_kernel<NV, F16>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, 1,
+                                            tokens, rows, T, cls, pos, vpt, n_vpt, g_pre, b_pre, g1, b1, y, stats, stats_slots,
+                                            patch_out, shift)));
+  return e;
 }
 
 cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, const float* g, const float* b,
@@ -621,27 +629,17 @@ cudaError_t launch_tail(const float* tokens, int64_t n_views, int T, int W, cons
     cudaError_t e = cudaSuccess;
     JCB_DISPATCH_NV(W, (e = ensure_dynamic_smem(tail_kernel<NV, 512, false>, smem)));
     if (e != cudaSuccess) return e;
-    JCB_DISPATCH_NV(W, (tail_kernel<NV, 512, false><<<groups, TAIL_THREADS, smem, stream>>>(tokens, n_views, T, g, b, proj,
-                                                                                          normalize, out, row_idx)));
-    return cudaGetLastError();
+    const long long nv0 = n_views;
+    JCB_DISPATCH_NV(W, (e = launch_pdl(tail_kernel<NV, 512, false>, dim3(groups), dim3(TAIL_THREADS), smem, stream, 1, tokens,
+                                       nv0, T, g, b, proj, normalize, out, row_idx)));
+    return e;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(groups * TAIL_SPLIT);
-  cfg.blockDim = dim3(TAIL_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = TAIL_SPLIT;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   const long long nv = n_views;
   cudaError_t e = cudaSuccess;
   JCB_DISPATCH_NV(W, (e = ensure_dynamic_smem(tail_kernel<NV, 512, true>, smem)));
   if (e != cudaSuccess) return e;
-  JCB_DISPATCH_NV(W, (e = cudaLaunchKernelEx(&cfg, tail_kernel<NV, 512, true>, tokens, nv, T, g, b, proj, normalize, out, row_idx)));
+  JCB_DISPATCH_NV(W, (e = launch_pdl(tail_kernel<NV, 512, true>, dim3(groups * TAIL_SPLIT), dim3(TAIL_THREADS), smem, stream,
+                                     TAIL_SPLIT, tokens, nv, T, g, b, proj, normalize, out, row_idx)));
   return e;
 }
 
