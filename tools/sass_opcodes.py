@@ -5,7 +5,8 @@
 
 UTCHMMA = tcgen05.mma (.2CTA = cta_group::2), LDTM / STTM = tcgen05.ld / st (TMEM), UTMALDG / UTMASTG / UTMAREDG = TMA
 tensor load / store / reduce-add (cp.async.bulk.tensor, cp.reduce.async.bulk.tensor), UTCBAR = tcgen05.commit,
-HMMA = legacy mma.sync (the A/B baseline attention kernel only), SYNCS = mbarrier operations.
+HMMA = legacy mma.sync (the A/B baseline attention kernel only), SYNCS = mbarrier operations, ACQBULK / PREEXIT =
+griddepcontrol.wait / launch_dependents (programmatic dependent launch), UCGABAR = barrier.cluster (thread-block clusters).
 """
 import collections
 import re
@@ -13,7 +14,7 @@ import subprocess
 import sys
 
 LIB = sys.argv[1] if len(sys.argv) > 1 else "jittor-clip-fewshot_b200/libjclip_b200.so"
-OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTCBAR", "HMMA", "SYNCS", "MUFU.TANH", "MUFU.EX2"]
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTCBAR", "HMMA", "SYNCS", "MUFU.TANH", "MUFU.EX2", "ACQBULK", "PREEXIT", "UCGABAR"]
 
 
 def demangle(names):
@@ -73,6 +74,12 @@ def main():
             c["MUFU.TANH"] += 1
         elif op.startswith("MUFU.EX2"):
             c["MUFU.EX2"] += 1
+        elif op.startswith("ACQBULK"):
+            c["ACQBULK"] += 1
+        elif op.startswith("PREEXIT"):
+            c["PREEXIT"] += 1
+        elif op.startswith("UCGABAR"):
+            c["UCGABAR"] += 1
     names = demangle(list(counts))
     print(f"# SASS opcode histogram of `{LIB}` (cuobjdump -sass; architectures: {', '.join(sorted(arch))})\n")
     print("Static instruction counts per kernel; kernels without any of the listed opcodes are summarised at the end.  "
