@@ -211,6 +211,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa_cpus = jb.dist.bind_to_gpu_numa(local)     # before any pinned allocation
+    t_start = time.perf_counter()
+
+    def stage(name):
+        """Progress marker on stderr (stdout carries the one JSON line): which leg a run that hangs or is killed was in."""
+        print(f"[bench rank {rank} +{time.perf_counter() - t_start:6.1f}s] {name}", file=sys.stderr, flush=True)
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     peaks = measured_peaks()
@@ -246,6 +251,7 @@ def main():
     I_max = I if world == 1 else int(I * 1.15) + 2
     pool = make_images(I_max)
     images = pool[:I]
+    stage("problem built")
     balance = None
     if world > 1 and not args.no_balance:
         # The GPUs of one box differ by a few per cent under the power cap, and every step ends in an all-gather: with
@@ -357,6 +363,7 @@ def main():
         assert all(oks), shard_check
 
     sampler = ClockSampler(local)
+    stage("warm-up done, timed region")
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     jb.dist.barrier()
@@ -393,6 +400,7 @@ def main():
         balance["timed_ms_per_step_by_rank"] = [round(m / K, 2) for m in jb.dist.all_gather_floats(ev0.elapsed_time(ev1), dev)]
     value = n_total * K / (ms_total / 1e3)
 
+    stage("timed region done; leg: cls_only_last_block")
     # ---- informational: the opt-in schedule that runs the last block on the class-token rows only (results agree to
     #      rounding; 0.53 of the 8.82 GFLOP per view are work whose output encode_image never returns)
     cls_only = None
@@ -419,6 +427,7 @@ def main():
                     "note": "jcb_ctx_set_cls_only_last_block(1): attention / out_proj / MLP of block 12 on 1 of 50 token rows; "
                             "NOT used for value / e2e / roofline"}
 
+    stage("leg: e2e (host views)")
     # ---- end to end: pinned host images in, host top-5 out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -465,6 +474,7 @@ def main():
                "blocking_call": {"value": n_total * K / dt_block, "ms_per_step": 1e3 * dt_block / K,
                                  "api": "HotPath.evaluate_base(host_views), one blocking call per step"}}
         del host_images
+    stage("leg: e2e_from_images")
     # ---- informational: the same step fed from DECODED IMAGES: crop boxes drawn on the host, one upload of the
     #      source image per image, views generated on the GPU (TTAViews, Pillow-exact), then the hot path
     e2e_img = None
@@ -504,6 +514,7 @@ def main():
                    "note": "host: 500x375 uint8 decoded images + crop-box draw; device: Pillow-exact centre view + "
                            f"{args.crops} RandomResizedCrop(0.5-1)+flip views per image written straight into the conv1 patch "
                            "matrix on a second stream while the previous batch's towers run, then the hot path"}
+    stage("leg: single_image_call")
     # ---- informational: the reference's own call pattern, one image x (N+1) views per call (test.py:1692-1742), blocking,
     #      host top-5 out: launch-latency-bound (~200 launches per call; encoded TMA descriptors are cached per shape)
     single = None
@@ -520,6 +531,7 @@ def main():
         single = {"ms_per_call": 1e3 * dt1, "images_per_s": 1.0 / dt1, "views_per_call": V, "cuda_graphs": ctx.graph_stats(),
                   "api": "HotPath.evaluate_base(1 image x views, device-resident), host top-5 back, one blocking call per image "
                          "(served from a CUDA graph from the third call on: jcb_ctx_set_graphs)"}
+    stage("leg: other_operand_type")
     # ---- informational: the same device-resident step with the OTHER 16-bit operand type (the towers are re-packed)
     other_operands = None
     if not args.no_e2e:
@@ -544,6 +556,7 @@ def main():
         other_operands = {"operands": alt, "value": n_total / (ms_a / 1e3), "unit": UNIT, "ms_per_step": ms_a,
                           "identical_top5_sets_vs_headline_operands": float((out_a.sort(dim=1).values == out.sort(dim=1).values).all(dim=1).float().mean()),
                           "note": "same kernels, tcgen05 kind::f16 runs fp16 and bf16 operands at the same rate; NOT used for value / e2e / roofline"}
+    stage("leg: lora_applied")
     # ---- informational: the same device-resident step with the adapters APPLIED as low-rank GEMMs instead of merged
     #      (jcb_ctx_set_lora_mode; the towers are re-packed): what a caller that swaps adapters per request pays
     lora_applied = None
@@ -570,6 +583,7 @@ def main():
                         "note": "jcb_ctx_set_lora_mode(JCB_LORA_APPLIED): y = W x + b + s B (A x) (test.py:388-398) as a narrow tcgen05 GEMM "
                                 "+ a second TMA operand pair accumulated into the QKV tile, stand-alone LayerNorm schedule; "
                                 "NOT used for value / e2e / roofline (those run the default merged mode)"}
+    stage("legs done")
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     clocks = sampler.summary()

@@ -17,8 +17,12 @@
 using namespace jcb;
 
 namespace jcb {
+// Programmatic dependent launch is OPT-IN (JCB_PDL=1).  Measured with it on: one image x 65 views per call 1.43 -> 1.39 ms
+// (CUDA graphs) / 1.59 -> 1.43 (no graphs), the batched step +0.5 %, all GPU tests green on one GPU and under torchrun --
+// but bench.py on TWO ranks hung in its first full-size passes after NCCL had been initialised (profiles/r02_pdl_ab.log,
+// r02_pdl_n2_hang.log; JCB_PDL=0 in the same run: fine).  Not understood, so not the default.
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("JCB_PDL"); return !(e && e[0] == '0'); }();
+  static const bool on = [] { const char* e = getenv("JCB_PDL"); return e && e[0] == '1'; }();
   return on;
 }
 cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {

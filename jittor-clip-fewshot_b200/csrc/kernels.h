@@ -157,7 +157,8 @@ inline cudaError_t ensure_dynamic_smem(F* func, size_t bytes) {
 
 // Launch `kern` as a programmatic dependent of the kernel in front of it in `stream` (ptx.cuh griddep_wait): EVERY kernel
 // launched through this MUST call griddep_wait() before its first access to global memory another kernel produced or
-// still reads.  cluster_x > 1 adds a run-time cluster dimension.  JCB_PDL=0 launches them as ordinary kernels.
+// still reads.  cluster_x > 1 adds a run-time cluster dimension.  Opt-in: JCB_PDL=1 (see pdl_enabled in api.cu for why it
+// is not the default); otherwise these are ordinary launches and griddep_wait() is a no-op.
 bool pdl_enabled();
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

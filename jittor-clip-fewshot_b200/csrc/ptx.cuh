@@ -303,7 +303,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // tail, and the launch latency itself disappears from the chain (~70 dependent kernels per pipeline call).
 // griddep_wait() returns once ALL prerequisite grids have completed and their memory is visible; nothing that another
 // kernel wrote may be read, and nothing it may still read may be written, before it.  Both are no-ops in a kernel
-// launched without the attribute / without a dependent.
+// launched without the attribute / without a dependent.  The attribute is opt-in (JCB_PDL=1, api.cu pdl_enabled).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
