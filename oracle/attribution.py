@@ -66,17 +66,19 @@ def main():
     run = lambda encode: heads(towers(encode))
     out = {"images": I, "views": V, "text": a.text, "oracle_min_gap_5th_6th": gaps, "variants": {}}
     for var in a.variants.split(","):
-        act, wgt = var.split("/")
+        # "act/wgt" or "act/wgt/applied" (LoRA as low-rank GEMMs, stand-alone LayerNorm schedule: jcb_ctx_set_lora_mode)
+        act, wgt, *mode = var.split("/")
+        lora_mode = mode[0] if mode else "merged"
         t0 = time.time()
-        got = run(lambda x: vit_encode_image_rounded(sd, x, lora=lora, scaling=0.5, act=act, wgt=wgt))
+        got = run(lambda x: vit_encode_image_rounded(sd, x, lora=lora, scaling=0.5, act=act, wgt=wgt, lora_mode=lora_mode))
         cos = torch.nn.functional.cosine_similarity(got[0].double(), ref[0].double(), dim=-1)
         row = {"min_embedding_cosine": float(cos.min()), "max_embedding_l2": float((got[0] - ref[0]).norm(dim=-1).max())}
         for s in ("cs1", "cs5"):
             d = (got[1][s] - ref[1][s]).abs()
             row[s] = {"max_abs_logit_diff": float(d.max()), "mean_abs_logit_diff": float(d.mean()),
                       "top5_label_agreement": sum(len(x & y) for x, y in zip(got[2][s], ref[2][s])) / (5 * I)}
-        out["variants"][f"act={act},wgt={wgt}"] = row
-        print(f"act={act} wgt={wgt} ({time.time() - t0:.1f} s): {json.dumps(row)}", flush=True)
+        out["variants"][f"act={act},wgt={wgt}" + (f",lora={lora_mode}" if mode else "")] = row
+        print(f"act={act} wgt={wgt} lora={lora_mode} ({time.time() - t0:.1f} s): {json.dumps(row)}", flush=True)
     if a.out:
         with open(a.out, "w") as fh:
             json.dump(out, fh, indent=1)

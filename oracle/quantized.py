@@ -30,19 +30,26 @@ def _q(x, kind):
 
 @torch.no_grad()
 def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm=True, normalize=True,
-                             act="bf16", wgt="bf16", fold=True, centre=True, kinds=None, layer_kind=None):
+                             act="bf16", wgt="bf16", fold=True, centre=True, kinds=None, layer_kind=None,
+                             lora_mode="merged"):
     """kinds: optional per-tensor-class overrides of `act` / `wgt`, e.g. {"hidden": "bf16"}; classes: patch, conv_w,
     ln1_copy, qkv_w, qkv, p, attn, out_w, ln2_copy, fc_w, hidden, proj_w (per-class attribution of the deviation).
     layer_kind: optional callable block index -> operand type of EVERY 16-bit tensor of that block (overrides act / wgt /
     kinds inside the blocks; per-layer attribution).
     fold: LayerNorm folded into the consuming GEMM (JCB_LN_FOLD=2) instead of a rounded stand-alone LayerNorm.
     centre: the 16-bit copy of the residual row is x - shift, shift = the row's mean at the previous LayerNorm point
-    (what the EPI_RESID_LNPREP_* epilogues write since round 2); False = the round-1 raw copy."""
+    (what the EPI_RESID_LNPREP_* epilogues write since round 2); False = the round-1 raw copy.
+    lora_mode: "merged" (W + s B A in fp32, then rounded: api.cu Packer) or "applied" (jcb_ctx_set_lora_mode: base weights
+    rounded un-merged, U = x [A_q; A_k; A_v]^T rounded to 16 bits, the projection accumulates U (s B)^T with s B rounded;
+    stand-alone LayerNorm schedule, i.e. fold is ignored; test.py:388-398)."""
     x = _t(images)
     if apply_clip_norm:
         x = clip_normalize(x)
     rows = None
-    if lora:
+    applied = bool(lora) and lora_mode == "applied"
+    if applied:
+        fold = False
+    elif lora:
         sd = merge_lora_into_state_dict(sd, lora, scaling)    # fp32 merge, then rounding (api.cu Packer)
     g = lambda k: _t(sd[k])
     conv_w = g("visual.conv1.weight")
@@ -95,14 +102,28 @@ def vit_encode_image_rounded(sd, images, lora=None, scaling=0.5, apply_clip_norm
         else:
             A, Wk = base_A, base_W
         p = f"visual.transformer.resblocks.{i}."
-        qkv = _q(ln_linear(x, g(p + "ln_1.weight"), g(p + "ln_1.bias"), g(p + "attn.in_proj_weight"),
-                           g(p + "attn.in_proj_bias"), A("ln1_copy"), Wk("qkv_w")), A("qkv"))
+        qkv = ln_linear(x, g(p + "ln_1.weight"), g(p + "ln_1.bias"), g(p + "attn.in_proj_weight"),
+                        g(p + "attn.in_proj_bias"), A("ln1_copy"), Wk("qkv_w"))
+        if applied:   # + U (s B)^T accumulated in the same fp32 tile; U = ln_1(x) A^T stored as a 16-bit operand
+            mean1, r1 = ln_stats(x)
+            u_in = _q((x - mean1) * r1 * g(p + "ln_1.weight") + g(p + "ln_1.bias"), A("ln1_copy"))
+            delta = torch.zeros_like(qkv)
+            for j, name in enumerate(("q_proj", "k_proj", "v_proj")):
+                if name in lora[i]:
+                    La, Lb = _t(lora[i][name][0]), _t(lora[i][name][1])
+                    U = _q(u_in @ _q(La, Wk("qkv_w")).t(), A("qkv"))
+                    delta[..., j * W:(j + 1) * W] = U @ _q(scaling * Lb, Wk("qkv_w")).t()
+            qkv = qkv + delta
+        qkv = _q(qkv, A("qkv"))
         q, k, v = (t.view(B, S_, H, 64).permute(0, 2, 1, 3) for t in qkv.split(W, dim=-1))
         s = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(64))
         pnum = torch.exp(s - s.max(-1, keepdim=True).values)
         o = (_q(pnum, A("p")) @ v) / pnum.sum(-1, keepdim=True)     # P rounded, row sum in fp32
         o = _q(o.permute(0, 2, 1, 3).reshape(B, S_, W), A("attn"))
         x = x + o @ _q(g(p + "attn.out_proj.weight"), Wk("out_w")).t() + g(p + "attn.out_proj.bias")
+        if applied and "proj" in lora[i]:
+            La, Lb = _t(lora[i]["proj"][0]), _t(lora[i]["proj"][1])
+            x = x + _q(o @ _q(La, Wk("out_w")).t(), A("attn")) @ _q(scaling * Lb, Wk("out_w")).t()
         h = ln_linear(x, g(p + "ln_2.weight"), g(p + "ln_2.bias"), g(p + "mlp.c_fc.weight"), g(p + "mlp.c_fc.bias"),
                       A("ln2_copy"), Wk("fc_w"))
         h = _q(h * torch.sigmoid(1.702 * h), A("hidden"))
