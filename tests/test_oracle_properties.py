@@ -79,3 +79,25 @@ def test_folded_clip_normalisation_is_affine(jb):
     a = vit_encode_image(sd, img, apply_clip_norm=True)
     b = vit_encode_image(sd, jb.synth.clip_normalize(img))
     assert (a - b).abs().max() < 1e-5
+
+
+def test_quantized_restatement_without_rounding_is_the_oracle(jb):
+    """oracle/quantized.py (the tower with the GEMM operands rounded where the CUDA schedule rounds them) must be the
+    fp32 oracle when nothing is rounded -- for the folded-LayerNorm schedule, the stand-alone one, and for LoRA in
+    merged and in applied form (test.py:388-398: W x + b + s B (A x) is the same function as the merged weight)."""
+    import torch
+    from oracle import vit_encode_image
+    from oracle.quantized import vit_encode_image_rounded
+    sd = {k: torch.from_numpy(v) for k, v in jb.synth.make_vit_state_dict(seed=4, layers=2).items()}
+    lora = jb.synth.make_lora(seed=5, layers=2, params=["q", "k", "v", "o"], b_std=0.3)
+    imgs = jb.synth.make_views(3, 1, 3).reshape(3, 3, 224, 224)
+    ref = vit_encode_image(sd, imgs, lora=lora, scaling=0.5, apply_clip_norm=True, normalize=True)
+    ref0 = vit_encode_image(sd, imgs, apply_clip_norm=True, normalize=True)
+    assert (ref - ref0).abs().max() > 1e-3                      # the adapters matter
+    for kw in ({"fold": True}, {"fold": False}, {"lora_mode": "applied"}):
+        got = vit_encode_image_rounded(sd, imgs, lora=lora, scaling=0.5, act="f32", wgt="f32", **kw)
+        assert (got - ref).abs().max() <= 2e-5, kw
+    # and rounding the operands of the applied form to fp16 costs no more than it costs the merged form (x 2)
+    e_m = (vit_encode_image_rounded(sd, imgs, lora=lora, scaling=0.5, act="f16", wgt="f16") - ref).abs().max()
+    e_a = (vit_encode_image_rounded(sd, imgs, lora=lora, scaling=0.5, act="f16", wgt="f16", lora_mode="applied") - ref).abs().max()
+    assert e_a <= 2 * e_m + 1e-5 and e_a <= 2e-3
