@@ -265,6 +265,7 @@ def main():
             for _ in range(3):
                 hp.evaluate_base(images, topk_to_host=False)
             torch.cuda.synchronize()
+            stage(f"calibration round {_round}: 3 untimed passes done")
             jb.dist.barrier()
             c0.record()
             for _ in range(5):
@@ -272,6 +273,7 @@ def main():
             c1.record()
             torch.cuda.synchronize()
             ms_all = jb.dist.all_gather_floats(c0.elapsed_time(c1) / 5, dev)
+            stage(f"calibration round {_round}: timed, exchanged")
             rounds.append({"shard_images": list(sizes), "ms_per_step_by_rank": [round(m, 2) for m in ms_all]})
             new_sizes = jb.dist.balanced_shard_sizes(n_total, [m / max(n, 1) for m, n in zip(ms_all, sizes)])
             if max(new_sizes) <= I_max:

@@ -18,9 +18,12 @@ using namespace jcb;
 
 namespace jcb {
 // Programmatic dependent launch is OPT-IN (JCB_PDL=1).  Measured with it on: one image x 65 views per call 1.43 -> 1.39 ms
-// (CUDA graphs) / 1.59 -> 1.43 (no graphs), the batched step +0.5 %, all GPU tests green on one GPU and under torchrun --
-// but bench.py on TWO ranks hung in its first full-size passes after NCCL had been initialised (profiles/r02_pdl_ab.log,
-// r02_pdl_n2_hang.log; JCB_PDL=0 in the same run: fine).  Not understood, so not the default.
+// (CUDA graphs) / 1.59 -> 1.43 (no graphs), the batched step +0.5 %, all GPU tests green.  But two FULL-SIZE pipeline calls
+// that are adjacent in the stream (call k's head kernel directly followed by call k + 1's im2col, both programmatic
+// launches, while call k is still running) never finish: reproduced on one GPU without NCCL by
+// tools/pdl_first_calls_probe.py (profiles/r02_pdl_hang_probes.log); any foreign kernel between the calls (bench.py's
+// own steps have one), a host synchronisation, small calls, or either form of the head kernel make no difference / avoid
+// it.  Inside a call every adjacency works.  Not understood in the GPU time that was left, so not the default.
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("JCB_PDL"); return e && e[0] == '1'; }();
   return on;
