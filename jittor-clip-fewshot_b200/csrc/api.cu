@@ -17,13 +17,13 @@
 using namespace jcb;
 
 namespace jcb {
-// Programmatic dependent launch is OPT-IN (JCB_PDL=1).  Measured with it on: one image x 65 views per call 1.43 -> 1.39 ms
-// (CUDA graphs) / 1.59 -> 1.43 (no graphs), the batched step +0.5 %, all GPU tests green.  But two FULL-SIZE pipeline calls
-// that are adjacent in the stream (call k's head kernel directly followed by call k + 1's im2col, both programmatic
-// launches, while call k is still running) never finish: reproduced on one GPU without NCCL by
-// tools/pdl_first_calls_probe.py (profiles/r02_pdl_hang_probes.log); any foreign kernel between the calls (bench.py's
-// own steps have one), a host synchronisation, small calls, or either form of the head kernel make no difference / avoid
-// it.  Inside a call every adjacency works.  Not understood in the GPU time that was left, so not the default.
+// Programmatic dependent launch is OPT-IN (JCB_PDL=1).  Measured with it on AND the explicit early trigger
+// (griddepcontrol.launch_dependents right after the wait, now only with -DJCB_PDL_EARLY_TRIGGER): one image x 65 views per
+// call 1.43 -> 1.39 ms (CUDA graphs) / 1.59 -> 1.43 (no graphs), the batched step +0.5 %, all GPU tests green -- but two
+// FULL-SIZE pipeline calls adjacent in the stream (call k's head kernel directly followed by call k + 1's im2col while
+// call k is still running) never finish: tools/pdl_first_calls_probe.py, profiles/r02_pdl_hang_probes.log (one GPU, no
+// NCCL).  Without the early trigger (the shipped build: dependents are released by the exit of the primary's CTAs) the same
+// probe finishes; that form was checked by the probe and a test subset only, hence still not the default.
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("JCB_PDL"); return e && e[0] == '1'; }();
   return on;

@@ -305,7 +305,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // kernel wrote may be read, and nothing it may still read may be written, before it.  Both are no-ops in a kernel
 // launched without the attribute / without a dependent.  The attribute is opt-in (JCB_PDL=1, api.cu pdl_enabled).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The explicit early trigger is compiled in only with -DJCB_PDL_EARLY_TRIGGER: with it, two full-size pipeline calls adjacent
+// in a stream hang (tools/pdl_first_calls_probe.py, profiles/r02_pdl_hang_probes.log); without it the dependents are released
+// by the exit of the primary's CTAs -- the same probe finishes (0.55 s) -- and still overlap their prologue with its last wave.
+__device__ __forceinline__ void griddep_launch_dependents() {
+#ifdef JCB_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
